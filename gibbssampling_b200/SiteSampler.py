@@ -1,0 +1,194 @@
+"""SiteSampler -- the reference module's functions (fs:298-707) behind the CUDA library.
+
+Same names, argument order and result shapes as /root/reference/GibbsSampling/GibbsSampling.fs:
+every function returns `(float*int)[]` as a list of (log2 score, start position) tuples. The
+keyword-only arguments are the documented ADDITIONS at the boundary: the
+reference seeds System.Random() from the clock, so reproducible runs need `seed` (Philox stream
+`(seed, chain)`) or an injected stream of `uniforms`; `engine` lets callers keep the sequences
+resident in HBM between calls.
+
+All arithmetic runs in libgibbs_b200.so on the GPU. There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from .CompositeVector import ProbabilityCompositeVector
+from .engine import GibbsEngine, make_params, symbol_code
+
+SiteArray = list  # (float*int)[]
+
+
+def _bg_of(alphabet: Sequence, pcv: ProbabilityCompositeVector) -> list[float]:
+    if alphabet is None or pcv is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "alphabet / pcv is null (ArgumentNullException)")
+    codes = {symbol_code(a) for a in alphabet}
+    missing = [ch for ch in "ACGT" if ord(ch) not in codes]
+    if missing:
+        raise _abi.GibbsUnsupportedError(
+            _abi.GIBBS_ERR_UNSUPPORTED,
+            f"alphabet lacks {missing}: windows over those bases would score 0 (fs:283-287); "
+            "the 2-bit GPU path needs A, C, G, T in the alphabet")
+    return [float(pcv[ch]) for ch in "ACGT"]
+
+
+def _engine_for(sources, engine: Optional[GibbsEngine]) -> tuple[GibbsEngine, bool]:
+    if engine is not None:
+        return engine, False
+    return GibbsEngine(sources), True
+
+
+def _to_site_array(scores: np.ndarray, sites: np.ndarray) -> SiteArray:
+    return [(float(s), int(p)) for s, p in zip(scores, sites)]
+
+
+def _split_state(startPositions) -> tuple[np.ndarray, np.ndarray]:
+    if startPositions is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "startPositions is null (ArgumentNullException)")
+    scores = np.array([float(s) for s, _ in startPositions], dtype=np.float64)
+    sites = np.array([int(p) for _, p in startPositions], dtype=np.int32)
+    return scores, sites
+
+
+def _run_phases(phase_mask: int, motifLength: int, pseudoCount: float, alphabet, sources, pcv, *, start=None,
+                seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
+                max_sweeps: int = 0) -> SiteArray:
+    bg = _bg_of(alphabet, pcv)
+    eng, own = _engine_for(sources, engine)
+    try:
+        params = make_params(motifLength, pseudoCount, len(alphabet), bg, phase_mask=phase_mask,
+                             max_sweeps=max_sweeps)
+        if start is not None:
+            scores, sites = _split_state(start)
+            eng.set_start_state(sites, scores)
+        u = None if uniforms is None else np.asarray(uniforms, dtype=np.float64).reshape(1, -1)
+        res = eng.run(params, 1, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        return _to_site_array(res.scores[0], res.sites[0])
+    finally:
+        if own:
+            eng.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's functions
+# ---------------------------------------------------------------------------------------------
+def getBestPWMSsWithBPV(motifLength: int, pseudoCount: float, alphabet, sources, pcv, positions: Sequence[int],
+                        heldOut: int, *, engine: Optional[GibbsEngine] = None) -> tuple[float, int]:
+    """fs:301-314 applied to sources.[heldOut] with the leave-one-out PPM of `positions` (fs:392-398).
+
+    The reference takes the PPM as an argument; at this boundary the PPM never leaves the GPU, so
+    the caller passes what it is built from: the other sequences' start positions.
+    """
+    bg = _bg_of(alphabet, pcv)
+    eng, own = _engine_for(sources, engine)
+    try:
+        return eng.pick_argmax(positions, heldOut, make_params(motifLength, pseudoCount, len(alphabet), bg))
+    finally:
+        if own:
+            eng.close()
+
+
+def getPWMOfRandomStartsWithBPV(motifLength, pseudoCount, alphabet, sources, pcv, **kw) -> SiteArray:
+    """fs:412-430."""
+    return _run_phases(_abi.PHASE_INIT, motifLength, pseudoCount, alphabet, sources, pcv, **kw)
+
+
+def findBestMotifWithStartPosition(motifLength, pseudoCount, alphabet, sources, pcv, startPositions, **kw) -> SiteArray:
+    """fs:381-408."""
+    return _run_phases(_abi.PHASE_GREEDY, motifLength, pseudoCount, alphabet, sources, pcv, start=startPositions, **kw)
+
+
+def getLeftShiftedBestPWMSsWithBPV(motifLength, pseudoCount, alphabet, sources, pcv, startPositions, **kw) -> SiteArray:
+    """fs:350-377."""
+    return _run_phases(_abi.PHASE_LEFT, motifLength, pseudoCount, alphabet, sources, pcv, start=startPositions, **kw)
+
+
+def getRightShiftedBestPWMSsWithBPV(motifLength, pseudoCount, alphabet, sources, pcv, startPositions, **kw) -> SiteArray:
+    """fs:318-346."""
+    return _run_phases(_abi.PHASE_RIGHT, motifLength, pseudoCount, alphabet, sources, pcv, start=startPositions, **kw)
+
+
+def doSiteSamplingWithBPV(motifLength, pseudoCount, alphabet, sources, pcv, **kw) -> SiteArray:
+    """fs:691-695: random starts |> greedy sweeps |> left shifts |> right shifts."""
+    mask = _abi.PHASE_INIT | _abi.PHASE_GREEDY | _abi.PHASE_LEFT | _abi.PHASE_RIGHT
+    return _run_phases(mask, motifLength, pseudoCount, alphabet, sources, pcv, **kw)
+
+
+def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, restart_sites: np.ndarray) -> SiteArray:
+    """The promote-or-restart loop of fs:435-459 (quirk A.6-8) over restarts that already ran.
+
+    The reference runs restarts one after another; here restart r is chain r of one kernel launch,
+    and this function replays the loop's decisions over their results in the same order, so the
+    returned array is the one the sequential loop would return.
+    """
+    acc: list = []
+    best: list = [(0.0, 0)]
+    r = 0
+    n = 0
+    while True:
+        if n > numberOfRepetitions:
+            return best
+        if acc == best:  # structural equality of (float*int)[]
+            return best
+        ia = 0.0
+        for s, _ in acc:
+            ia = ia + s
+        ib = 0.0
+        for s, _ in best:
+            ib = ib + s
+        if ia > ib:
+            best = acc if acc else best
+            acc = []
+        else:
+            acc = _to_site_array(restart_scores[r], restart_sites[r])
+            r += 1
+        n += 1
+
+
+def getMotifsWithBestInformationContentWithBPV(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, pcv, *,
+                                               seed: int = 0, chain: int = 0, uniforms=None,
+                                               engine: Optional[GibbsEngine] = None, max_sweeps: int = 0) -> SiteArray:
+    """fs:434-459. At most numberOfRepetitions + 1 restarts can run; they run as parallel chains."""
+    bg = _bg_of(alphabet, pcv)
+    eng, own = _engine_for(sources, engine)
+    try:
+        n_restarts = max(int(numberOfRepetitions) + 1, 1)
+        params = make_params(motifLength, pseudoCount, len(alphabet), bg, max_sweeps=max_sweeps)
+        u = None
+        if uniforms is not None:
+            u = np.asarray(uniforms, dtype=np.float64).reshape(n_restarts, -1)  # restart r consumes row r
+        res = eng.run(params, n_restarts, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        return replay_restart_loop(int(numberOfRepetitions), res.scores, res.sites)
+    finally:
+        if own:
+            eng.close()
+
+
+def _unsupported(name: str, where: str):
+    raise _abi.GibbsUnsupportedError(
+        _abi.GIBBS_ERR_UNSUPPORTED,
+        f"{name} ({where}) derives its background from the data (per-window drifting counts, fs:470-473); "
+        "only the fixed-background WithBPV family is built on the GPU so far (SURVEY.md section 8f, rank 1)")
+
+
+def doSiteSampling(motifLength, pseudoCount, alphabet, sources, **kw):
+    """fs:697-701 -- data-derived background: not built yet."""
+    _unsupported("doSiteSampling", "fs:697")
+
+
+def getMotifsWithBestInformationContent(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, **kw):
+    """fs:615-640 -- data-derived background: not built yet."""
+    _unsupported("getMotifsWithBestInformationContent", "fs:615")
+
+
+def doSiteSamplingWithPPM(motifLength, pseudoCount, alphabet, sources, ppM, **kw):
+    """fs:703-707 -- data-derived background: not built yet."""
+    _unsupported("doSiteSamplingWithPPM", "fs:703")
+
+
+def getBestInformationContentOfPPM(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, ppM, **kw):
+    """fs:664-689 -- data-derived background: not built yet."""
+    _unsupported("getBestInformationContentOfPPM", "fs:664")

@@ -1,0 +1,685 @@
+// gibbssampling_b200/csrc/gibbs_api.cu -- extern "C" boundary of libgibbs_b200.so (include/gibbs_b200.h).
+//
+// Host side of the drop-in: owns device memory and a stream, validates arguments the way the
+// reference's exceptions would fire, launches the sm_100a kernels. There is no
+// CPU implementation of any compute path in this file: without a CUDA device every compute entry
+// point returns GIBBS_ERR_CUDA.
+#include "../../include/gibbs_b200.h"
+#include "gibbs_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace gibbs;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int32_t fail(int32_t code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(e_ == cudaErrorMemoryAllocation ? GIBBS_ERR_NOMEM : GIBBS_ERR_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(e_));                                                           \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+} // namespace
+
+struct gibbs_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int32_t n = 0, row_words = 0, max_len = 0, min_len = 0;
+    DevBuf<uint8_t> ascii;
+    DevBuf<int64_t> off;
+    DevBuf<uint32_t> packed;
+    DevBuf<int32_t> len;
+    DevBuf<int> flags; // [0] bad symbol, [1..3] wtab range
+
+    // PWM value table, keyed by the parameters it was built for
+    DevBuf<WEnt> wtab;
+    bool wtab_valid = false;
+    double wt_pc = 0, wt_bg[4] = {0, 0, 0, 0};
+    int32_t wt_alen = 0;
+    int wt_min = 0, wt_max = 0, wt_abnormal = 0;
+
+    // primitive scratch
+    DevBuf<int32_t> prim_sites;
+    DevBuf<int32_t> prim_i32;
+    DevBuf<double> prim_f64;
+
+    // chain results
+    DevBuf<int32_t> sites;
+    DevBuf<double> hv, scores, sums;
+    DevBuf<double> uniforms;
+    DevBuf<unsigned long long> stats;
+    DevBuf<int32_t> best; // [0] best chain, [1..] counts k*4
+    int32_t run_chains = 0, run_k = 0, run_fast = 0, run_launches = 0;
+    bool run_done = false;
+    int32_t start_chains = 0; // chains covered by gibbs_set_start_state (0 = none pending)
+};
+
+namespace {
+
+int32_t set_device(const gibbs_handle *h) {
+    CUDA_TRY(cudaSetDevice(h->device));
+    return GIBBS_OK;
+}
+
+int32_t check_params(const gibbs_handle *h, const gibbs_params *p) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    if (!p) return fail(GIBBS_ERR_ARG, "null params");
+    if (h->n < 1) return fail(GIBBS_ERR_ARG, "handle holds no sequences");
+    if (p->k < 1 || p->k > GIBBS_MAX_K) return fail(GIBBS_ERR_ARG, "motif width k=%d outside 1..%d", p->k, GIBBS_MAX_K);
+    if (h->min_len < p->k)
+        return fail(GIBBS_ERR_SHORT_SEQ, "a sequence of length %d is shorter than k=%d (Array.take, fs:152)", h->min_len, p->k);
+    if (p->alphabet_size < 1) return fail(GIBBS_ERR_ARG, "alphabet_size must be >= 1");
+    if (!(p->pseudocount >= 0.0)) return fail(GIBBS_ERR_ARG, "pseudocount must be >= 0");
+    for (int b = 0; b < 4; ++b)
+        if (!(p->bg[b] > 0.0)) return fail(GIBBS_ERR_ARG, "background probability bg[%d] must be > 0", b);
+    return GIBBS_OK;
+}
+
+// (re)build W(c, b) for c = 0..n-1 when the parameters it depends on changed
+int32_t ensure_wtab(gibbs_handle *h, const gibbs_params *p, int *launches) {
+    bool same = h->wtab_valid && h->wt_pc == p->pseudocount && h->wt_alen == p->alphabet_size;
+    for (int b = 0; b < 4 && same; ++b) same = h->wt_bg[b] == p->bg[b];
+    if (same) return GIBBS_OK;
+    CUDA_TRY(h->wtab.reserve((size_t)h->n * 4));
+    const int init[3] = {INT32_MAX, INT32_MIN, 0};
+    CUDA_TRY(cudaMemcpyAsync(h->flags.p + 1, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    // normalizePPM: sum = float sourceCount + float alphabet.Length * pseudoCount (fs:257)
+    const double den = (double)(h->n - 1) + ((double)p->alphabet_size * p->pseudocount);
+    const int total = h->n * 4;
+    wtab_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(h->n, p->pseudocount, den, p->bg[0], p->bg[1], p->bg[2],
+                                                           p->bg[3], h->wtab.p, h->flags.p + 1);
+    CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    int out[3];
+    CUDA_TRY(cudaMemcpyAsync(out, h->flags.p + 1, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->wt_min = out[0];
+    h->wt_max = out[1];
+    h->wt_abnormal = out[2];
+    h->wt_pc = p->pseudocount;
+    h->wt_alen = p->alphabet_size;
+    memcpy(h->wt_bg, p->bg, sizeof h->wt_bg);
+    h->wtab_valid = true;
+    return GIBBS_OK;
+}
+
+// The fixed-point ranking pass is valid when no partial product of k table entries can leave the
+// normal float64 range (and so the int32 key cannot overflow): |k * extreme log2| < 1000.
+int fast_path_ok(const gibbs_handle *h, int k) {
+    if (h->wt_abnormal) return 0;
+    const double unit = 1.0 / (double)(1 << LG_FRAC_BITS);
+    const double lo = (double)k * (h->wt_min < 0 ? h->wt_min : 0) * unit;
+    const double hi = (double)k * (h->wt_max > 0 ? h->wt_max : 0) * unit;
+    return (lo > -1000.0 && hi < 1000.0) ? 1 : 0;
+}
+
+template <typename K>
+int32_t set_smem(K kernel, int bytes) {
+    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return GIBBS_OK;
+}
+
+#define KP_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
+int32_t launch_chain(gibbs_handle *h, const ChainArgs &a) {
+    const int kp = (a.k + 1) / 2;
+    const int smem = warp_smem_bytes(a.s.row_words);
+    switch (kp) {
+#define X(KPV)                                                                          \
+    case KPV: {                                                                         \
+        int32_t rc = set_smem(chain_kernel<KPV>, smem);                                 \
+        if (rc) return rc;                                                              \
+        chain_kernel<KPV><<<a.n_chains, 32, smem, h->stream>>>(a);                      \
+        break;                                                                          \
+    }
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
+int32_t launch_loo_counts(gibbs_handle *h, const PrimArgs &a) {
+    const int kp = (a.k + 1) / 2;
+    const int smem = warp_smem_bytes(a.s.row_words);
+    switch (kp) {
+#define X(KPV)                                                                          \
+    case KPV: {                                                                         \
+        int32_t rc = set_smem(loo_counts_kernel<KPV>, smem);                            \
+        if (rc) return rc;                                                              \
+        loo_counts_kernel<KPV><<<1, 32, smem, h->stream>>>(a);                          \
+        break;                                                                          \
+    }
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
+int32_t launch_scan(gibbs_handle *h, const PrimArgs &a, int mode) {
+    const int kp = (a.k + 1) / 2;
+    const int smem = warp_smem_bytes(a.s.row_words);
+    switch (kp) {
+#define X(KPV)                                                                          \
+    case KPV: {                                                                         \
+        int32_t rc = set_smem(scan_kernel<KPV>, smem);                                  \
+        if (rc) return rc;                                                              \
+        scan_kernel<KPV><<<1, 32, smem, h->stream>>>(a, mode);                          \
+        break;                                                                          \
+    }
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
+int32_t launch_all_counts(gibbs_handle *h, const DeviceSeqs &s, const int32_t *sites, int k, int32_t *out) {
+    const int kp = (k + 1) / 2;
+    const int smem = warp_smem_bytes(s.row_words);
+    switch (kp) {
+#define X(KPV)                                                                          \
+    case KPV: {                                                                         \
+        int32_t rc = set_smem(all_counts_kernel<KPV>, smem);                            \
+        if (rc) return rc;                                                              \
+        all_counts_kernel<KPV><<<1, 32, smem, h->stream>>>(s, sites, k, out);           \
+        break;                                                                          \
+    }
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
+DeviceSeqs dev_seqs(const gibbs_handle *h) {
+    DeviceSeqs s;
+    s.packed = h->packed.p;
+    s.len = h->len.p;
+    s.n = h->n;
+    s.row_words = h->row_words;
+    return s;
+}
+
+int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs) {
+    if (!seqs || !offsets) return fail(GIBBS_ERR_ARG, "null sequence buffer (ArgumentNullException)");
+    if (n_seqs < 1) return fail(GIBBS_ERR_ARG, "n_seqs must be >= 1");
+    int64_t max_len = 0, min_len = INT64_MAX;
+    for (int32_t i = 0; i < n_seqs; ++i) {
+        const int64_t l = offsets[i + 1] - offsets[i];
+        if (l < 0) return fail(GIBBS_ERR_ARG, "offsets must be non-decreasing");
+        if (l > max_len) max_len = l;
+        if (l < min_len) min_len = l;
+    }
+    if (max_len > GIBBS_MAX_LEN) return fail(GIBBS_ERR_ARG, "sequence longer than %d", GIBBS_MAX_LEN);
+    if (max_len < 1) return fail(GIBBS_ERR_SHORT_SEQ, "all sequences are empty");
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    const int64_t total = offsets[n_seqs] - offsets[0];
+    const int row_words = (int)(((max_len + 15) / 16 + 4 + 3) / 4 * 4);
+    if (warp_smem_bytes(row_words) > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequence too long for shared-memory staging");
+    CUDA_TRY(h->ascii.reserve((size_t)(total > 0 ? total : 1)));
+    CUDA_TRY(h->off.reserve((size_t)n_seqs + 1));
+    CUDA_TRY(h->packed.reserve((size_t)n_seqs * row_words));
+    CUDA_TRY(h->len.reserve((size_t)n_seqs));
+    CUDA_TRY(h->flags.reserve(8));
+    std::vector<int64_t> rel((size_t)n_seqs + 1);
+    for (int32_t i = 0; i <= n_seqs; ++i) rel[i] = offsets[i] - offsets[0];
+    CUDA_TRY(cudaMemcpyAsync(h->ascii.p, seqs + offsets[0], (size_t)total, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->off.p, rel.data(), rel.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->flags.p, 0, 8 * sizeof(int), h->stream));
+    const int64_t words = (int64_t)n_seqs * row_words;
+    pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, h->stream>>>(h->ascii.p, h->off.p, n_seqs, row_words, h->packed.p,
+                                                                       h->len.p, h->flags.p);
+    CUDA_TRY(cudaGetLastError());
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, h->flags.p, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream)); // also keeps `rel` alive until the copy is done
+    h->n = 0;
+    h->wtab_valid = false;
+    h->run_done = false;
+    if (bad)
+        return fail(GIBBS_ERR_SYMBOL, "symbol '%c' (0x%02x) is outside A,C,G,T (IndexOutOfRangeException analogue, fs:17)",
+                    (bad - 1) >= 32 && (bad - 1) < 127 ? (char)(bad - 1) : '?', bad - 1);
+    h->n = n_seqs;
+    h->row_words = row_words;
+    h->max_len = (int32_t)max_len;
+    h->min_len = (int32_t)min_len;
+    return GIBBS_OK;
+}
+
+int32_t stage_sites(gibbs_handle *h, const int32_t *sites, int32_t heldout, int32_t k) {
+    if (!sites) return fail(GIBBS_ERR_ARG, "null sites");
+    if (heldout < -1 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
+    // positions must address a full k-mer (getSegment, fs:149-153); lengths are validated on the device
+    // side by construction: the host keeps only min/max, so re-read lengths when ragged
+    CUDA_TRY(h->prim_sites.reserve((size_t)h->n));
+    if (h->min_len != h->max_len) {
+        std::vector<int32_t> len((size_t)h->n);
+        CUDA_TRY(cudaMemcpyAsync(len.data(), h->len.p, len.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int32_t i = 0; i < h->n; ++i)
+            if (i != heldout && sites[i] >= 0 && sites[i] + k > len[i])
+                return fail(GIBBS_ERR_ARG, "site %d of sequence %d leaves the sequence (length %d, k %d)", sites[i], i, len[i], k);
+    } else {
+        for (int32_t i = 0; i < h->n; ++i)
+            if (i != heldout && sites[i] >= 0 && sites[i] + k > h->max_len)
+                return fail(GIBBS_ERR_ARG, "site %d of sequence %d leaves the sequence (length %d, k %d)", sites[i], i, h->max_len, k);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->prim_sites.p, sites, (size_t)h->n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    return GIBBS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t gibbs_abi_version(void) { return GIBBS_ABI_VERSION; }
+
+const char *gibbs_last_error(void) { return g_err; }
+
+int32_t gibbs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t gibbs_create(const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs, int32_t device, gibbs_handle **out) {
+    if (!out) return fail(GIBBS_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(GIBBS_ERR_CUDA, "no CUDA device available (%s); libgibbs_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= ndev) return fail(GIBBS_ERR_ARG, "device %d outside 0..%d", device, ndev - 1);
+    gibbs_handle *h = new (std::nothrow) gibbs_handle();
+    if (!h) return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+    h->device = device;
+    int32_t rc = set_device(h);
+    if (!rc) {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev0);
+        if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev1);
+        if (e2 != cudaSuccess) rc = fail(GIBBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(e2));
+        h->own_stream = true;
+    }
+    if (!rc) rc = upload(h, seqs, offsets, n_seqs);
+    if (rc) {
+        gibbs_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    return upload(h, seqs, offsets, n_seqs);
+}
+
+int32_t gibbs_destroy(gibbs_handle *h) {
+    if (!h) return GIBBS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->ascii.release(); h->off.release(); h->packed.release(); h->len.release(); h->flags.release();
+    h->wtab.release(); h->prim_sites.release(); h->prim_i32.release(); h->prim_f64.release();
+    h->sites.release(); h->hv.release(); h->scores.release(); h->sums.release(); h->uniforms.release();
+    h->stats.release(); h->best.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_set_stream(gibbs_handle *h, void *cuda_stream) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    if (cuda_stream) {
+        h->stream = (cudaStream_t)cuda_stream;
+        h->own_stream = false;
+    } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return GIBBS_OK;
+}
+
+int32_t gibbs_num_sequences(const gibbs_handle *h) { return h ? h->n : 0; }
+
+int32_t gibbs_synchronize(gibbs_handle *h) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GIBBS_OK;
+}
+
+int32_t gibbs_loo_counts(gibbs_handle *h, const int32_t *sites, int32_t heldout, int32_t k, int32_t *counts_out) {
+    if (!h || !counts_out) return fail(GIBBS_ERR_ARG, "null argument");
+    if (h->n < 1) return fail(GIBBS_ERR_ARG, "handle holds no sequences");
+    if (k < 1 || k > GIBBS_MAX_K) return fail(GIBBS_ERR_ARG, "motif width k=%d outside 1..%d", k, GIBBS_MAX_K);
+    if (h->min_len < k) return fail(GIBBS_ERR_SHORT_SEQ, "a sequence of length %d is shorter than k=%d", h->min_len, k);
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    rc = stage_sites(h, sites, heldout, k);
+    if (rc) return rc;
+    CUDA_TRY(h->prim_i32.reserve(GIBBS_MAX_K * 4 + 8));
+    PrimArgs a{};
+    a.s = dev_seqs(h);
+    a.sites = h->prim_sites.p;
+    a.heldout = heldout;
+    a.k = k;
+    a.counts_out = h->prim_i32.p;
+    rc = launch_loo_counts(h, a);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(counts_out, h->prim_i32.p, (size_t)k * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GIBBS_OK;
+}
+
+static int32_t scan_common(gibbs_handle *h, const int32_t *sites, int32_t heldout, const gibbs_params *p, int mode,
+                           double *raw_out, double *log2_out, double *score_out, int32_t *site_out) {
+    int32_t rc = check_params(h, p);
+    if (rc) return rc;
+    if (heldout < 0 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
+    rc = set_device(h);
+    if (rc) return rc;
+    rc = stage_sites(h, sites, heldout, p->k);
+    if (rc) return rc;
+    rc = ensure_wtab(h, p, nullptr);
+    if (rc) return rc;
+    int32_t len_h = h->max_len;
+    if (h->min_len != h->max_len) {
+        CUDA_TRY(cudaMemcpyAsync(&len_h, h->len.p + heldout, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    const int W = len_h - p->k + 1;
+    CUDA_TRY(h->prim_f64.reserve((size_t)2 * W + 8));
+    CUDA_TRY(h->prim_i32.reserve(GIBBS_MAX_K * 4 + 8));
+    PrimArgs a{};
+    a.s = dev_seqs(h);
+    a.wtab = h->wtab.p;
+    a.sites = h->prim_sites.p;
+    a.heldout = heldout;
+    a.k = p->k;
+    a.fast_ok = fast_path_ok(h, p->k);
+    a.raw_out = h->prim_f64.p;
+    a.log2_out = h->prim_f64.p + W;
+    a.score_out = h->prim_f64.p + 2 * (size_t)W;
+    a.site_out = h->prim_i32.p;
+    rc = launch_scan(h, a, mode);
+    if (rc) return rc;
+    if (mode == 0) {
+        if (raw_out) CUDA_TRY(cudaMemcpyAsync(raw_out, a.raw_out, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (log2_out) CUDA_TRY(cudaMemcpyAsync(log2_out, a.log2_out, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        if (score_out) CUDA_TRY(cudaMemcpyAsync(score_out, a.score_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (site_out) CUDA_TRY(cudaMemcpyAsync(site_out, a.site_out, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GIBBS_OK;
+}
+
+int32_t gibbs_window_scores(gibbs_handle *h, const int32_t *sites, int32_t heldout, const gibbs_params *p, double *raw_out,
+                            double *log2_out) {
+    return scan_common(h, sites, heldout, p, 0, raw_out, log2_out, nullptr, nullptr);
+}
+
+int32_t gibbs_pick_argmax(gibbs_handle *h, const int32_t *sites, int32_t heldout, const gibbs_params *p, double *score_out,
+                          int32_t *site_out) {
+    return scan_common(h, sites, heldout, p, 1, nullptr, nullptr, score_out, site_out);
+}
+
+int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldout, const gibbs_params *p, double u,
+                            double *pwms_out, int32_t *site_out) {
+    (void)h; (void)sites; (void)heldout; (void)p; (void)u; (void)pwms_out; (void)site_out;
+    return fail(GIBBS_ERR_UNSUPPORTED, "gibbs_pick_roulette: MotifSampler kernels are not built yet");
+}
+
+int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base, uint64_t seed,
+                         int32_t rng_mode, const double *uniforms, int64_t uniforms_per_chain) {
+    int32_t rc = check_params(h, p);
+    if (rc) return rc;
+    if (n_chains < 1) return fail(GIBBS_ERR_ARG, "n_chains must be >= 1");
+    if (p->sampler != GIBBS_SITE_SAMPLER) return fail(GIBBS_ERR_UNSUPPORTED, "sampler %d: MotifSampler kernels are not built yet", p->sampler);
+    if (rng_mode != GIBBS_RNG_PHILOX && rng_mode != GIBBS_RNG_INJECTED) return fail(GIBBS_ERR_ARG, "unknown rng_mode %d", rng_mode);
+    if (rng_mode == GIBBS_RNG_INJECTED && (!uniforms || uniforms_per_chain < 0)) return fail(GIBBS_ERR_ARG, "injected uniforms missing");
+    rc = set_device(h);
+    if (rc) return rc;
+    h->run_done = false;
+    int launches = 0;
+    rc = ensure_wtab(h, p, &launches);
+    if (rc) return rc;
+    const size_t cells = (size_t)n_chains * h->n;
+    CUDA_TRY(h->sites.reserve(cells));
+    CUDA_TRY(h->hv.reserve(cells));
+    CUDA_TRY(h->scores.reserve(cells));
+    CUDA_TRY(h->sums.reserve((size_t)n_chains));
+    CUDA_TRY(h->stats.reserve(ST_NSLOTS));
+    CUDA_TRY(h->best.reserve(1 + GIBBS_MAX_K * 4));
+    CUDA_TRY(cudaMemsetAsync(h->stats.p, 0, ST_NSLOTS * sizeof(unsigned long long), h->stream));
+    ChainArgs a{};
+    a.s = dev_seqs(h);
+    a.wtab = h->wtab.p;
+    a.k = p->k;
+    a.phase_shifts = p->phase_shifts ? 1 : 0;
+    a.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 1000000;
+    a.fast_ok = fast_path_ok(h, p->k);
+    a.sampler = p->sampler;
+    a.phase_mask = p->phase_mask ? p->phase_mask
+                                 : (GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | (p->phase_shifts ? (GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT) : 0));
+    if (a.phase_mask & ~(GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT))
+        return fail(GIBBS_ERR_UNSUPPORTED, "phase_mask 0x%x: MotifSampler phases are not built yet", a.phase_mask);
+    if (!(a.phase_mask & GIBBS_PHASE_INIT) && h->start_chains != n_chains)
+        return fail(GIBBS_ERR_ARG, "phase_mask without GIBBS_PHASE_INIT needs gibbs_set_start_state for %d chains", n_chains);
+    h->start_chains = 0;
+    a.rng_mode = rng_mode;
+    a.seed = seed;
+    a.chain_id_base = chain_id_base;
+    a.uniforms = nullptr;
+    a.uniforms_per_chain = 0;
+    if (rng_mode == GIBBS_RNG_INJECTED) {
+        const size_t nu = (size_t)n_chains * (size_t)uniforms_per_chain;
+        CUDA_TRY(h->uniforms.reserve(nu > 0 ? nu : 1));
+        if (nu) CUDA_TRY(cudaMemcpyAsync(h->uniforms.p, uniforms, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        a.uniforms = h->uniforms.p;
+        a.uniforms_per_chain = uniforms_per_chain;
+    }
+    a.n_chains = n_chains;
+    a.sites = h->sites.p;
+    a.hv = h->hv.p;
+    a.scores = h->scores.p;
+    a.sums = h->sums.p;
+    a.stats = h->stats.p;
+    a.cutoff = p->cutoff;
+    memcpy(a.bg, p->bg, sizeof a.bg);
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    rc = launch_chain(h, a);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    ++launches;
+    best_chain_kernel<<<1, 32, 0, h->stream>>>(h->sums.p, n_chains, h->best.p);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+    h->run_chains = n_chains;
+    h->run_k = p->k;
+    h->run_fast = a.fast_ok;
+    h->run_launches = launches;
+    h->run_done = true;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_set_start_state(gibbs_handle *h, int32_t n_chains, const int32_t *sites, const double *scores) {
+    if (!h || !sites || !scores) return fail(GIBBS_ERR_ARG, "null argument (ArgumentNullException)");
+    if (h->n < 1 || n_chains < 1) return fail(GIBBS_ERR_ARG, "nothing to set");
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    const size_t cells = (size_t)n_chains * h->n;
+    std::vector<int32_t> len;
+    if (h->min_len != h->max_len) {
+        len.resize((size_t)h->n);
+        CUDA_TRY(cudaMemcpyAsync(len.data(), h->len.p, len.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    for (size_t c = 0; c < cells; ++c) {
+        const int32_t l = len.empty() ? h->max_len : len[c % (size_t)h->n];
+        if (sites[c] < -1 || sites[c] >= l) return fail(GIBBS_ERR_ARG, "start site %d outside its sequence", sites[c]);
+    }
+    CUDA_TRY(h->sites.reserve(cells));
+    CUDA_TRY(h->hv.reserve(cells));
+    CUDA_TRY(h->scores.reserve(cells));
+    CUDA_TRY(cudaMemcpyAsync(h->sites.p, sites, cells * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->scores.p, scores, cells * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->hv.p, 0xFF, cells * sizeof(double), h->stream)); // all-ones = NaN marker
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->start_chains = n_chains;
+    h->run_done = false;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_fetch(gibbs_handle *h, int32_t *sites_out, double *scores_out, double *sums_out, int32_t *best_chain_out,
+                    int32_t *counts_out, gibbs_run_stats *stats_out) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    if (!h->run_done) return fail(GIBBS_ERR_ARG, "gibbs_fetch without a preceding gibbs_run_device");
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    const size_t cells = (size_t)h->run_chains * h->n;
+    int32_t best = 0;
+    CUDA_TRY(cudaMemcpyAsync(&best, h->best.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (sites_out) CUDA_TRY(cudaMemcpyAsync(sites_out, h->sites.p, cells * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (scores_out) CUDA_TRY(cudaMemcpyAsync(scores_out, h->scores.p, cells * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sums_out) CUDA_TRY(cudaMemcpyAsync(sums_out, h->sums.p, (size_t)h->run_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long st[ST_NSLOTS];
+    CUDA_TRY(cudaMemcpyAsync(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int extra_launches = 0;
+    if (counts_out) {
+        rc = launch_all_counts(h, dev_seqs(h), h->sites.p + (size_t)best * h->n, h->run_k, h->best.p + 1);
+        if (rc) return rc;
+        ++extra_launches;
+        CUDA_TRY(cudaMemcpyAsync(counts_out, h->best.p + 1, (size_t)h->run_k * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (best_chain_out) *best_chain_out = best;
+    if (stats_out) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        stats_out->site_updates = (int64_t)st[ST_SITE_UPDATES];
+        stats_out->window_scores = (int64_t)st[ST_WINDOW_SCORES];
+        stats_out->sweeps = (int64_t)st[ST_SWEEPS];
+        stats_out->exact_rescans = (int64_t)st[ST_EXACT_RESCANS];
+        stats_out->capped_chains = (int64_t)st[ST_CAPPED];
+        stats_out->kernel_launches = h->run_launches + extra_launches;
+        stats_out->fast_path = h->run_fast;
+        stats_out->kernel_ms = (double)ms;
+    }
+    return GIBBS_OK;
+}
+
+int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base, uint64_t seed,
+                  int32_t rng_mode, const double *uniforms, int64_t uniforms_per_chain, int32_t *sites_out,
+                  double *scores_out, double *sums_out, int32_t *best_chain_out, int32_t *counts_out,
+                  gibbs_run_stats *stats_out) {
+    int32_t rc = gibbs_run_device(h, p, n_chains, chain_id_base, seed, rng_mode, uniforms, uniforms_per_chain);
+    if (rc) return rc;
+    return gibbs_fetch(h, sites_out, scores_out, sums_out, best_chain_out, counts_out, stats_out);
+}
+
+int32_t gibbs_device_results(gibbs_handle *h, void **sites_dev, void **scores_dev, void **sums_dev) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    if (!h->run_done) return fail(GIBBS_ERR_ARG, "no run on this handle yet");
+    if (sites_dev) *sites_dev = h->sites.p;
+    if (scores_dev) *scores_dev = h->scores.p;
+    if (sums_dev) *sums_dev = h->sums.p;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_measure_smem_bandwidth(int32_t device, int32_t iters, double *gbps_out, double *ms_out) {
+    if (!gbps_out) return fail(GIBBS_ERR_ARG, "null output");
+    if (iters < 1) iters = 1;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    unsigned int *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(unsigned int)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 2;
+    smem_stream_kernel<<<grid, 1024>>>(iters, sink); // warm-up
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        smem_stream_kernel<<<grid, 1024>>>(iters, sink);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double bytes = (double)grid * 1024.0 * 16.0 * 8.0 * (double)iters;
+    *gbps_out = bytes / ((double)best_ms * 1e-3) / 1e9;
+    if (ms_out) *ms_out = (double)best_ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return GIBBS_OK;
+}
+
+} // extern "C"

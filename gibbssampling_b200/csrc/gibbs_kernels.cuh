@@ -1,0 +1,363 @@
+// gibbssampling_b200/csrc/gibbs_kernels.cuh -- __global__ kernels (sm_100a only).
+#pragma once
+#include "gibbs_device.cuh"
+
+namespace gibbs {
+
+enum Phase { PH_INIT = 0, PH_GREEDY = 1, PH_LEFT = 2, PH_RIGHT = 3, PH_DONE = 4 };
+
+// first phase >= from whose bit (1 << phase) is set in mask
+__device__ __forceinline__ int next_phase(int from, int mask) {
+    int ph = from;
+    while (ph < PH_DONE && !((mask >> ph) & 1)) ++ph;
+    return ph;
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup kernels
+// ------------------------------------------------------------------------------------------------
+// ASCII -> 2-bit rows. One thread per packed word. Any symbol outside A,C,G,T raises *bad.
+__global__ void pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off, int n, int row_words,
+                            uint32_t *__restrict__ packed, int32_t *__restrict__ len_out, int *bad) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * row_words) return;
+    const int i = (int)(t / row_words), wd = (int)(t % row_words);
+    const int64_t o = off[i];
+    const int len = (int)(off[i + 1] - o);
+    if (wd == 0) len_out[i] = len;
+    uint32_t v = 0;
+    const int b0 = wd * 16;
+#pragma unroll
+    for (int x = 0; x < 16; ++x) {
+        const int b = b0 + x;
+        if (b < len) {
+            const uint8_t c = ascii[o + b];
+            uint32_t code;
+            if (c == 'A') code = 0;
+            else if (c == 'C') code = 1;
+            else if (c == 'G') code = 2;
+            else if (c == 'T') code = 3;
+            else {
+                code = 0;
+                atomicExch(bad, 1 + (int)c);
+            }
+            v |= code << (2 * x);
+        }
+    }
+    packed[t] = v;
+}
+
+// W(c, b) = ((c + pc) / den) / q[b]   (normalizePPM fs:260, createPositionWeightMatrix fs:286)
+// plus its fixed-point log2. range[0] = min lg, range[1] = max lg, range[2] = any non-normal W.
+__global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, double q2, double q3, WEnt *wtab,
+                            int *range) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 4) return;
+    const int c = t >> 2, b = t & 3;
+    const double q = b == 0 ? q0 : b == 1 ? q1 : b == 2 ? q2 : q3;
+    const double w = __ddiv_rn(__ddiv_rn(__dadd_rn((double)c, pc), den), q);
+    WEnt e;
+    e.w = w;
+    e.pad = 0;
+    const bool normal = (w >= 2.2250738585072014e-308) && (w <= 1.7976931348623157e308);
+    if (normal) {
+        double units = rint(log2(w) * (double)(1 << LG_FRAC_BITS));
+        units = fmin(fmax(units, -4000000.0), 4000000.0);
+        const int u = (int)units;
+        e.lg = u * (1 << KEY_IDX_BITS);
+        atomicMin(&range[0], u);
+        atomicMax(&range[1], u);
+    } else {
+        e.lg = 0;
+        atomicExch(&range[2], 1);
+    }
+    wtab[t] = e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// uniform stream -> leave-one-out counts of the random initial sites (fs:418-426)
+// ------------------------------------------------------------------------------------------------
+// Draw index of (held-out n, other sequence i) = n (N-1) + rank of i among the others, the order in
+// which the reference's Array.map consumes System.Random (fs:419-421, quirk A.6-5).
+template <int KP>
+__device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
+                                                  const WarpSmem &S, int lane) {
+    const int N = a.s.n, k = a.k;
+    zero_total(S.total, lane);
+    if (N < 2) return;
+    const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
+    const uint64_t d_end = base + (uint64_t)(N - 1);
+    const uint64_t blk0 = base >> 2, blk1 = (d_end + 3) >> 2;
+    const int iters = (int)((blk1 - blk0 + 31) >> 5);
+    Hist<KP> h;
+    h.clear();
+    for (int it0 = 0; it0 < iters; it0 += 63) { // byte counters: 63 rounds x 4 draws per lane
+        const int it1 = min(iters, it0 + 63);
+        for (int it = it0; it < it1; ++it) {
+            const uint64_t blk = blk0 + (uint64_t)it * 32 + lane;
+            if (blk < blk1) {
+                uint32_t wd[4] = {0, 0, 0, 0};
+                if (a.rng_mode == 0) {
+                    const uint4 r = philox4x32_10(
+                        make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const uint64_t d = blk * 4 + x;
+                    if (d >= base && d < d_end) {
+                        const int r = (int)(d - base);
+                        const int i = r + (r >= n ? 1 : 0);
+                        const int range = __ldg(a.s.len + i) - k + 1;
+                        int pos;
+                        if (a.rng_mode == 0) {
+                            pos = (int)__umulhi(wd[x], (uint32_t)range); // floor(word * 2^-32 * range), exact
+                        } else {
+                            const double u = ((int64_t)d < a.uniforms_per_chain)
+                                                 ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
+                                                 : 0.0;
+                            pos = (int)(u * (double)range); // rnd.Next(0, L-k+1), fs:145
+                            pos = min(max(pos, 0), range - 1); // memory safety for u outside [0,1)
+                        }
+                        h.add(kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos));
+                    }
+                }
+            }
+        }
+        h.flush_add(S.total, k, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the chain kernel: one warp = one restart of SiteSampler.doSiteSamplingWithBPV (fs:691-695)
+// ------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(32) chain_kernel(const ChainArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int chain = blockIdx.x;
+    const WarpSmem S = carve_smem(smem_raw, a.s.row_words);
+    RowPipe pipe;
+    pipe.init(S, a.s, lane);
+
+    const int N = a.s.n, k = a.k;
+    int32_t *sites = a.sites + (size_t)chain * N;
+    double *hv = a.hv + (size_t)chain * N;
+    const uint64_t chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
+
+    unsigned long long st_updates = 0, st_windows = 0, st_sweeps = 0, st_slow = 0;
+    int capped = 0;
+
+    pipe.issue(0, 0, lane);
+
+    double *scores = a.scores + (size_t)chain * N;
+    int phase = next_phase(PH_INIT, a.phase_mask);
+    int sweeps_in_phase = 0;
+    while (phase != PH_DONE) {
+        const int mode = phase == PH_LEFT ? SHIFT_LEFT : phase == PH_RIGHT ? SHIFT_RIGHT : SHIFT_NONE;
+        // all-sites counts: once when the greedy phase starts (then kept incrementally: -old site,
+        // +new site), once per sweep for the shift phases (they read the shifted snapshot, fs:357)
+        if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && sweeps_in_phase == 0))
+            site_counts<KP>(a.s, sites, -1, k, mode, S.total, lane);
+        bool changed = false;
+        int site_next = 0;
+        double hv_next = 0.0;
+        if (phase != PH_INIT) {
+            site_next = __ldcg(sites);
+            hv_next = __ldcg(hv);
+        }
+        for (int n = 0; n < N; ++n) {
+            const uint32_t *row = pipe.acquire(n + 1 < N ? n + 1 : 0, lane);
+            const int len_n = __ldg(a.s.len + n);
+            const int Wn = len_n - k + 1;
+            int site_n = 0;
+            double hv_n = 0.0;
+            uint64_t own = 0;
+            if (phase == PH_INIT) {
+                random_loo_counts<KP>(a, chain_uid, chain, n, S, lane);
+            } else {
+                site_n = site_next;
+                hv_n = hv_next;
+                if (n + 1 < N) {
+                    site_next = __ldcg(sites + n + 1);
+                    hv_next = __ldcg(hv + n + 1);
+                }
+                own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
+            }
+            build_tables<KP>(S, phase != PH_INIT, own, k, a.wtab, lane);
+            double p;
+            int w;
+            const bool slow = pick_argmax<KP>(S, row, Wn, k, a.fast_ok, lane, p, w);
+            st_updates += 1;
+            st_windows += (unsigned long long)Wn;
+            st_slow += slow ? 1 : 0;
+            if (phase == PH_INIT) {
+                if (lane == 0) {
+                    sites[n] = w;
+                    hv[n] = p;
+                }
+            } else if (score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0)) { // fs:402
+                if (w != site_n) {
+                    changed = true;
+                    if (phase == PH_GREEDY) { // in-place sweep: later n see the new site (fs:388)
+                        const uint64_t neu = kmer_shared<KP>(row, w);
+                        if (lane < k) {
+                            const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
+                            if (bo != bn) {
+                                S.total[lane * 4 + bo] -= 1;
+                                S.total[lane * 4 + bn] += 1;
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    sites[n] = w;
+                    hv[n] = p;
+                }
+            }
+            __syncwarp();
+        }
+        st_sweeps += 1;
+        if (phase == PH_INIT) {
+            phase = next_phase(PH_GREEDY, a.phase_mask);
+            sweeps_in_phase = 0;
+            continue;
+        }
+        ++sweeps_in_phase;
+        bool next = !changed; // positions(acc) = positions(bestMotif), fs:384
+        if (!next && sweeps_in_phase >= a.max_sweeps) {
+            next = true;
+            capped = 1;
+        }
+        if (next) {
+            sweeps_in_phase = 0;
+            phase = next_phase(phase + 1, a.phase_mask);
+        }
+    }
+    pipe.drain();
+    __syncwarp();
+
+    // (log2 highValue, highIndex), fs:303
+    for (int n = lane; n < N; n += 32) {
+        const double v = __ldcg(hv + n);
+        if (v == v) scores[n] = log2_ref(v); // NaN = untouched caller-supplied entry keeps its score
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double sum = 0.0; // Array.sum, left to right (fs:445)
+        for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(scores + n));
+        a.sums[chain] = sum;
+        atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
+        atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
+        atomicAdd(a.stats + ST_SWEEPS, st_sweeps);
+        atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
+        atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// primitive kernels (one warp): same device routines as the chain kernel
+// ------------------------------------------------------------------------------------------------
+struct PrimArgs {
+    DeviceSeqs s;
+    const WEnt *wtab;
+    const int32_t *sites; // [n] device
+    int32_t heldout;
+    int32_t k;
+    int32_t fast_ok;
+    int32_t *counts_out;  // [k*4]
+    double *raw_out;      // [W] or null
+    double *log2_out;     // [W] or null
+    double *score_out;    // [2]: log2 max, raw max
+    int32_t *site_out;    // [2]: argmax, used_exact_rescan
+};
+
+template <int KP>
+__global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const WarpSmem S = carve_smem(smem_raw, a.s.row_words);
+    site_counts<KP>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
+    for (int e = lane; e < a.k * 4; e += 32) a.counts_out[e] = S.total[e];
+}
+
+// mode 0: every window in float64 (raw product and log2); mode 1: argmax pick
+template <int KP>
+__global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const WarpSmem S = carve_smem(smem_raw, a.s.row_words);
+    RowPipe pipe;
+    pipe.init(S, a.s, lane);
+    pipe.issue(0, a.heldout, lane);
+    site_counts<KP>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
+    const uint32_t *row = pipe.acquire(a.heldout, lane);
+    build_tables<KP>(S, false, 0, a.k, a.wtab, lane);
+    const int W = __ldg(a.s.len + a.heldout) - a.k + 1;
+    if (mode == 0) {
+        for (int w = lane; w < W; w += 32) {
+            const double p = exact_window<KP>(row, w, a.k, S.wcol);
+            if (a.raw_out) a.raw_out[w] = p;
+            if (a.log2_out) a.log2_out[w] = log2_ref(p);
+        }
+    } else {
+        double p;
+        int w;
+        const bool slow = pick_argmax<KP>(S, row, W, a.k, a.fast_ok, lane, p, w);
+        if (lane == 0) {
+            a.score_out[0] = log2_ref(p);
+            a.score_out[1] = p;
+            a.site_out[0] = w;
+            a.site_out[1] = slow ? 1 : 0;
+        }
+    }
+    pipe.drain();
+}
+
+// counts of all N sites of one chain (PWM counts reported with the best chain)
+template <int KP>
+__global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int32_t *sites, int k, int32_t *counts_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const WarpSmem S = carve_smem(smem_raw, s.row_words);
+    site_counts<KP>(s, sites, -1, k, SHIFT_NONE, S.total, lane);
+    for (int e = lane; e < k * 4; e += 32) counts_out[e] = S.total[e];
+}
+
+// first chain with the largest sum (strict >), the restart selection of fs:450 / fs:156-170
+__global__ void best_chain_kernel(const double *sums, int n_chains, int *best_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int best = 0;
+        double bs = sums[0];
+        for (int c = 1; c < n_chains; ++c)
+            if (sums[c] > bs) {
+                bs = sums[c];
+                best = c;
+            }
+        *best_out = best;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory streaming microbenchmark: the measured denominator of the smem roofline
+// ------------------------------------------------------------------------------------------------
+// 1024 threads x LDS.128, conflict-free, 8 loads per round: bytes = grid * 1024 * 16 * 8 * iters
+__global__ void __launch_bounds__(1024) smem_stream_kernel(int iters, unsigned int *sink) {
+    __shared__ uint4 buf[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = make_uint4(i, i * 3, i * 5, i * 7);
+    __syncthreads();
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    int idx = threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint4 v = buf[idx];
+            acc.x ^= v.x; acc.y += v.y; acc.z ^= v.z; acc.w += v.w;
+            idx = (idx + 1024 + 32) & 2047;
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = 1;
+}
+
+} // namespace gibbs

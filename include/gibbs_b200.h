@@ -1,0 +1,188 @@
+/*
+ * include/gibbs_b200.h -- C ABI of libgibbs_b200.so, the B200 (sm_100a) replacement for the
+ * data-parallel hot path of Etschbeijer/GibbsSampling.
+ *
+ * Each entry point replaces a piece of /root/reference/GibbsSampling/GibbsSampling.fs (cited as
+ * fs:N). The F# module keeps the reference signatures and binds these symbols with P/Invoke
+ * (fsharp/GibbsSamplingB200.fs); in this repository the same symbols are bound
+ * with ctypes by gibbssampling_b200/_abi.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer; the library never keeps
+ *     a host pointer after a call returns; device memory is owned by the handle
+ *   - every function returns a gibbs_status (0 = OK); the text of the last failure is available
+ *     from gibbs_last_error(); nothing throws or aborts across the boundary
+ *   - sequences: ONE contiguous buffer of upper-case ASCII symbols (BioItem.symbol, fs:17) plus
+ *     int64 offsets[n_seqs + 1]. This build accepts A, C, G, T only; any other symbol is
+ *     GIBBS_ERR_SYMBOL (the reference's 49-slot tables accept '*'..'Z', fs:20)
+ *   - base order of every 4-wide table: A, C, G, T
+ *   - (float*int)[] results: parallel arrays double score[n] (log2, fs:303) and int32 site[n]
+ *   - there is NO CPU fallback: every compute entry point launches CUDA kernels on the handle's
+ *     device and fails with GIBBS_ERR_CUDA if that is impossible
+ */
+#ifndef GIBBS_B200_H
+#define GIBBS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIBBS_ABI_VERSION 1
+#define GIBBS_MAX_K 32          /* motif width limit of the packed 64-bit window register      */
+#define GIBBS_MAX_LEN (1 << 20) /* longest sequence                                            */
+
+typedef enum gibbs_status {
+    GIBBS_OK = 0,
+    GIBBS_ERR_ARG = 1,         /* ArgumentNullException / ArgumentException (fs:24, fs:183)        */
+    GIBBS_ERR_SYMBOL = 2,      /* IndexOutOfRangeException analogue: symbol outside A,C,G,T (fs:17) */
+    GIBBS_ERR_SHORT_SEQ = 3,   /* InvalidOperationException from Array.take when L < k (fs:152)     */
+    GIBBS_ERR_CUDA = 4,        /* CUDA runtime / launch failure or no usable device                 */
+    GIBBS_ERR_NCCL = 5,        /* reserved: collectives run in the host layer (torch.distributed)   */
+    GIBBS_ERR_NOMEM = 6,       /* host or device allocation failed                                  */
+    GIBBS_ERR_ROULETTE = 7,    /* ArgumentException of fs:753: pick beyond the accumulated mass     */
+    GIBBS_ERR_UNSUPPORTED = 8  /* a mode outside the built hot path (out of scope)   */
+} gibbs_status;
+
+/* sampler: which reference pipeline one chain (= one restart) runs */
+#define GIBBS_SITE_SAMPLER 0  /* SiteSampler.doSiteSamplingWithBPV, fs:691-695                    */
+#define GIBBS_MOTIF_SAMPLER 1 /* MotifSampler restart with fixed pcv, fs:876-879, motifAmount = 1 */
+
+/* uniform source */
+#define GIBBS_RNG_PHILOX 0    /* Philox4x32-10(key = seed, counter = (draw/4, chain)), u = word * 2^-32 */
+#define GIBBS_RNG_INJECTED 1  /* caller-supplied doubles in [0,1): uniforms[chain][draw]                */
+
+typedef struct gibbs_params {
+    int32_t k;             /* motifLength                                                       */
+    int32_t alphabet_size; /* alphabet.Length: the |A| of every pseudocount denominator (fs:257) */
+    double pseudocount;    /* pseudoCount                                                       */
+    double bg[4];          /* pcv.[A], pcv.[C], pcv.[G], pcv.[T] of the WithBPV family (fs:301)  */
+    double cutoff;         /* MotifSampler cutOff (log2), fs:735                                */
+    int32_t sampler;       /* GIBBS_SITE_SAMPLER | GIBBS_MOTIF_SAMPLER                          */
+    int32_t phase_shifts;  /* SiteSampler: 1 = run the left/right shift sweeps (fs:694-695)     */
+    int32_t max_sweeps;    /* safety cap per phase (the reference has none); 0 = 1000000        */
+    int32_t phase_mask;    /* 0 = the whole pipeline of `sampler`; else a set of GIBBS_PHASE_* bits,  */
+                           /* run in pipeline order from the state given to gibbs_set_start_state    */
+} gibbs_params;
+
+/* phases = the reference functions a pipeline is made of */
+#define GIBBS_PHASE_INIT 1        /* getPWMOfRandomStartsWithBPV, fs:412-430                          */
+#define GIBBS_PHASE_GREEDY 2      /* findBestMotifWithStartPosition, fs:381-408                       */
+#define GIBBS_PHASE_LEFT 4        /* getLeftShiftedBestPWMSsWithBPV, fs:350-377                       */
+#define GIBBS_PHASE_RIGHT 8       /* getRightShiftedBestPWMSsWithBPV, fs:318-346                      */
+#define GIBBS_PHASE_STOCHASTIC 16 /* findBestMotifPositionsWithStartPositionsByPCV, fs:828-853        */
+#define GIBBS_PHASE_MOTIF_GREEDY 32 /* findBestMotifPositionsWithStartPositionByPCV, fs:788-822       */
+
+typedef struct gibbs_run_stats {
+    int64_t site_updates;  /* scans of one held-out sequence, all chains                        */
+    int64_t window_scores; /* windows scored inside those scans                                 */
+    int64_t sweeps;        /* passes n = 0..N-1, all chains                                     */
+    int64_t exact_rescans; /* site updates that fell back to the all-windows float64 path       */
+    int64_t capped_chains; /* chains stopped by max_sweeps                                      */
+    int32_t kernel_launches; /* CUDA kernels launched by the call                               */
+    int32_t fast_path;     /* 1 = fixed-point filter + float64 verification was usable          */
+    double kernel_ms;      /* device time of the chain kernel (CUDA events on the handle stream) */
+} gibbs_run_stats;
+
+typedef struct gibbs_handle gibbs_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int32_t gibbs_abi_version(void);
+/* message of the most recent failure on this thread (never NULL) */
+const char *gibbs_last_error(void);
+/* number of CUDA devices visible, or 0 */
+int32_t gibbs_device_count(void);
+
+/*
+ * Replaces: the `sources : BioArray<#IBioItem>[]` argument of every reference entry point
+ * (fs:615, fs:691, fs:973 ...). Validates and uploads the sequences, 2-bit packs them on the GPU
+ * (one row per sequence, rows padded to 16 B for bulk copies) and keeps them resident in HBM.
+ */
+int32_t gibbs_create(const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs, int32_t device,
+                     gibbs_handle **out);
+/* replace the sequences of an existing handle (re-upload + re-pack, reusing device capacity) */
+int32_t gibbs_upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs);
+int32_t gibbs_destroy(gibbs_handle *h);
+/* run all work of this handle on an existing CUDA stream (cudaStream_t as void*; NULL = own stream) */
+int32_t gibbs_set_stream(gibbs_handle *h, void *cuda_stream);
+int32_t gibbs_num_sequences(const gibbs_handle *h);
+int32_t gibbs_synchronize(gibbs_handle *h);
+
+/* ---- primitives: parity can be checked at the level the reference composes them -------------- */
+/*
+ * Replaces: getSegment -> createPFMOf -> fusePositionFrequencyMatrices for the N-1 other
+ * sequences (fs:149, fs:211, fs:218; call sites fs:392-396). sites[i] < 0 means "no site"
+ * (MotifSampler Positions = []). counts_out is int32 [k][4]. Bit-exact.
+ */
+int32_t gibbs_loo_counts(gibbs_handle *h, const int32_t *sites, int32_t heldout, int32_t k,
+                         int32_t *counts_out);
+/*
+ * Replaces: createPPMOf -> normalizePPM -> createPositionWeightMatrix -> calculateSegmentScoreBy
+ * for every window of sources.[heldout] (fs:249-293, loop of fs:301-314). raw_out (nullable) gets
+ * the float64 products, log2_out (nullable) their log2; both have L - k + 1 entries.
+ */
+int32_t gibbs_window_scores(gibbs_handle *h, const int32_t *sites, int32_t heldout,
+                            const gibbs_params *p, double *raw_out, double *log2_out);
+/* Replaces: getBestPWMSsWithBPV (fs:301-314): first strict maximum; returns (log2 max, argmax). */
+int32_t gibbs_pick_argmax(gibbs_handle *h, const int32_t *sites, int32_t heldout,
+                          const gibbs_params *p, double *score_out, int32_t *site_out);
+/*
+ * Replaces: calculateNormalizedSegmentScores (motifAmount = 1) |> rouletteWheelSelection u
+ * (fs:759-784, fs:746-754). site_out = -1 when a background ("no site") entry is selected;
+ * pwms_out = the PWMS of the selected MotifIndex.
+ */
+int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldout,
+                            const gibbs_params *p, double u, double *pwms_out, int32_t *site_out);
+
+/* ---- chains / restarts ------------------------------------------------------------------------ */
+/*
+ * Replaces: one restart pipeline per chain --
+ *   sampler 0: getPWMOfRandomStartsWithBPV |> findBestMotifWithStartPosition
+ *              |> getLeftShiftedBestPWMSsWithBPV |> getRightShiftedBestPWMSsWithBPV (fs:691-695)
+ *   sampler 1: getPWMOfRandomStartsWithBPV |> findBestMotifPositionsWithStartPositionsByPCV
+ *              |> findBestMotifPositionsWithStartPositionByPCV, motifAmount = 1 (fs:876-879)
+ * n_chains independent chains run concurrently (one warp each); chain c uses the uniform stream
+ * (seed, chain_id_base + c) or uniforms[c * uniforms_per_chain ...]. Draw order inside a chain:
+ * random init n ascending, i ascending skipping n (fs:595-598), then one draw per n for the
+ * stochastic sweep (fs:851). Results stay on the device until gibbs_fetch.
+ */
+/*
+ * Start state for pipelines whose phase_mask lacks GIBBS_PHASE_INIT: the `startPositions :
+ * (float*int)[]` / `motifMem : MotifIndex[]` argument of the sweep functions (fs:381, fs:350, fs:318,
+ * fs:788, fs:828). sites int32 [n_chains][n_seqs] (-1 = Positions []), scores double
+ * [n_chains][n_seqs]. Consumed by the next gibbs_run_device with the same n_chains.
+ */
+int32_t gibbs_set_start_state(gibbs_handle *h, int32_t n_chains, const int32_t *sites,
+                              const double *scores);
+int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chains,
+                         int64_t chain_id_base, uint64_t seed, int32_t rng_mode,
+                         const double *uniforms_or_null, int64_t uniforms_per_chain);
+/*
+ * Copies the results of the last gibbs_run_device to host buffers (any may be NULL):
+ *   sites_out  int32 [n_chains][n_seqs]   (-1 = no site, MotifSampler only)
+ *   scores_out double [n_chains][n_seqs]  log2 score / PWMS per sequence
+ *   sums_out   double [n_chains]          Array.sum of the scores, left to right (fs:445)
+ *   best_chain_out                        first chain with the largest sum (strict >, fs:450)
+ *   counts_out int32 [k][4]               PWM counts (all N sites) of the best chain
+ */
+int32_t gibbs_fetch(gibbs_handle *h, int32_t *sites_out, double *scores_out, double *sums_out,
+                    int32_t *best_chain_out, int32_t *counts_out, gibbs_run_stats *stats_out);
+/* gibbs_run_device + gibbs_fetch */
+int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base,
+                  uint64_t seed, int32_t rng_mode, const double *uniforms_or_null,
+                  int64_t uniforms_per_chain, int32_t *sites_out, double *scores_out,
+                  double *sums_out, int32_t *best_chain_out, int32_t *counts_out,
+                  gibbs_run_stats *stats_out);
+/* device pointers of the last run, for zero-copy collectives in the host layer (may be NULL) */
+int32_t gibbs_device_results(gibbs_handle *h, void **sites_dev, void **scores_dev, void **sums_dev);
+
+/* ---- measurement support ------------------------------------------------------------------------ */
+/* Streams `bytes` of shared-memory loads per SM for `iters` rounds; returns the achieved GB/s. */
+int32_t gibbs_measure_smem_bandwidth(int32_t device, int32_t iters, double *gbps_out,
+                                     double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIBBS_B200_H */
