@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs window-scores/s and site-updates/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch: `chains` independent restarts of
+SiteSampler.doSiteSamplingWithBPV (fs:691-695: random starts, greedy sweeps to convergence, left and
+right phase-shift sweeps) on synthetic planted-motif DNA. At N = 1 the workload is BASELINE.json
+configs[1] (C2: 1000 seqs x 500 bp, k = 12, 1024 chains). With N > 1 every rank runs `chains` more
+chains (weak scaling; chain ids are global so results do not depend on N) and the step ends with the
+single NCCL all_gather of each GPU's best (sum of scores, site vector).
+
+One JSON line is printed by rank 0. `value` = window-scores/s over all ranks with the sequences
+already resident in HBM (CUDA events on the launch stream, max over ranks); `e2e` = the same metric
+through the public API with HOST buffers: per step the ASCII sequences are uploaded from pinned
+memory and 2-bit packed, the chains run, and sites/scores/sums come back to the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n_seqs, length, k, chains per GPU, phase shifts)
+    "C1": (20, 100, 8, 1, True),          # reference-scale: 20 x 100 bp, planted 8-mer, 1 chain
+    "C2": (1000, 500, 12, 1024, True),    # the single-GPU configuration the metric is quoted on
+    "C3": (10000, 1000, 16, 1024, True),  # 8192 restarts over 8 GPUs = 1024 per GPU
+    "C4": (100000, 200, 20, 148, True),   # ChIP-seq-peak-sized set with phase-shift moves
+}
+PSEUDOCOUNT = 1e-4      # fsx:384
+ALPHABET_SIZE = 5       # dnaBases = [A; T; G; C; Gap], fsx:368-369
+SEED = 0xB200
+
+
+def algorithmic_smem_bytes_per_window(k: int) -> float:
+    """k log-odds reads of 4 B + 2k bits of sequence per window score."""
+    return 4.0 * k + k / 4.0
+
+
+def algorithmic_hbm_bytes_per_site_update(length: int) -> float:
+    """ceil(L/4) packed row bytes + 8 B (old site read + new site write)."""
+    return float((length + 3) // 4 + 8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "_source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the F# reference; the reference itself needs .NET, absent here)
+# ---------------------------------------------------------------------------------------------------
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    oracle_lib.lib()
+    return oracle_lib
+
+
+def cpu_sample(ps, k, bg, *, threads: int, full_restart: bool, seed: int, chain_base: int) -> tuple[float, int, int]:
+    """Run `threads` chains concurrently on host threads (ctypes releases the GIL).
+    Returns (wall seconds, window scores, site updates)."""
+    O = _oracle()
+    S = O.sources(ps.sequences())
+    pcv = O.pcv_from_acgt(bg)
+    name = "do_site_sampling_with_bpv" if full_restart else "random_starts_with_bpv"
+    out = [None] * threads
+
+    def work(t):
+        rng, _ = O.make_rng(seed=seed, chain=chain_base + t)
+        _, _, st = O.site_step(name, S, k, PSEUDOCOUNT, pcv=pcv, rng=rng)
+        out[t] = (st.window_scores, st.site_updates)
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return dt, sum(o[0] for o in out), sum(o[1] for o in out)
+
+
+def run_reference_arm(args, cfg_name, cfg) -> None:
+    """`--impl reference`: the reference's CPU algorithm on the box's host cores. The F# cannot run here
+    (no .NET runtime in the image or on the GPU box), so this times the oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gibbssampling_b200.synthetic import background_of, planted_motif_set
+
+    n, length, k, chains, shifts = cfg
+    ps = planted_motif_set(n, length, k, seed=SEED)
+    bg = background_of(ps.ascii, PSEUDOCOUNT, ALPHABET_SIZE)
+    cores = os.cpu_count() or 1
+    for w in range(args.warmup):
+        cpu_sample(ps, k, bg, threads=cores, full_restart=False, seed=SEED, chain_base=w * cores)
+    tot_t = tot_w = tot_u = 0.0
+    for s in range(args.steps):
+        dt, ws, us = cpu_sample(ps, k, bg, threads=cores, full_restart=False, seed=SEED,
+                                chain_base=(args.warmup + s) * cores)
+        tot_t += dt
+        tot_w += ws
+        tot_u += us
+    value = tot_w / tot_t
+    sample = (f"per step: one getPWMOfRandomStartsWithBPV sweep (fs:412, {n} site updates, from-scratch PWM per "
+              f"site update and per window like the F#) per host thread, {cores} threads; oracle port (C, -O2)")
+    line = {
+        "impl": "reference", "metric": "gibbs_window_scores_per_sec", "value": value, "unit": "window-scores/s",
+        "site_updates_per_sec": tot_u / tot_t, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic planted-motif DNA (seed 0xB200)",
+        "config": {"workload": f"{cfg_name}: {n} seqs x {length} bp, k={k}, SiteSampler WithBPV restarts",
+                   "pseudocount": PSEUDOCOUNT, "alphabet_size": ALPHABET_SIZE},
+        "cpu_baseline": {"value": value, "unit": "window-scores/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "window-scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, cfg_name, cfg) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gibbssampling_b200 import SiteSampler
+    from gibbssampling_b200.distributed import allgather_best
+    from gibbssampling_b200.engine import GibbsEngine, make_params, measure_smem_bandwidth
+    from gibbssampling_b200.synthetic import background_of, planted_motif_set
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gibbssampling_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, length, k, chains, shifts = cfg
+    if args.chains:
+        chains = args.chains
+    ps = planted_motif_set(n, length, k, seed=SEED)
+    bg = background_of(ps.ascii, PSEUDOCOUNT, ALPHABET_SIZE)
+    params = make_params(k, PSEUDOCOUNT, ALPHABET_SIZE, bg, phase_shifts=shifts)
+    windows = length - k + 1
+
+    # pinned host copies of the inputs (e2e path uploads them every step)
+    host_ascii = torch.empty(ps.ascii.size, dtype=torch.uint8, pin_memory=True)
+    host_ascii.numpy()[:] = ps.ascii
+    host_off = torch.empty(ps.offsets.size, dtype=torch.int64, pin_memory=True)
+    host_off.numpy()[:] = ps.offsets
+
+    eng = GibbsEngine(ps.sequences(), device=local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")  # > 126 MB L2
+    chain_base = rank * chains
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(step: int):
+        """hot path with inputs resident in HBM; ends with the all_gather of each GPU's best result"""
+        eng.run_device(params, chains, chain_id_base=chain_base, seed=SEED + step)
+
+    def finish_step():
+        res = eng.fetch(want_sites=True, want_scores=True, want_counts=False)
+        b = res.best_chain
+        if world > 1:
+            allgather_best(float(res.sums[b]), chain_base + b, res.sites[b], res.scores[b])
+        return res
+
+    # ---- warm-up ----
+    for w in range(args.warmup):
+        device_step(-1 - w)
+        finish_step()
+    barrier()
+
+    # ---- timed: device-resident ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    tot_windows = tot_updates = tot_sweeps = tot_rescans = launches = 0
+    kernel_ms = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s)                      # L2 flush between steps, outside the per-step event window
+        ev[s][0].record(stream)
+        device_step(s)
+        ev[s][1].record(stream)
+        res = finish_step()                 # sync + D2H (not inside the event window)
+        st = res.stats
+        tot_windows += st["window_scores"]
+        tot_updates += st["site_updates"]
+        tot_sweeps += st["sweeps"]
+        tot_rescans += st["exact_rescans"]
+        launches += st["kernel_launches"]
+        kernel_ms.append(st["kernel_ms"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop()
+
+    # ---- timed: end to end through the public API with host buffers ----
+    e2e_windows = 0
+    h2d = int(ps.ascii.size + ps.offsets.size * 8)
+    d2h = int(chains * n * (4 + 8) + chains * 8 + 4)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        eng.upload_flat(host_ascii.numpy(), host_off.numpy())      # H2D + GPU 2-bit pack
+        r = eng.run(params, chains, chain_id_base=chain_base, seed=SEED + 1000 + s, want_counts=False)
+        best = SiteSampler.replay_restart_loop(chains - 1, r.scores, r.sites)   # what fs:434 returns
+        if world > 1:
+            allgather_best(float(r.sums[r.best_chain]), chain_base + r.best_chain, r.sites[r.best_chain],
+                           r.scores[r.best_chain])
+        e2e_windows += r.stats["window_scores"]
+        launches_e2e = r.stats["kernel_launches"] + 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert len(best) in (1, n)
+
+    # ---- reduce over ranks: totals summed, times max ----
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s, t_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([tot_windows, tot_updates, e2e_windows, tot_sweeps, tot_rescans], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, t_wall = (float(x) for x in t.tolist())
+        g_windows, g_updates, g_e2e_windows, g_sweeps, g_rescans = (float(x) for x in c.tolist())
+    else:
+        g_windows, g_updates, g_e2e_windows, g_sweeps, g_rescans = tot_windows, tot_updates, e2e_windows, tot_sweeps, tot_rescans
+
+    if rank == 0:
+        peaks = measured_peaks()
+        smem_gbs, _ = measure_smem_bandwidth(local_rank, 20000)
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        smem_theory = sm_count * 128.0 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        rank_windows_per_s = (tot_windows / args.steps) / (k_ms * 1e-3)
+        rank_updates_per_s = (tot_updates / args.steps) / (k_ms * 1e-3)
+        achieved = rank_windows_per_s * algorithmic_smem_bytes_per_window(k) / 1e9
+        hbm_achieved = rank_updates_per_s * algorithmic_hbm_bytes_per_site_update(length) / 1e9
+        value = g_windows / (dev_ms * 1e-3)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            dt, ws, us = cpu_sample(ps, k, bg, threads=1, full_restart=True, seed=SEED, chain_base=0)
+            cpu = {"value": ws / dt, "unit": "window-scores/s", "site_updates_per_sec": us / dt, "cores": 1,
+                   "kind": "port", "seconds": dt,
+                   "sample": (f"chain 0 of the same workload, one full doSiteSamplingWithBPV restart ({us} site updates) "
+                              "on 1 host core; C port of the F# reference (oracle/), reference-faithful from-scratch rebuilds; "
+                              "the F# itself needs .NET, absent from this image")}
+        line = {
+            "metric": "gibbs_window_scores_per_sec", "value": value, "unit": "window-scores/s",
+            "site_updates_per_sec": g_updates / (dev_ms * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic planted-motif DNA (Philox key 0xB200, 10% planted-base mutation)",
+            "config": {"workload": f"{cfg_name}: {n} seqs x {length} bp, k={k}, {chains} chains/GPU, SiteSampler WithBPV "
+                                   f"restarts (random starts + greedy sweeps + {'left/right shift sweeps' if shifts else 'no shifts'})",
+                       "chains_per_gpu": chains, "pseudocount": PSEUDOCOUNT, "alphabet_size": ALPHABET_SIZE,
+                       "background": "fixed (WithBPV), whole-set base counts",
+                       "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event window; the packed "
+                             "sequences (125 KB at C2) are L2/SMEM-resident by design",
+                       "timing": "CUDA events on the launch stream around each step, summed; max over ranks"},
+            "window_scores_per_step": g_windows / args.steps, "site_updates_per_step": g_updates / args.steps,
+            "sweeps_per_chain": g_sweeps / (args.steps * chains * world), "exact_rescans_per_step": g_rescans / args.steps,
+            "wall_s_timed_region": t_wall,
+            "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s", "frac": achieved / smem_gbs,
+                         "traffic": None, "peak_source": "measured live: LDS.128 streaming microbenchmark (gibbs_measure_smem_bandwidth)",
+                         "peak_theoretical": smem_theory, "frac_of_theoretical": achieved / smem_theory,
+                         "algorithmic_bytes_per_window_score": algorithmic_smem_bytes_per_window(k),
+                         "kernel": "gibbs::chain_kernel", "kernel_ms": k_ms,
+                         "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": hbm_achieved / peaks["hbm_gbs"], "peak_source": peaks["_source"],
+                                 "algorithmic_bytes_per_site_update": algorithmic_hbm_bytes_per_site_update(length)}},
+            "cpu_baseline": cpu,
+            "e2e": {"value": g_e2e_windows / e2e_s, "unit": "window-scores/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "api": "gibbs_upload + gibbs_run (C ABI) + replay of the fs:434 restart loop"},
+            "gpu_launches": launches, "gpu_launches_e2e_per_step": launches_e2e,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="C2")
+    ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, args.config, cfg)
+    else:
+        run_gpu_arm(args, args.config, cfg)
+
+
+if __name__ == "__main__":
+    main()
