@@ -30,7 +30,7 @@ PHASE_INIT, PHASE_GREEDY, PHASE_LEFT, PHASE_RIGHT, PHASE_STOCHASTIC, PHASE_MOTIF
 # every symbol include/gibbs_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "gibbs_abi_version", "gibbs_last_error", "gibbs_device_count", "gibbs_create", "gibbs_upload",
-    "gibbs_destroy", "gibbs_set_stream", "gibbs_num_sequences", "gibbs_synchronize",
+    "gibbs_destroy", "gibbs_set_stream", "gibbs_num_sequences", "gibbs_set_team_warps", "gibbs_synchronize",
     "gibbs_loo_counts", "gibbs_window_scores", "gibbs_pick_argmax", "gibbs_pick_roulette",
     "gibbs_set_start_state", "gibbs_run_device", "gibbs_fetch", "gibbs_run", "gibbs_device_results",
     "gibbs_measure_smem_bandwidth",
@@ -101,8 +101,11 @@ class RunStats(C.Structure):
         ("sweeps", C.c_int64),
         ("exact_rescans", C.c_int64),
         ("capped_chains", C.c_int64),
+        ("speculative_discards", C.c_int64),
         ("kernel_launches", C.c_int32),
         ("fast_path", C.c_int32),
+        ("team_warps", C.c_int32),
+        ("reserved", C.c_int32),
         ("kernel_ms", C.c_double),
     ]
 
@@ -137,6 +140,7 @@ def load() -> C.CDLL:
     lib.gibbs_set_stream.argtypes = [vp, vp]
     lib.gibbs_num_sequences.argtypes = [vp]
     lib.gibbs_synchronize.argtypes = [vp]
+    lib.gibbs_set_team_warps.argtypes = [vp, i32]
     lib.gibbs_loo_counts.argtypes = [vp, P(i32), i32, i32, P(i32)]
     lib.gibbs_window_scores.argtypes = [vp, P(i32), i32, P(Params), P(f64), P(f64)]
     lib.gibbs_pick_argmax.argtypes = [vp, P(i32), i32, P(Params), P(f64), P(i32)]

@@ -16,6 +16,7 @@ DEPS = SOURCES + [
 ]
 
 NVCC_FLAGS = [
+    "--split-compile", "0",   # parallel ptxas over the template instantiations
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",

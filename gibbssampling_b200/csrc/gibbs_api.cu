@@ -91,6 +91,9 @@ struct gibbs_handle {
     int32_t run_chains = 0, run_k = 0, run_fast = 0, run_launches = 0;
     bool run_done = false;
     int32_t start_chains = 0; // chains covered by gibbs_set_start_state (0 = none pending)
+    int32_t team_warps = 0;   // 0 = choose per launch; 1 or 4 = forced (gibbs_set_team_warps)
+    int32_t run_team = 0;
+    int sm_count = 0;
 };
 
 namespace {
@@ -160,28 +163,51 @@ int32_t set_smem(K kernel, int bytes) {
 
 #define KP_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
-int32_t launch_chain(gibbs_handle *h, const ChainArgs &a) {
-    const int kp = (a.k + 1) / 2;
-    const int smem = warp_smem_bytes(a.s.row_words);
-    switch (kp) {
-#define X(KPV)                                                                          \
-    case KPV: {                                                                         \
-        int32_t rc = set_smem(chain_kernel<KPV>, smem);                                 \
-        if (rc) return rc;                                                              \
-        chain_kernel<KPV><<<a.n_chains, 32, smem, h->stream>>>(a);                      \
-        break;                                                                          \
+// Warps per chain: 4 when every chain can then be resident at once (the C2 case: 1024 chains on 148 SMs
+// would otherwise leave most warp slots empty and each chain latency-bound), else 1.
+// Warps per chain: 4 when every chain can then be resident at once (the C2 case: 1024 chains on 148 SMs
+// would otherwise leave most warp slots empty and each chain latency-bound), else 1.
+template <int KPV>
+int32_t launch_chain_kp(gibbs_handle *h, const ChainArgs &a) {
+    int team = h->team_warps;
+    const int smem4 = team_smem_bytes(a.s.row_words, 4), smem1 = team_smem_bytes(a.s.row_words, 1);
+    if (team == 0) {
+        int nb = 0;
+        if (smem4 <= 200 * 1024) {
+            int32_t rc = set_smem(chain_kernel<KPV, 4>, smem4);
+            if (rc) return rc;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<KPV, 4>, 128, smem4));
+        }
+        team = ((long long)nb * h->sm_count >= a.n_chains) ? 4 : 1;
     }
-        KP_CASES(X)
-#undef X
-    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    h->run_team = team;
+    if (team == 4) {
+        if (smem4 > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for 4 warps per chain");
+        int32_t rc = set_smem(chain_kernel<KPV, 4>, smem4);
+        if (rc) return rc;
+        chain_kernel<KPV, 4><<<a.n_chains, 128, smem4, h->stream>>>(a);
+    } else {
+        int32_t rc = set_smem(chain_kernel<KPV, 1>, smem1);
+        if (rc) return rc;
+        chain_kernel<KPV, 1><<<a.n_chains, 32, smem1, h->stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return GIBBS_OK;
 }
 
+int32_t launch_chain(gibbs_handle *h, const ChainArgs &a) {
+    const int kp = (a.k + 1) / 2;
+    switch (kp) {
+#define X(KPV) case KPV: return launch_chain_kp<KPV>(h, a);
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+}
+
 int32_t launch_loo_counts(gibbs_handle *h, const PrimArgs &a) {
     const int kp = (a.k + 1) / 2;
-    const int smem = warp_smem_bytes(a.s.row_words);
+    const int smem = team_smem_bytes(a.s.row_words, 1);
     switch (kp) {
 #define X(KPV)                                                                          \
     case KPV: {                                                                         \
@@ -200,7 +226,7 @@ int32_t launch_loo_counts(gibbs_handle *h, const PrimArgs &a) {
 
 int32_t launch_scan(gibbs_handle *h, const PrimArgs &a, int mode) {
     const int kp = (a.k + 1) / 2;
-    const int smem = warp_smem_bytes(a.s.row_words);
+    const int smem = team_smem_bytes(a.s.row_words, 1);
     switch (kp) {
 #define X(KPV)                                                                          \
     case KPV: {                                                                         \
@@ -219,7 +245,7 @@ int32_t launch_scan(gibbs_handle *h, const PrimArgs &a, int mode) {
 
 int32_t launch_all_counts(gibbs_handle *h, const DeviceSeqs &s, const int32_t *sites, int k, int32_t *out) {
     const int kp = (k + 1) / 2;
-    const int smem = warp_smem_bytes(s.row_words);
+    const int smem = team_smem_bytes(s.row_words, 1);
     switch (kp) {
 #define X(KPV)                                                                          \
     case KPV: {                                                                         \
@@ -261,7 +287,7 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
     if (rc) return rc;
     const int64_t total = offsets[n_seqs] - offsets[0];
     const int row_words = (int)(((max_len + 15) / 16 + 4 + 3) / 4 * 4);
-    if (warp_smem_bytes(row_words) > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequence too long for shared-memory staging");
+    if (team_smem_bytes(row_words, 1) > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequence too long for shared-memory staging");
     CUDA_TRY(h->ascii.reserve((size_t)(total > 0 ? total : 1)));
     CUDA_TRY(h->off.reserve((size_t)n_seqs + 1));
     CUDA_TRY(h->packed.reserve((size_t)n_seqs * row_words));
@@ -353,6 +379,10 @@ int32_t gibbs_create(const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs
         if (e2 != cudaSuccess) rc = fail(GIBBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(e2));
         h->own_stream = true;
     }
+    if (!rc) {
+        cudaError_t e3 = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+        if (e3 != cudaSuccess) rc = fail(GIBBS_ERR_CUDA, "device attribute: %s", cudaGetErrorString(e3));
+    }
     if (!rc) rc = upload(h, seqs, offsets, n_seqs);
     if (rc) {
         gibbs_destroy(h);
@@ -399,6 +429,13 @@ int32_t gibbs_set_stream(gibbs_handle *h, void *cuda_stream) {
 }
 
 int32_t gibbs_num_sequences(const gibbs_handle *h) { return h ? h->n : 0; }
+
+int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    if (warps != 0 && warps != 1 && warps != 4) return fail(GIBBS_ERR_ARG, "team size must be 0 (auto), 1 or 4 warps");
+    h->team_warps = warps;
+    return GIBBS_OK;
+}
 
 int32_t gibbs_synchronize(gibbs_handle *h) {
     if (!h) return fail(GIBBS_ERR_ARG, "null handle");
@@ -516,7 +553,6 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     a.s = dev_seqs(h);
     a.wtab = h->wtab.p;
     a.k = p->k;
-    a.phase_shifts = p->phase_shifts ? 1 : 0;
     a.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 1000000;
     a.fast_ok = fast_path_ok(h, p->k);
     a.sampler = p->sampler;
@@ -623,8 +659,10 @@ int32_t gibbs_fetch(gibbs_handle *h, int32_t *sites_out, double *scores_out, dou
         stats_out->sweeps = (int64_t)st[ST_SWEEPS];
         stats_out->exact_rescans = (int64_t)st[ST_EXACT_RESCANS];
         stats_out->capped_chains = (int64_t)st[ST_CAPPED];
+        stats_out->speculative_discards = (int64_t)st[ST_SPECULATED];
         stats_out->kernel_launches = h->run_launches + extra_launches;
         stats_out->fast_path = h->run_fast;
+        stats_out->team_warps = h->run_team;
         stats_out->kernel_ms = (double)ms;
     }
     return GIBBS_OK;

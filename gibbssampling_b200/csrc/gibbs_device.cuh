@@ -1,8 +1,10 @@
 // gibbssampling_b200/csrc/gibbs_device.cuh -- device-side building blocks (sm_100a only).
 //
-// One warp owns one chain (= one restart of the reference, fs:691-695). Everything a site update
-// needs lives in that warp's shared memory: the k x 4 count matrix, the float64 PWM column table,
-// the fixed-point log2-odds pair table and two TMA-staged rows of 2-bit packed sequence.
+// A team of T warps (one CTA) owns one chain (= one restart of the reference, fs:691-695). The unit
+// of work is one SITE UPDATE (leave-one-out PWM -> score every window of the held-out sequence ->
+// pick), and one WARP does a whole site update: its k x 4 PWM column table (float64), its
+// fixed-point log2-odds pair table and the 2-bit packed row it scans live in shared memory. The T
+// warps of a team work on T consecutive held-out sequences at once (see gibbs_kernels.cuh).
 //
 // Exactness strategy (DESIGN.md "Kernels"): every window is first scored with an int32
 // fixed-point sum of log2-odds looked up two bases at a time (one LDS + half an IADD3 per
@@ -19,12 +21,12 @@ namespace gibbs {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int LG_FRAC_BITS = 11;          // log2-odds fixed point: 2^-11 units ...
 constexpr int KEY_IDX_BITS = 8;           // ... shifted left by 8 to leave room for a window index
-constexpr int LG_ENTRY_SHIFT = LG_FRAC_BITS + KEY_IDX_BITS;
 constexpr int MAX_COLS = 32;              // GIBBS_MAX_K
 constexpr double LN2 = 0.6931471805599453; // log 2.0 as float64 (FSharpAux log2 = ln x / ln 2)
 
 enum ShiftMode { SHIFT_NONE = 0, SHIFT_LEFT = 1, SHIFT_RIGHT = 2 };
-enum StatSlot { ST_SITE_UPDATES = 0, ST_WINDOW_SCORES = 1, ST_SWEEPS = 2, ST_EXACT_RESCANS = 3, ST_CAPPED = 4, ST_NSLOTS = 8 };
+enum StatSlot { ST_SITE_UPDATES = 0, ST_WINDOW_SCORES = 1, ST_SWEEPS = 2, ST_EXACT_RESCANS = 3, ST_CAPPED = 4,
+                ST_SPECULATED = 5, ST_NSLOTS = 8 };
 
 // one entry per (count, base): the odds ratio W = ((c + pc) / den) / q[b] of fs:260 + fs:286 as
 // float64, and round(log2 W * 2^11) << 8 for the ranking pass
@@ -45,7 +47,6 @@ struct ChainArgs {
     DeviceSeqs s;
     const WEnt *wtab;       // [n][4]
     int32_t k;
-    int32_t phase_shifts;
     int32_t max_sweeps;
     int32_t fast_ok;
     int32_t sampler;
@@ -66,33 +67,62 @@ struct ChainArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// per-warp shared memory
+// shared memory: per-warp tables + per-team state
 // ------------------------------------------------------------------------------------------------
-struct WarpSmem {
-    uint64_t *bar;   // [2] mbarriers of the two row buffers
-    int32_t *total;  // [32*4] counts, entry j*4+b
-    int32_t *lgcol;  // [32*4] fixed-point log2 odds per column
-    int32_t *ptab;   // [16*16] pair table: ptab[p*16 + nib] = lgcol[2p][nib&3] + lgcol[2p+1][nib>>2]
-    double *wcol;    // [32*4] float64 odds per column
-    double *scratch; // [32]
-    uint32_t *row[2];
+struct WarpTables {       // private to the warp that runs a site update
+    double *wcol;         // [32*4] float64 odds per column, entry j*4+b
+    int32_t *ptab;        // [16*16] pair table: ptab[p*16 + nib] = lgcol[2p][nib&3] + lgcol[2p+1][nib>>2]
+    int32_t *lgcol;       // [32*4] fixed-point log2 odds per column
+    int32_t *counts;      // [32*4] leave-one-out counts of the random-init phase
+};
+constexpr int WARP_TABLE_BYTES = 1024 + 1024 + 512 + 512;
+
+struct TeamSmem {
+    uint64_t *bar;        // [ring] mbarriers of the staged rows
+    int32_t *total;       // [32*4] counts over ALL current sites of the chain
+    int32_t *flags;       // [8]  per-warp outcome of a round
+    double *blk_hv;       // [2][32] state of two 32-sequence blocks
+    int32_t *blk_site;    // [2][32]
+    int32_t *blk_len;     // [2][32]
+    unsigned char *warp_tables; // T x WARP_TABLE_BYTES
+    uint32_t *row0;       // ring of staged rows, slot s at row0 + s * row_words
 };
 
-constexpr int WARP_SMEM_FIXED = 16 + 512 + 512 + 1024 + 1024 + 256; // bytes before the row buffers
+constexpr int MAX_RING = 16;
+constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 32 + 512 + 256 + 256; // bar, total, flags, blk_hv, blk_site, blk_len
 
-__host__ __device__ inline int warp_smem_bytes(int row_words) { return WARP_SMEM_FIXED + 2 * row_words * 4; }
+__host__ __device__ inline int ring_slots(int team_warps) { return 2 * team_warps < 4 ? 4 : 2 * team_warps; }
+__host__ __device__ inline int team_smem_bytes(int row_words, int team_warps) {
+    return TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES + ring_slots(team_warps) * row_words * 4;
+}
 
-__device__ __forceinline__ WarpSmem carve_smem(unsigned char *base, int row_words) {
-    WarpSmem s;
+__device__ __forceinline__ TeamSmem carve_smem(unsigned char *base, int team_warps) {
+    TeamSmem s;
     s.bar = reinterpret_cast<uint64_t *>(base);
-    s.total = reinterpret_cast<int32_t *>(base + 16);
-    s.lgcol = reinterpret_cast<int32_t *>(base + 16 + 512);
-    s.ptab = reinterpret_cast<int32_t *>(base + 16 + 1024);
-    s.wcol = reinterpret_cast<double *>(base + 16 + 2048);
-    s.scratch = reinterpret_cast<double *>(base + 16 + 3072);
-    s.row[0] = reinterpret_cast<uint32_t *>(base + WARP_SMEM_FIXED);
-    s.row[1] = s.row[0] + row_words;
+    s.total = reinterpret_cast<int32_t *>(base + 128);
+    s.flags = reinterpret_cast<int32_t *>(base + 640);
+    s.blk_hv = reinterpret_cast<double *>(base + 672);
+    s.blk_site = reinterpret_cast<int32_t *>(base + 1184);
+    s.blk_len = reinterpret_cast<int32_t *>(base + 1440);
+    s.warp_tables = base + TEAM_FIXED_BYTES;
+    s.row0 = reinterpret_cast<uint32_t *>(base + TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES);
     return s;
+}
+
+__device__ __forceinline__ WarpTables warp_tables(const TeamSmem &s, int warp) {
+    unsigned char *b = s.warp_tables + warp * WARP_TABLE_BYTES;
+    WarpTables t;
+    t.wcol = reinterpret_cast<double *>(b);
+    t.ptab = reinterpret_cast<int32_t *>(b + 1024);
+    t.lgcol = reinterpret_cast<int32_t *>(b + 2048);
+    t.counts = reinterpret_cast<int32_t *>(b + 2560);
+    return t;
+}
+
+template <int T>
+__device__ __forceinline__ void team_sync() {
+    if (T == 1) __syncwarp();
+    else __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -126,51 +156,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
-// Double-buffered row staging: one elected lane issues the bulk copy of the NEXT held-out row while
-// the warp scores the current one.
-struct RowPipe {
-    uint64_t *bar;    // [2]
-    uint32_t *row0;   // slot s lives at row0 + s * row_words
+// Ring of staged rows. Visits are numbered 0, 1, 2, ... over the whole chain (visit v scans sequence
+// (first + v) mod N: every sweep walks n = 0..N-1), visit v lives in slot v % R and completes phase
+// (v / R) & 1 of that slot's mbarrier, so any warp can find and wait for its row from v alone. One
+// elected thread keeps the rows of visits [head, head + R) in flight with cp.async.bulk (TMA).
+struct RowRing {
+    uint64_t *bar;
+    uint32_t *row0;
     const uint32_t *gpacked;
-    int row_words;
-    uint32_t phase;   // bit s = parity to wait for on slot s
-    uint32_t visit;
+    int row_words, n_seqs, slots;
+    long long issued; // visits [0, issued) have been requested (meaningful on thread 0 only)
 
-    __device__ __forceinline__ void init(const WarpSmem &s, const DeviceSeqs &d, int lane) {
+    __device__ __forceinline__ void init(const TeamSmem &s, const DeviceSeqs &d, int r, int tid) {
         bar = s.bar;
-        row0 = s.row[0];
+        row0 = s.row0;
         gpacked = d.packed;
         row_words = d.row_words;
-        phase = 0;
-        visit = 0;
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            mbar_init(bar + 1, 1);
+        n_seqs = d.n;
+        slots = r;
+        issued = 0;
+        if (tid == 0) {
+            for (int i = 0; i < r; ++i) mbar_init(bar + i, 1);
             fence_barrier_init();
         }
-        __syncwarp();
     }
-    __device__ __forceinline__ void issue(int slot, int seq, int lane) {
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)row_words * 4u;
+    // thread 0 only: request the rows of visits [issued, upto); sequence of visit v = (first + v) % n_seqs
+    __device__ __forceinline__ void fill(long long upto, int first) {
+        const uint32_t bytes = (uint32_t)row_words * 4u;
+        for (; issued < upto; ++issued) {
+            const int slot = (int)(issued % slots);
+            const int seq = (int)((first + issued) % n_seqs);
             mbar_expect_tx(bar + slot, bytes);
             bulk_g2s(row0 + slot * row_words, gpacked + (size_t)seq * row_words, bytes, bar + slot);
         }
     }
-    // row of the current visit is (or was prefetched) in slot visit&1; prefetch `next` into the other slot
-    __device__ __forceinline__ const uint32_t *acquire(int next, int lane) {
-        const int slot = visit & 1;
-        mbar_wait(bar + slot, (phase >> slot) & 1u);
-        phase ^= 1u << slot;
-        __syncwarp(); // every lane is done reading the other slot (previous visit)
-        issue(slot ^ 1, next, lane);
-        ++visit;
+    __device__ __forceinline__ const uint32_t *wait(long long v) const {
+        const int slot = (int)(v % slots);
+        mbar_wait(bar + slot, (uint32_t)((v / slots) & 1));
         return row0 + slot * row_words;
-    }
-    __device__ __forceinline__ void drain() { // one prefetch is always outstanding
-        const int slot = visit & 1;
-        mbar_wait(bar + slot, (phase >> slot) & 1u);
-        phase ^= 1u << slot;
     }
 };
 
@@ -225,7 +248,7 @@ __device__ __forceinline__ int shifted_site(int pos, int len, int k, int mode) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-lane packed histogram of k-mers: 4 byte-wide counters (A,C,G,T) per column register
+// per-thread packed histogram of k-mers: 4 byte-wide counters (A,C,G,T) per column register
 // (replaces createPFMOf + fusePositionFrequencyMatrices, fs:211-226)
 // ------------------------------------------------------------------------------------------------
 template <int KP>
@@ -235,69 +258,77 @@ struct Hist {
 #pragma unroll
         for (int j = 0; j < 2 * KP; ++j) c[j] = 0;
     }
-    __device__ __forceinline__ void add(uint64_t kmer) {
+    __device__ __forceinline__ void add(uint64_t kmer, uint32_t inc) { // inc = 1 (count it) or 0
 #pragma unroll
         for (int j = 0; j < 2 * KP; ++j) {
             const uint32_t b8 = ((uint32_t)(kmer >> (2 * j)) & 3u) * 8u;
-            c[j] += 1u << b8;
+            c[j] += inc << b8;
         }
     }
-    // at most 255 adds per lane since the last clear; total[] += warp sums
-    __device__ __forceinline__ void flush_add(int32_t *total, int k, int lane) {
+    // at most 255 adds per thread since the last clear; dst[] += warp sums. Bytes are widened to
+    // 16-bit fields (32 lanes x 255 < 65536) so one REDUX.SUM reduces two counters at once.
+    // ATOMIC: several warps add into the same dst.
+    template <bool ATOMIC>
+    __device__ __forceinline__ void flush_add(int32_t *dst, int k, int lane) {
 #pragma unroll
         for (int j = 0; j < 2 * KP; ++j) {
             if (j < k) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t s = __reduce_add_sync(FULL, (c[j] >> (8 * b)) & 255u);
-                    if (lane == ((j * 4 + b) & 31)) total[j * 4 + b] += (int32_t)s;
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t s = __reduce_add_sync(FULL, (c[j] >> (8 * h)) & 0x00FF00FFu);
+                    if (lane == ((2 * j + h) & 31)) {
+                        if (!ATOMIC) {
+                            dst[j * 4 + h] += (int32_t)(s & 0xFFFFu);
+                            dst[j * 4 + h + 2] += (int32_t)(s >> 16);
+                        } else {
+                            atomicAdd(&dst[j * 4 + h], (int32_t)(s & 0xFFFFu));
+                            atomicAdd(&dst[j * 4 + h + 2], (int32_t)(s >> 16));
+                        }
+                    }
                 }
             }
             c[j] = 0;
         }
-        __syncwarp();
     }
 };
 
-__device__ __forceinline__ void zero_total(int32_t *total, int lane) {
-#pragma unroll
-    for (int e = lane; e < MAX_COLS * 4; e += 32) total[e] = 0;
-    __syncwarp();
-}
-
 // counts over the sites of all sequences except `exclude` (sites < 0 = no site), positions shifted
-// by `mode`: the fused PFM of fs:392-396 (exclude = held-out) or the all-sites total
-template <int KP>
+// by `mode`: the fused PFM of fs:392-396 (exclude = held-out) or the all-sites total. All T warps
+// of the team take part; ends with a team sync.
+template <int KP, int T>
 __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *sites, int exclude, int k, int mode,
-                                            int32_t *total, int lane) {
-    zero_total(total, lane);
+                                            int32_t *total, int tid) {
+    constexpr int THREADS = 32 * T;
+    for (int e = tid; e < MAX_COLS * 4; e += THREADS) total[e] = 0;
+    team_sync<T>();
     Hist<KP> h;
     h.clear();
-    const int iters = (s.n + 31) >> 5;
-    for (int it0 = 0; it0 < iters; it0 += 255) { // byte counters hold 255 adds per lane
+    const int iters = (s.n + THREADS - 1) / THREADS;
+    for (int it0 = 0; it0 < iters; it0 += 255) { // byte counters hold 255 adds per thread
         const int it1 = min(iters, it0 + 255);
         for (int it = it0; it < it1; ++it) {
-            const int i = it * 32 + lane;
+            const int i = it * THREADS + tid;
             if (i < s.n && i != exclude) {
                 const int site = __ldcg(sites + i);
                 if (site >= 0) {
                     const int pos = shifted_site(site, __ldg(s.len + i), k, mode);
-                    h.add(kmer_global<KP>(s.packed + (size_t)i * s.row_words, pos));
+                    h.add(kmer_global<KP>(s.packed + (size_t)i * s.row_words, pos), 1u);
                 }
             }
         }
-        h.flush_add(total, k, lane);
+        h.template flush_add<(T > 1)>(total, k, tid & 31);
     }
+    team_sync<T>();
 }
 
 // ------------------------------------------------------------------------------------------------
-// PWM tables for one held-out sequence
+// PWM tables for one held-out sequence (one warp)
 // ------------------------------------------------------------------------------------------------
-// Leave-one-out count c = total - own, then W(c, b) and its fixed-point log2 are gathered from the
+// Leave-one-out count c = counts - own, then W(c, b) and its fixed-point log2 are gathered from the
 // precomputed table (normalizePPM fs:255-261 + createPositionWeightMatrix fs:282-287 evaluated once
 // per distinct count instead of once per window).
 template <int KP>
-__device__ __forceinline__ void build_tables(const WarpSmem &S, bool has_own, uint64_t own, int k,
+__device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
                                              const WEnt *__restrict__ wtab, int lane) {
 #pragma unroll
     for (int e = lane; e < 8 * KP; e += 32) {
@@ -305,20 +336,20 @@ __device__ __forceinline__ void build_tables(const WarpSmem &S, bool has_own, ui
         double w = 1.0;
         int32_t lg = 0;
         if (j < k) {
-            int c = S.total[e];
+            int c = counts[e];
             if (has_own && (int)((own >> (2 * j)) & 3u) == b) c -= 1;
             const int4 raw = __ldg(reinterpret_cast<const int4 *>(wtab + (size_t)c * 4 + b));
             w = __hiloint2double(raw.y, raw.x);
             lg = raw.z;
         }
-        S.wcol[e] = w;
-        S.lgcol[e] = lg;
+        W.wcol[e] = w;
+        W.lgcol[e] = lg;
     }
     __syncwarp();
 #pragma unroll
     for (int idx = lane; idx < 16 * KP; idx += 32) {
         const int p = idx >> 4, nib = idx & 15;
-        S.ptab[idx] = S.lgcol[(2 * p) * 4 + (nib & 3)] + S.lgcol[(2 * p + 1) * 4 + (nib >> 2)];
+        W.ptab[idx] = W.lgcol[(2 * p) * 4 + (nib & 3)] + W.lgcol[(2 * p + 1) * 4 + (nib >> 2)];
     }
     __syncwarp();
 }
@@ -339,13 +370,15 @@ __device__ __forceinline__ double exact_window(const uint32_t *row, int w, int k
     return p;
 }
 
+__device__ __forceinline__ bool better(double ohv, int ow, double hv, int w) { return ohv > hv || (ohv == hv && ow < w); }
+
 // (max value, lowest index) over the warp; every lane ends with the result
 __device__ __forceinline__ void warp_argmax(double &hv, int &w) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         const double ohv = __shfl_xor_sync(FULL, hv, o);
         const int ow = __shfl_xor_sync(FULL, w, o);
-        if (ohv > hv || (ohv == hv && ow < w)) {
+        if (better(ohv, ow, hv, w)) {
             hv = ohv;
             w = ow;
         }
@@ -406,38 +439,11 @@ struct ScanGeom {
     static constexpr int CPS = 32 * RPS;        // chunks per segment
 };
 
-// one segment: chunks [c_begin, c_end), at most CPS of them
-template <int KP, int CH>
-__device__ __forceinline__ void scan_segment(const uint32_t *row, int W, const int32_t *ptab, int c_begin, int c_end,
-                                             int lane, int32_t &m1, int32_t &m2) {
-    using G = ScanGeom<KP, CH>;
-    m1 = INT32_MIN;
-    m2 = INT32_MIN;
-    int r = 0;
-    for (int c = c_begin + lane; c < c_end; c += 32, ++r) {
-        const int base0 = c * CH;
-        const uint32_t *p = row + (base0 >> 4);
-        uint32_t a[G::NWA + 1], b[G::NWA];
-        if (CH == 16) {
-#pragma unroll
-            for (int i = 0; i < G::NWA; ++i) a[i] = p[i];
-        } else {
-            const int sh = (base0 & 15) * 2;
-            uint32_t raw[G::NWA + 1];
-#pragma unroll
-            for (int i = 0; i <= G::NWA; ++i) raw[i] = p[i];
-#pragma unroll
-            for (int i = 0; i < G::NWA; ++i) a[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
-        }
-        a[G::NWA] = 0;
-#pragma unroll
-        for (int i = 0; i < G::NWA; ++i) b[i] = __funnelshift_r(a[i], a[i + 1], 2);
-        const int lim = W - base0;
-        const int idx0 = 255 - r * CH;
-        if (lim >= CH) score_chunk<KP, CH, false>(a, b, ptab, idx0, lim, m1, m2);
-        else score_chunk<KP, CH, true>(a, b, ptab, idx0, lim, m1, m2);
-    }
-}
+// first window of chunk c: the last chunk is pulled back so that every chunk is full (its overlap
+// with the previous chunk only rescans windows, harmless for a maximum); rows shorter than one
+// chunk (W < CH) are the single masked case
+template <int CH>
+__device__ __forceinline__ int chunk_base(int c, int W) { return max(0, min(c * CH, W - CH)); }
 
 // per-lane best key M1 (from segment S1), second best M2, over all windows of the row
 template <int KP, int CH>
@@ -449,8 +455,25 @@ __device__ __forceinline__ void scan_fast(const uint32_t *row, int W, const int3
     M2 = INT32_MIN;
     S1 = 0;
     for (int seg = 0, c0 = 0; c0 < n_chunks; ++seg, c0 += G::CPS) {
-        int32_t m1, m2;
-        scan_segment<KP, CH>(row, W, ptab, c0, min(n_chunks, c0 + G::CPS), lane, m1, m2);
+        int32_t m1 = INT32_MIN, m2 = INT32_MIN;
+        const int c_end = min(n_chunks, c0 + G::CPS);
+        int r = 0;
+        for (int c = c0 + lane; c < c_end; c += 32, ++r) {
+            const int base0 = chunk_base<CH>(c, W);
+            const uint32_t *p = row + (base0 >> 4);
+            const int sh = (base0 & 15) * 2;
+            uint32_t raw[G::NWA + 1], a[G::NWA + 1], b[G::NWA];
+#pragma unroll
+            for (int i = 0; i <= G::NWA; ++i) raw[i] = p[i];
+#pragma unroll
+            for (int i = 0; i < G::NWA; ++i) a[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+            a[G::NWA] = 0;
+#pragma unroll
+            for (int i = 0; i < G::NWA; ++i) b[i] = __funnelshift_r(a[i], a[i + 1], 2);
+            const int idx0 = 255 - r * CH;
+            if (W >= CH) score_chunk<KP, CH, false>(a, b, ptab, idx0, CH, m1, m2); // warp-uniform branch
+            else score_chunk<KP, CH, true>(a, b, ptab, idx0, W, m1, m2);
+        }
         if (m1 > M1) {
             M2 = max(max(M2, M1), m2);
             M1 = m1;
@@ -462,21 +485,21 @@ __device__ __forceinline__ void scan_fast(const uint32_t *row, int W, const int3
 }
 
 template <int KP, int CH>
-__device__ __forceinline__ int decode_window(int32_t key, int seg, int lane) {
+__device__ __forceinline__ int decode_window(int32_t key, int seg, int lane, int W) {
     using G = ScanGeom<KP, CH>;
     const int local = 255 - (key & 255);
     const int r = local / CH, i = local % CH;
-    return (seg * G::CPS + lane + 32 * r) * CH + i;
+    return chunk_base<CH>(seg * G::CPS + lane + 32 * r, W) + i;
 }
 
 // getBestPWMSsWithBPV (fs:301-314) for the staged row: (raw float64 maximum, first argmax).
-// Returns true when the all-windows float64 path had to be taken.
+// Returns true when the all-windows float64 path has to be taken.
 template <int KP, int CH>
-__device__ __forceinline__ bool pick_argmax_ch(const WarpSmem &S, const uint32_t *row, int W, int k, int lane,
+__device__ __forceinline__ bool pick_argmax_ch(const WarpTables &T, const uint32_t *row, int W, int k, int lane,
                                                double &hv_out, int &w_out) {
     int32_t M1, M2;
     int S1;
-    scan_fast<KP, CH>(row, W, S.ptab, lane, M1, M2, S1);
+    scan_fast<KP, CH>(row, W, T.ptab, lane, M1, M2, S1);
     const int32_t M = __reduce_max_sync(FULL, M1);
     // |key/256 - true log2 score * 2^11| <= k/2 units for every window, so any window whose exact
     // product can reach the maximum has key >= M - (k + 1) units (index bits: 255 more)
@@ -487,8 +510,8 @@ __device__ __forceinline__ bool pick_argmax_ch(const WarpSmem &S, const uint32_t
     double p = 0.0;
     int w = INT32_MAX;
     if (is_cand) {
-        w = decode_window<KP, CH>(M1, S1, lane);
-        p = exact_window<KP>(row, w, k, S.wcol);
+        w = decode_window<KP, CH>(M1, S1, lane, W);
+        p = exact_window<KP>(row, w, k, T.wcol);
     }
     if (__popc(cand) == 1) {
         const int src = __ffs(cand) - 1;
@@ -503,15 +526,15 @@ __device__ __forceinline__ bool pick_argmax_ch(const WarpSmem &S, const uint32_t
 }
 
 template <int KP>
-__device__ __forceinline__ bool pick_argmax(const WarpSmem &S, const uint32_t *row, int W, int k, int fast_ok, int lane,
+__device__ __forceinline__ bool pick_argmax(const WarpTables &T, const uint32_t *row, int W, int k, int fast_ok, int lane,
                                             double &hv_out, int &w_out) {
     bool slow = !fast_ok;
     if (!slow) {
-        if (W > 256) slow = pick_argmax_ch<KP, 16>(S, row, W, k, lane, hv_out, w_out);
-        else if (W > 128) slow = pick_argmax_ch<KP, 8>(S, row, W, k, lane, hv_out, w_out);
-        else slow = pick_argmax_ch<KP, 4>(S, row, W, k, lane, hv_out, w_out);
+        if (W > 256) slow = pick_argmax_ch<KP, 16>(T, row, W, k, lane, hv_out, w_out);
+        else if (W > 128) slow = pick_argmax_ch<KP, 8>(T, row, W, k, lane, hv_out, w_out);
+        else slow = pick_argmax_ch<KP, 4>(T, row, W, k, lane, hv_out, w_out);
     }
-    if (slow) scan_exact_all<KP>(row, W, k, S.wcol, lane, hv_out, w_out);
+    if (slow) scan_exact_all<KP>(row, W, k, T.wcol, lane, hv_out, w_out);
     return slow;
 }
 

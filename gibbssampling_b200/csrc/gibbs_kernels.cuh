@@ -75,15 +75,18 @@ __global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// uniform stream -> leave-one-out counts of the random initial sites (fs:418-426)
+// uniform stream -> leave-one-out counts of the random initial sites (fs:418-426), one warp
 // ------------------------------------------------------------------------------------------------
 // Draw index of (held-out n, other sequence i) = n (N-1) + rank of i among the others, the order in
-// which the reference's Array.map consumes System.Random (fs:419-421, quirk A.6-5).
+// which the reference's Array.map consumes System.Random (fs:419-421, quirk A.6-5). Each lane
+// takes one Philox block (4 draws) per round; the 4 draws are processed branch-free so their
+// length / row loads overlap.
 template <int KP>
 __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
-                                                  const WarpSmem &S, int lane) {
+                                                  int32_t *counts, int lane) {
     const int N = a.s.n, k = a.k;
-    zero_total(S.total, lane);
+    for (int e = lane; e < MAX_COLS * 4; e += 32) counts[e] = 0;
+    __syncwarp();
     if (N < 2) return;
     const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
     const uint64_t d_end = base + (uint64_t)(N - 1);
@@ -95,63 +98,80 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
         const int it1 = min(iters, it0 + 63);
         for (int it = it0; it < it1; ++it) {
             const uint64_t blk = blk0 + (uint64_t)it * 32 + lane;
-            if (blk < blk1) {
-                uint32_t wd[4] = {0, 0, 0, 0};
-                if (a.rng_mode == 0) {
-                    const uint4 r = philox4x32_10(
-                        make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
-                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-                    wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
-                }
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const uint64_t d = blk * 4 + x;
-                    if (d >= base && d < d_end) {
-                        const int r = (int)(d - base);
-                        const int i = r + (r >= n ? 1 : 0);
-                        const int range = __ldg(a.s.len + i) - k + 1;
-                        int pos;
-                        if (a.rng_mode == 0) {
-                            pos = (int)__umulhi(wd[x], (uint32_t)range); // floor(word * 2^-32 * range), exact
-                        } else {
-                            const double u = ((int64_t)d < a.uniforms_per_chain)
-                                                 ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
-                                                 : 0.0;
-                            pos = (int)(u * (double)range); // rnd.Next(0, L-k+1), fs:145
-                            pos = min(max(pos, 0), range - 1); // memory safety for u outside [0,1)
-                        }
-                        h.add(kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos));
-                    }
-                }
+            uint32_t wd[4] = {0, 0, 0, 0};
+            if (a.rng_mode == 0) {
+                const uint4 r = philox4x32_10(
+                    make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
             }
+            uint64_t kmer[4];
+            uint32_t valid[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const uint64_t d = blk * 4 + x;
+                const bool ok = blk < blk1 && d >= base && d < d_end;
+                valid[x] = ok ? 1u : 0u;
+                const int r = ok ? (int)(d - base) : 0;
+                const int i = r + (r >= n ? 1 : 0); // always a valid sequence index (N >= 2)
+                const int range = __ldg(a.s.len + i) - k + 1;
+                int pos;
+                if (a.rng_mode == 0) {
+                    pos = (int)__umulhi(wd[x], (uint32_t)range); // floor(word * 2^-32 * range), exact
+                } else {
+                    const double u = (ok && (int64_t)d < a.uniforms_per_chain)
+                                         ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
+                                         : 0.0;
+                    pos = (int)(u * (double)range);      // rnd.Next(0, L-k+1), fs:145
+                    pos = min(max(pos, 0), range - 1);   // memory safety for u outside [0,1)
+                }
+                kmer[x] = kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) h.add(kmer[x], valid[x]);
         }
-        h.flush_add(S.total, k, lane);
+        h.template flush_add<false>(counts, k, lane);
     }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
-// the chain kernel: one warp = one restart of SiteSampler.doSiteSamplingWithBPV (fs:691-695)
+// the chain kernel: one team (CTA of T warps) = one restart of SiteSampler.doSiteSamplingWithBPV
+// (fs:691-695)
 // ------------------------------------------------------------------------------------------------
-template <int KP>
-__global__ void __launch_bounds__(32) chain_kernel(const ChainArgs a) {
+// A ROUND = T consecutive held-out sequences n0 .. n0+T-1, one per warp, scored concurrently.
+//   random starts (fs:412) and shift sweeps (fs:350 / fs:318): every site update of a sweep reads
+//     the same snapshot, so all T results of a round are committed.
+//   greedy sweeps (fs:381) are in-place: sequence n must see the sites accepted for 0..n-1. The round
+//     is speculative: results are committed in order up to and including the first warp whose accepted
+//     update MOVES a site (that changes the counts); later warps of the round are discarded and redone
+//     in the next round, which starts right after the mover. The committed sequence of site updates is
+//     therefore exactly the reference's sequential sweep.
+template <int KP, int T>
+__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
+    constexpr int THREADS = 32 * T;
+    constexpr int R = (2 * T < 4) ? 4 : 2 * T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chain = blockIdx.x;
-    const WarpSmem S = carve_smem(smem_raw, a.s.row_words);
-    RowPipe pipe;
-    pipe.init(S, a.s, lane);
+    const TeamSmem S = carve_smem(smem_raw, T);
+    const WarpTables WT = warp_tables(S, warp);
 
     const int N = a.s.n, k = a.k;
     int32_t *sites = a.sites + (size_t)chain * N;
     double *hv = a.hv + (size_t)chain * N;
+    double *scores = a.scores + (size_t)chain * N;
     const uint64_t chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
 
-    unsigned long long st_updates = 0, st_windows = 0, st_sweeps = 0, st_slow = 0;
-    int capped = 0;
+    RowRing ring;
+    ring.init(S, a.s, R, tid);
+    team_sync<T>();
+    if (tid == 0) ring.fill(R, 0);
 
-    pipe.issue(0, 0, lane);
+    unsigned long long st_updates = 0, st_windows = 0, st_slow = 0, st_spec = 0;
+    int st_sweeps = 0, capped = 0;
+    long long vbase = 0; // visit index of n = 0 in the current sweep
 
-    double *scores = a.scores + (size_t)chain * N;
     int phase = next_phase(PH_INIT, a.phase_mask);
     int sweeps_in_phase = 0;
     while (phase != PH_DONE) {
@@ -159,65 +179,104 @@ __global__ void __launch_bounds__(32) chain_kernel(const ChainArgs a) {
         // all-sites counts: once when the greedy phase starts (then kept incrementally: -old site,
         // +new site), once per sweep for the shift phases (they read the shifted snapshot, fs:357)
         if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && sweeps_in_phase == 0))
-            site_counts<KP>(a.s, sites, -1, k, mode, S.total, lane);
-        bool changed = false;
-        int site_next = 0;
-        double hv_next = 0.0;
-        if (phase != PH_INIT) {
-            site_next = __ldcg(sites);
-            hv_next = __ldcg(hv);
-        }
-        for (int n = 0; n < N; ++n) {
-            const uint32_t *row = pipe.acquire(n + 1 < N ? n + 1 : 0, lane);
-            const int len_n = __ldg(a.s.len + n);
-            const int Wn = len_n - k + 1;
-            int site_n = 0;
-            double hv_n = 0.0;
-            uint64_t own = 0;
-            if (phase == PH_INIT) {
-                random_loo_counts<KP>(a, chain_uid, chain, n, S, lane);
-            } else {
-                site_n = site_next;
-                hv_n = hv_next;
-                if (n + 1 < N) {
-                    site_next = __ldcg(sites + n + 1);
-                    hv_next = __ldcg(hv + n + 1);
+            site_counts<KP, T>(a.s, sites, -1, k, mode, S.total, tid);
+        // state of two 32-sequence blocks (lengths, sites, raw scores): coalesced loads, kept one block ahead
+        auto load_block = [&](int b) {
+            const int i = b * 32 + tid;
+            if (tid < 32 && i < N) {
+                const int o = (b & 1) * 32 + tid;
+                S.blk_len[o] = __ldg(a.s.len + i);
+                if (phase != PH_INIT) {
+                    S.blk_site[o] = __ldcg(sites + i);
+                    S.blk_hv[o] = __ldcg(hv + i);
                 }
-                own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
             }
-            build_tables<KP>(S, phase != PH_INIT, own, k, a.wtab, lane);
-            double p;
-            int w;
-            const bool slow = pick_argmax<KP>(S, row, Wn, k, a.fast_ok, lane, p, w);
-            st_updates += 1;
-            st_windows += (unsigned long long)Wn;
-            st_slow += slow ? 1 : 0;
-            if (phase == PH_INIT) {
-                if (lane == 0) {
-                    sites[n] = w;
-                    hv[n] = p;
+        };
+        load_block(0);
+        load_block(1);
+        team_sync<T>();
+        bool changed = false;
+        int cur_blk = 0;
+        int n0 = 0;
+        while (n0 < N) {
+            if ((n0 >> 5) != cur_blk) { // entering a new block: fetch the one after it (not read this round)
+                cur_blk = n0 >> 5;
+                load_block(cur_blk + 1);
+            }
+            const int n = n0 + warp;
+            const bool active = n < N;
+            int flag = 0, site_n = 0, w = 0, Wn = 0;
+            double p = 0.0;
+            uint64_t own = 0;
+            const uint32_t *row = nullptr;
+            if (active) {
+                row = ring.wait(vbase + n);
+                const int o = ((n >> 5) & 1) * 32 + (n & 31);
+                const int len_n = S.blk_len[o];
+                Wn = len_n - k + 1;
+                double hv_n = 0.0;
+                if (phase == PH_INIT) {
+                    random_loo_counts<KP>(a, chain_uid, chain, n, WT.counts, lane);
+                    build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+                } else {
+                    site_n = S.blk_site[o];
+                    hv_n = S.blk_hv[o];
+                    own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
+                    build_tables<KP>(WT, S.total, true, own, k, a.wtab, lane);
                 }
-            } else if (score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0)) { // fs:402
-                if (w != site_n) {
-                    changed = true;
-                    if (phase == PH_GREEDY) { // in-place sweep: later n see the new site (fs:388)
-                        const uint64_t neu = kmer_shared<KP>(row, w);
-                        if (lane < k) {
-                            const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
-                            if (bo != bn) {
-                                S.total[lane * 4 + bo] -= 1;
-                                S.total[lane * 4 + bn] += 1;
+                const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
+                bool accept = true, moved = false;
+                if (phase != PH_INIT) {
+                    accept = score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0); // fs:402
+                    moved = accept && (w != site_n);
+                }
+                flag = (accept ? 1 : 0) | (moved ? 2 : 0) | (slow ? 4 : 0);
+            }
+            if (lane == 0) S.flags[warp] = flag;
+            team_sync<T>();
+            int first_mover = T; // greedy only: later warps of the round saw stale counts
+            bool any_moved = false;
+#pragma unroll
+            for (int t = T - 1; t >= 0; --t) {
+                const bool mv = (S.flags[t] & 2) != 0;
+                if (mv && phase == PH_GREEDY) first_mover = t;
+                any_moved |= mv;
+            }
+            const int last_commit = min(first_mover, T - 1);
+            if (phase == PH_GREEDY) {
+                any_moved = first_mover < T;
+            }
+            changed |= any_moved;
+            if (active) {
+                if (warp <= last_commit) {
+                    st_updates += 1;
+                    st_windows += (unsigned long long)Wn;
+                    st_slow += (flag & 4) ? 1 : 0;
+                    if (flag & 1) {
+                        if (lane == 0) {
+                            sites[n] = w;
+                            hv[n] = p;
+                        }
+                        if (phase == PH_GREEDY && (flag & 2)) { // in-place sweep: later n see the new site (fs:388)
+                            const uint64_t neu = kmer_shared<KP>(row, w);
+                            if (lane < k) {
+                                const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
+                                if (bo != bn) {
+                                    S.total[lane * 4 + bo] -= 1;
+                                    S.total[lane * 4 + bn] += 1;
+                                }
                             }
                         }
                     }
-                }
-                if (lane == 0) {
-                    sites[n] = w;
-                    hv[n] = p;
+                } else {
+                    st_spec += 1;
                 }
             }
-            __syncwarp();
+            n0 += min(last_commit + 1, N - n0);
+            team_sync<T>(); // counts updated; rows of the committed visits are free
+            if (tid == 0) ring.fill(vbase + n0 + R, 0);
         }
+        vbase += N;
         st_sweeps += 1;
         if (phase == PH_INIT) {
             phase = next_phase(PH_GREEDY, a.phase_mask);
@@ -235,23 +294,27 @@ __global__ void __launch_bounds__(32) chain_kernel(const ChainArgs a) {
             phase = next_phase(phase + 1, a.phase_mask);
         }
     }
-    pipe.drain();
-    __syncwarp();
+    if (tid == 0) // the ring always has R rows in flight: let them land before the CTA exits
+        for (int i = 0; i < R; ++i) ring.wait(vbase + i);
+    team_sync<T>();
 
     // (log2 highValue, highIndex), fs:303
-    for (int n = lane; n < N; n += 32) {
+    for (int n = tid; n < N; n += THREADS) {
         const double v = __ldcg(hv + n);
         if (v == v) scores[n] = log2_ref(v); // NaN = untouched caller-supplied entry keeps its score
     }
-    __syncwarp();
+    team_sync<T>();
     if (lane == 0) {
+        atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
+        atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
+        atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
+        atomicAdd(a.stats + ST_SPECULATED, st_spec);
+    }
+    if (tid == 0) {
         double sum = 0.0; // Array.sum, left to right (fs:445)
         for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(scores + n));
         a.sums[chain] = sum;
-        atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
-        atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
-        atomicAdd(a.stats + ST_SWEEPS, st_sweeps);
-        atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
+        atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
         atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
     }
 }
@@ -277,8 +340,8 @@ template <int KP>
 __global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const WarpSmem S = carve_smem(smem_raw, a.s.row_words);
-    site_counts<KP>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
+    const TeamSmem S = carve_smem(smem_raw, 1);
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
     for (int e = lane; e < a.k * 4; e += 32) a.counts_out[e] = S.total[e];
 }
 
@@ -287,24 +350,26 @@ template <int KP>
 __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const WarpSmem S = carve_smem(smem_raw, a.s.row_words);
-    RowPipe pipe;
-    pipe.init(S, a.s, lane);
-    pipe.issue(0, a.heldout, lane);
-    site_counts<KP>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
-    const uint32_t *row = pipe.acquire(a.heldout, lane);
-    build_tables<KP>(S, false, 0, a.k, a.wtab, lane);
+    const TeamSmem S = carve_smem(smem_raw, 1);
+    const WarpTables WT = warp_tables(S, 0);
+    RowRing ring;
+    ring.init(S, a.s, 4, lane);
+    __syncwarp();
+    if (lane == 0) ring.fill(1, a.heldout);
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
+    const uint32_t *row = ring.wait(0);
+    build_tables<KP>(WT, S.total, false, 0, a.k, a.wtab, lane);
     const int W = __ldg(a.s.len + a.heldout) - a.k + 1;
     if (mode == 0) {
         for (int w = lane; w < W; w += 32) {
-            const double p = exact_window<KP>(row, w, a.k, S.wcol);
+            const double p = exact_window<KP>(row, w, a.k, WT.wcol);
             if (a.raw_out) a.raw_out[w] = p;
             if (a.log2_out) a.log2_out[w] = log2_ref(p);
         }
     } else {
         double p;
         int w;
-        const bool slow = pick_argmax<KP>(S, row, W, a.k, a.fast_ok, lane, p, w);
+        const bool slow = pick_argmax<KP>(WT, row, W, a.k, a.fast_ok, lane, p, w);
         if (lane == 0) {
             a.score_out[0] = log2_ref(p);
             a.score_out[1] = p;
@@ -312,7 +377,6 @@ __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
             a.site_out[1] = slow ? 1 : 0;
         }
     }
-    pipe.drain();
 }
 
 // counts of all N sites of one chain (PWM counts reported with the best chain)
@@ -320,8 +384,8 @@ template <int KP>
 __global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int32_t *sites, int k, int32_t *counts_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const WarpSmem S = carve_smem(smem_raw, s.row_words);
-    site_counts<KP>(s, sites, -1, k, SHIFT_NONE, S.total, lane);
+    const TeamSmem S = carve_smem(smem_raw, 1);
+    site_counts<KP, 1>(s, sites, -1, k, SHIFT_NONE, S.total, lane);
     for (int e = lane; e < k * 4; e += 32) counts_out[e] = S.total[e];
 }
 

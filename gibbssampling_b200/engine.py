@@ -138,6 +138,10 @@ class GibbsEngine:
     def set_stream(self, cuda_stream: int) -> None:
         _abi.check(self._lib.gibbs_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def set_team_warps(self, warps: int) -> None:
+        """Tuning knob: warps per chain (0 = automatic, 1 or 4)."""
+        _abi.check(self._lib.gibbs_set_team_warps(self._h, C.c_int32(warps)))
+
     def synchronize(self) -> None:
         _abi.check(self._lib.gibbs_synchronize(self._h))
 

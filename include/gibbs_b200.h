@@ -80,8 +80,11 @@ typedef struct gibbs_run_stats {
     int64_t sweeps;        /* passes n = 0..N-1, all chains                                     */
     int64_t exact_rescans; /* site updates that fell back to the all-windows float64 path       */
     int64_t capped_chains; /* chains stopped by max_sweeps                                      */
+    int64_t speculative_discards; /* greedy-sweep site updates computed ahead and thrown away   */
     int32_t kernel_launches; /* CUDA kernels launched by the call                               */
     int32_t fast_path;     /* 1 = fixed-point filter + float64 verification was usable          */
+    int32_t team_warps;    /* warps that ran each chain (1 or 4)                                */
+    int32_t reserved;
     double kernel_ms;      /* device time of the chain kernel (CUDA events on the handle stream) */
 } gibbs_run_stats;
 
@@ -107,6 +110,8 @@ int32_t gibbs_destroy(gibbs_handle *h);
 /* run all work of this handle on an existing CUDA stream (cudaStream_t as void*; NULL = own stream) */
 int32_t gibbs_set_stream(gibbs_handle *h, void *cuda_stream);
 int32_t gibbs_num_sequences(const gibbs_handle *h);
+/* tuning knob: warps per chain. 0 = automatic (4 when all chains fit on the GPU at once, else 1) */
+int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps);
 int32_t gibbs_synchronize(gibbs_handle *h);
 
 /* ---- primitives: parity can be checked at the level the reference composes them -------------- */

@@ -51,13 +51,18 @@ def _oracle_site_update(S, seqs, sites, h, k, pc, bg, alphabet):
     return O.acgt_counts(pfm), raw, score, pos
 
 
+TEAMS = [1, 4]   # warps per chain: both kernel variants must be bit-identical to the oracle
+
+
+@pytest.mark.parametrize("team", TEAMS)
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: f"n{c[0]}_L{c[1]}_k{c[3]}")
-def test_primitives_match_oracle(case):
+def test_primitives_match_oracle(case, team):
     ps, seqs, bg, alphabet = _setup(case)
     n, L, Lmin, k, alen, pc, seed = case
     S = O.sources(seqs)
     rng = np.random.default_rng(seed)
     with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
         params = make_params(k, pc, alen, bg)
         for trial in range(3):
             sites = np.array([rng.integers(0, len(s) - k + 1) for s in seqs], dtype=np.int32)
@@ -75,13 +80,15 @@ def test_primitives_match_oracle(case):
                 assert got_score == pytest.approx(score, rel=LOG2_RTOL)
 
 
-def test_argmax_first_maximum_on_ties():
+@pytest.mark.parametrize("team", TEAMS)
+def test_argmax_first_maximum_on_ties(team):
     # identical k-mers everywhere: every window ties; the reference keeps the FIRST strict maximum (fs:312)
     seqs = [b"ACGTACGTACGTACGTACGTACGTACGT", b"ACGTACGTACGTACGTACGTACGT", b"ACGTACGTACGTACGTACGT", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"]
     k, pc, alen = 4, 1e-4, 5
     bg = [0.25, 0.25, 0.25, 0.25]
     S = O.sources(seqs)
     with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
         params = make_params(k, pc, alen, bg)
         for sites in ([0, 0, 0, 0], [4, 8, 12, 3], [1, 2, 3, 0]):
             for h in range(len(seqs)):
@@ -90,7 +97,8 @@ def test_argmax_first_maximum_on_ties():
                 assert eng.window_scores(sites, h, params)[0].tobytes() == raw.tobytes()
 
 
-def test_zero_pseudocount_uses_exact_path():
+@pytest.mark.parametrize("team", TEAMS)
+def test_zero_pseudocount_uses_exact_path(team):
     # pc = 0 makes odds ratios 0 (log2 = -inf): the ranking pass is disabled and every window is
     # scored in float64; all-zero scores give (-inf, 0) like the reference
     seqs = [b"ACGTTGCAACGT", b"TTTTTTTTTTTT", b"ACGTACGTACGT", b"GGGGGGGGGGGG"]
@@ -98,6 +106,7 @@ def test_zero_pseudocount_uses_exact_path():
     bg = [0.25, 0.25, 0.25, 0.25]
     S = O.sources(seqs)
     with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
         params = make_params(k, pc, alen, bg)
         for sites in ([0, 0, 0, 0], [8, 3, 4, 1]):
             for h in range(len(seqs)):
@@ -113,8 +122,9 @@ def _oracle_chain(S, k, pc, pcv, alphabet, seed=None, chain=0, uniforms=None, na
     return O.site_step(name, S, k, pc, pcv=pcv, rng=rng, state=state, alphabet=alphabet)
 
 
+@pytest.mark.parametrize("team", TEAMS)
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: f"n{c[0]}_L{c[1]}_k{c[3]}")
-def test_chains_match_oracle_philox(case):
+def test_chains_match_oracle_philox(case, team):
     """Whole restarts (fs:691-695), several chains per launch, Philox stream shared with the oracle."""
     ps, seqs, bg, alphabet = _setup(case)
     n, L, Lmin, k, alen, pc, seed = case
@@ -122,6 +132,7 @@ def test_chains_match_oracle_philox(case):
     pcv = O.pcv_from_acgt(bg)
     n_chains, base = 6, 1000 * seed
     with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
         res = eng.run(make_params(k, pc, alen, bg), n_chains, chain_id_base=base, seed=0xB200 + seed)
     total_updates = 0
     for c in range(n_chains):
@@ -131,6 +142,7 @@ def test_chains_match_oracle_philox(case):
         assert res.sums[c] == pytest.approx(float(np.sum(score)), rel=1e-9)
         total_updates += st.site_updates
     assert res.stats["site_updates"] == total_updates
+    assert res.stats["team_warps"] == team
     best = int(np.argmax(res.sums))
     assert res.best_chain == best
     want_counts = np.zeros((k, 4), dtype=np.int64)
@@ -140,7 +152,8 @@ def test_chains_match_oracle_philox(case):
     assert res.counts.tolist() == want_counts.tolist()
 
 
-def test_chains_match_oracle_injected_uniforms():
+@pytest.mark.parametrize("team", TEAMS)
+def test_chains_match_oracle_injected_uniforms(team):
     """Same comparison with an injected stream of doubles (the parity definition of north_star)."""
     case = (10, 80, 50, 9, 5, 1e-4, 11)
     ps, seqs, bg, alphabet = _setup(case)
@@ -152,6 +165,7 @@ def test_chains_match_oracle_injected_uniforms():
     u = rng.random((n_chains, draws_per_chain(n)))
     u[0, :5] = [0.0, 0.999999999999, 0.5, 0.25, 1.0 - 2.0 ** -32]   # range boundaries
     with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
         res = eng.run(make_params(k, pc, alen, bg), n_chains, uniforms=u)
     for c in range(n_chains):
         score, pos, _ = _oracle_chain(S, k, pc, pcv, alphabet, uniforms=u[c])
@@ -159,7 +173,8 @@ def test_chains_match_oracle_injected_uniforms():
         np.testing.assert_allclose(res.scores[c], score, rtol=LOG2_RTOL)
 
 
-def test_phases_match_reference_functions():
+@pytest.mark.parametrize("team", TEAMS)
+def test_phases_match_reference_functions(team):
     """Each reference function on its own (fs:412, fs:381, fs:350, fs:318), chained through host state."""
     case = (11, 90, 60, 8, 5, 1e-4, 12)
     ps, seqs, bg, alphabet = _setup(case)
@@ -169,6 +184,7 @@ def test_phases_match_reference_functions():
     steps = [("random_starts_with_bpv", _abi.PHASE_INIT), ("find_best_motif_with_start_position", _abi.PHASE_GREEDY),
              ("left_shifted_with_bpv", _abi.PHASE_LEFT), ("right_shifted_with_bpv", _abi.PHASE_RIGHT)]
     with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
         state = None
         for name, mask in steps:
             o_score, o_pos, _ = _oracle_chain(S, k, pc, pcv, alphabet, seed=99, chain=3, name=name, state=state)
@@ -187,7 +203,12 @@ def test_chain_results_do_not_depend_on_batching():
     bg = background_of(ps.ascii, 1e-4, 5)
     params = make_params(10, 1e-4, 5, bg)
     with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(1)
+        solo = eng.run(params, 16, chain_id_base=0, seed=5)
+        eng.set_team_warps(4)
         full = eng.run(params, 16, chain_id_base=0, seed=5)
+        assert solo.sites.tolist() == full.sites.tolist() and solo.scores.tobytes() == full.scores.tobytes()
+        eng.set_team_warps(0)
         part = eng.run(params, 5, chain_id_base=9, seed=5)
         assert part.sites.tolist() == full.sites[9:14].tolist()
         assert part.scores.tobytes() == full.scores[9:14].tobytes()
