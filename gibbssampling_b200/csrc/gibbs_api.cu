@@ -163,23 +163,15 @@ int32_t set_smem(K kernel, int bytes) {
 
 #define KP_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
-// Warps per chain: 4 when every chain can then be resident at once (the C2 case: 1024 chains on 148 SMs
-// would otherwise leave most warp slots empty and each chain latency-bound), else 1.
-// Warps per chain: 4 when every chain can then be resident at once (the C2 case: 1024 chains on 148 SMs
-// would otherwise leave most warp slots empty and each chain latency-bound), else 1.
+// Warps per chain. Four warps work on four consecutive held-out sequences of the chain at once, which
+// shortens every chain's critical path (measured faster than one warp per chain both when all chains
+// are resident at once -- C2 -- and when they run in several waves); one warp is kept for sets with
+// fewer than 4 sequences or rows too long for four sets of staging buffers.
 template <int KPV>
 int32_t launch_chain_kp(gibbs_handle *h, const ChainArgs &a) {
     int team = h->team_warps;
     const int smem4 = team_smem_bytes(a.s.row_words, 4), smem1 = team_smem_bytes(a.s.row_words, 1);
-    if (team == 0) {
-        int nb = 0;
-        if (smem4 <= 200 * 1024) {
-            int32_t rc = set_smem(chain_kernel<KPV, 4>, smem4);
-            if (rc) return rc;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_kernel<KPV, 4>, 128, smem4));
-        }
-        team = ((long long)nb * h->sm_count >= a.n_chains) ? 4 : 1;
-    }
+    if (team == 0) team = (a.s.n >= 4 && smem4 <= 200 * 1024) ? 4 : 1;
     h->run_team = team;
     if (team == 4) {
         if (smem4 > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for 4 warps per chain");

@@ -81,6 +81,7 @@ struct TeamSmem {
     uint64_t *bar;        // [ring] mbarriers of the staged rows
     int32_t *total;       // [32*4] counts over ALL current sites of the chain
     int32_t *flags;       // [8]  per-warp outcome of a round
+    uint32_t *lut;        // [16] histogram increments per nibble (hist_lut_entry)
     double *blk_hv;       // [2][32] state of two 32-sequence blocks
     int32_t *blk_site;    // [2][32]
     int32_t *blk_len;     // [2][32]
@@ -89,9 +90,9 @@ struct TeamSmem {
 };
 
 constexpr int MAX_RING = 16;
-constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 32 + 512 + 256 + 256; // bar, total, flags, blk_hv, blk_site, blk_len
+constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 32 + 512 + 256 + 256 + 64; // bar, total, flags, blk_hv, blk_site, blk_len, lut
 
-__host__ __device__ inline int ring_slots(int team_warps) { return 2 * team_warps < 4 ? 4 : 2 * team_warps; }
+__host__ __device__ constexpr int ring_slots(int team_warps) { return 2 * team_warps < 4 ? 4 : 2 * team_warps; }
 __host__ __device__ inline int team_smem_bytes(int row_words, int team_warps) {
     return TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES + ring_slots(team_warps) * row_words * 4;
 }
@@ -104,6 +105,7 @@ __device__ __forceinline__ TeamSmem carve_smem(unsigned char *base, int team_war
     s.blk_hv = reinterpret_cast<double *>(base + 672);
     s.blk_site = reinterpret_cast<int32_t *>(base + 1184);
     s.blk_len = reinterpret_cast<int32_t *>(base + 1440);
+    s.lut = reinterpret_cast<uint32_t *>(base + 1696);
     s.warp_tables = base + TEAM_FIXED_BYTES;
     s.row0 = reinterpret_cast<uint32_t *>(base + TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES);
     return s;
@@ -158,41 +160,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 // Ring of staged rows. Visits are numbered 0, 1, 2, ... over the whole chain (visit v scans sequence
 // (first + v) mod N: every sweep walks n = 0..N-1), visit v lives in slot v % R and completes phase
-// (v / R) & 1 of that slot's mbarrier, so any warp can find and wait for its row from v alone. One
-// elected thread keeps the rows of visits [head, head + R) in flight with cp.async.bulk (TMA).
+// (v / R) & 1 of that slot's mbarrier, so any warp can find and wait for its row from v alone (R is a
+// power of two, so 32-bit wrap-around of v is harmless). One elected thread keeps the rows of visits
+// [head, head + R) in flight with cp.async.bulk (TMA).
+template <int R>
 struct RowRing {
+    static_assert((R & (R - 1)) == 0, "ring size must be a power of two");
     uint64_t *bar;
     uint32_t *row0;
     const uint32_t *gpacked;
-    int row_words, n_seqs, slots;
-    long long issued; // visits [0, issued) have been requested (meaningful on thread 0 only)
+    int row_words, n_seqs;
+    uint32_t issued;  // visits [0, issued) have been requested   (meaningful on thread 0 only)
+    int next_seq;     // sequence of visit `issued`                (thread 0 only)
 
-    __device__ __forceinline__ void init(const TeamSmem &s, const DeviceSeqs &d, int r, int tid) {
+    __device__ __forceinline__ void init(const TeamSmem &s, const DeviceSeqs &d, int first, int tid) {
         bar = s.bar;
         row0 = s.row0;
         gpacked = d.packed;
         row_words = d.row_words;
         n_seqs = d.n;
-        slots = r;
         issued = 0;
+        next_seq = first;
         if (tid == 0) {
-            for (int i = 0; i < r; ++i) mbar_init(bar + i, 1);
+#pragma unroll
+            for (int i = 0; i < R; ++i) mbar_init(bar + i, 1);
             fence_barrier_init();
         }
     }
-    // thread 0 only: request the rows of visits [issued, upto); sequence of visit v = (first + v) % n_seqs
-    __device__ __forceinline__ void fill(long long upto, int first) {
+    // thread 0 only: request the rows of visits [issued, upto)
+    __device__ __forceinline__ void fill(uint32_t upto) {
         const uint32_t bytes = (uint32_t)row_words * 4u;
-        for (; issued < upto; ++issued) {
-            const int slot = (int)(issued % slots);
-            const int seq = (int)((first + issued) % n_seqs);
+        while (issued != upto) {
+            const int slot = (int)(issued & (R - 1));
             mbar_expect_tx(bar + slot, bytes);
-            bulk_g2s(row0 + slot * row_words, gpacked + (size_t)seq * row_words, bytes, bar + slot);
+            bulk_g2s(row0 + slot * row_words, gpacked + (size_t)next_seq * row_words, bytes, bar + slot);
+            next_seq = next_seq + 1 < n_seqs ? next_seq + 1 : 0;
+            ++issued;
         }
     }
-    __device__ __forceinline__ const uint32_t *wait(long long v) const {
-        const int slot = (int)(v % slots);
-        mbar_wait(bar + slot, (uint32_t)((v / slots) & 1));
+    __device__ __forceinline__ const uint32_t *wait(uint32_t v) const {
+        const int slot = (int)(v & (R - 1));
+        mbar_wait(bar + slot, (v / R) & 1u);
         return row0 + slot * row_words;
     }
 };
@@ -248,46 +256,71 @@ __device__ __forceinline__ int shifted_site(int pos, int len, int k, int mode) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-thread packed histogram of k-mers: 4 byte-wide counters (A,C,G,T) per column register
-// (replaces createPFMOf + fusePositionFrequencyMatrices, fs:211-226)
+// per-thread packed histogram of k-mers (replaces createPFMOf + fusePositionFrequencyMatrices,
+// fs:211-226)
 // ------------------------------------------------------------------------------------------------
+// Two columns per lookup: lut[nib] (16 words of shared memory) holds a 1 in the 4-bit field of base
+// nib&3 of the even column (fields 0-3) and of base nib>>2 of the odd column (fields 4-7). Nibble
+// counters spill into byte counters every 15 adds, byte counters into dst[] every 255 adds.
+__device__ __forceinline__ uint32_t hist_lut_entry(int nib) { return (1u << (4 * (nib & 3))) | (1u << (16 + 4 * (nib >> 2))); }
+
 template <int KP>
 struct Hist {
-    uint32_t c[2 * KP];
+    uint32_t c4[KP];      // 8 nibble counters per column pair
+    uint32_t lo[KP];      // byte counters of fields 0,2,4,6
+    uint32_t hi[KP];      // byte counters of fields 1,3,5,7
+    int n4;               // adds since the last nibble spill
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int j = 0; j < 2 * KP; ++j) c[j] = 0;
+        for (int p = 0; p < KP; ++p) c4[p] = lo[p] = hi[p] = 0;
+        n4 = 0;
     }
-    __device__ __forceinline__ void add(uint64_t kmer, uint32_t inc) { // inc = 1 (count it) or 0
+    __device__ __forceinline__ void spill4() {
 #pragma unroll
-        for (int j = 0; j < 2 * KP; ++j) {
-            const uint32_t b8 = ((uint32_t)(kmer >> (2 * j)) & 3u) * 8u;
-            c[j] += inc << b8;
+        for (int p = 0; p < KP; ++p) {
+            lo[p] += c4[p] & 0x0F0F0F0Fu;
+            hi[p] += (c4[p] >> 4) & 0x0F0F0F0Fu;
+            c4[p] = 0;
         }
+        n4 = 0;
     }
-    // at most 255 adds per thread since the last clear; dst[] += warp sums. Bytes are widened to
+    // add up to 4 k-mers; caller guarantees n4 + 4 <= 15 after spill handling below
+    __device__ __forceinline__ void add(uint64_t kmer, const uint32_t *lut) {
+#pragma unroll
+        for (int p = 0; p < KP; ++p) c4[p] += lut[(uint32_t)(kmer >> (4 * p)) & 15u];
+        ++n4;
+    }
+    __device__ __forceinline__ void maybe_spill(int upcoming) {
+        if (n4 + upcoming > 15) spill4(); // uniform enough: n4 differs between lanes only at range edges
+    }
+    // at most 255 adds per thread since the last flush; dst[] += warp sums. Bytes are widened to
     // 16-bit fields (32 lanes x 255 < 65536) so one REDUX.SUM reduces two counters at once.
     // ATOMIC: several warps add into the same dst.
     template <bool ATOMIC>
     __device__ __forceinline__ void flush_add(int32_t *dst, int k, int lane) {
+        spill4();
 #pragma unroll
-        for (int j = 0; j < 2 * KP; ++j) {
-            if (j < k) {
+        for (int p = 0; p < KP; ++p) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t s = __reduce_add_sync(FULL, (c[j] >> (8 * h)) & 0x00FF00FFu);
-                    if (lane == ((2 * j + h) & 31)) {
-                        if (!ATOMIC) {
-                            dst[j * 4 + h] += (int32_t)(s & 0xFFFFu);
-                            dst[j * 4 + h + 2] += (int32_t)(s >> 16);
-                        } else {
-                            atomicAdd(&dst[j * 4 + h], (int32_t)(s & 0xFFFFu));
-                            atomicAdd(&dst[j * 4 + h + 2], (int32_t)(s >> 16));
-                        }
+            for (int q = 0; q < 4; ++q) {
+                // q = 0: lo bytes 0,2 (base 0 of both columns); 1: lo bytes 1,3 (base 2);
+                // q = 2: hi bytes 0,2 (base 1); 3: hi bytes 1,3 (base 3)
+                const uint32_t src = (q < 2) ? lo[p] : hi[p];
+                const uint32_t s = __reduce_add_sync(FULL, (src >> (8 * (q & 1))) & 0x00FF00FFu);
+                const int b = (q == 0) ? 0 : (q == 1) ? 2 : (q == 2) ? 1 : 3;
+                if (lane == ((4 * p + q) & 31)) {
+                    const int e0 = (2 * p) * 4 + b, e1 = (2 * p + 1) * 4 + b;
+                    const int32_t v0 = (int32_t)(s & 0xFFFFu), v1 = (int32_t)(s >> 16);
+                    if (!ATOMIC) {
+                        dst[e0] += v0;
+                        if (2 * p + 1 < k) dst[e1] += v1;
+                    } else {
+                        atomicAdd(&dst[e0], v0);
+                        if (2 * p + 1 < k) atomicAdd(&dst[e1], v1);
                     }
                 }
             }
-            c[j] = 0;
+            lo[p] = hi[p] = 0;
         }
     }
 };
@@ -297,7 +330,7 @@ struct Hist {
 // of the team take part; ends with a team sync.
 template <int KP, int T>
 __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *sites, int exclude, int k, int mode,
-                                            int32_t *total, int tid) {
+                                            int32_t *total, const uint32_t *lut, int tid) {
     constexpr int THREADS = 32 * T;
     for (int e = tid; e < MAX_COLS * 4; e += THREADS) total[e] = 0;
     team_sync<T>();
@@ -308,11 +341,12 @@ __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *
         const int it1 = min(iters, it0 + 255);
         for (int it = it0; it < it1; ++it) {
             const int i = it * THREADS + tid;
+            h.maybe_spill(1);
             if (i < s.n && i != exclude) {
                 const int site = __ldcg(sites + i);
                 if (site >= 0) {
                     const int pos = shifted_site(site, __ldg(s.len + i), k, mode);
-                    h.add(kmer_global<KP>(s.packed + (size_t)i * s.row_words, pos), 1u);
+                    h.add(kmer_global<KP>(s.packed + (size_t)i * s.row_words, pos), lut);
                 }
             }
         }
@@ -360,9 +394,13 @@ __device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t 
 template <int KP>
 __device__ __forceinline__ double exact_window(const uint32_t *row, int w, int k, const double *wcol) {
     const uint64_t kmer = kmer_shared<KP>(row, w);
+    const uint64_t k8 = kmer << 3; // base code * 8 = byte offset inside a 32 B column (columns 0..29)
+    const char *base = reinterpret_cast<const char *>(wcol);
     double f[2 * KP];
 #pragma unroll
-    for (int j = 0; j < 2 * KP; ++j) f[j] = wcol[j * 4 + (int)((kmer >> (2 * j)) & 3u)]; // dummy column = 1.0
+    for (int j = 0; j < 2 * KP; ++j) // dummy column (odd k) holds 1.0
+        f[j] = *reinterpret_cast<const double *>(
+            base + j * 32 + (j <= 29 ? ((uint32_t)(k8 >> (2 * j)) & 24u) : (((uint32_t)(kmer >> (2 * j)) << 3) & 24u)));
     double p = 1.0;
 #pragma unroll
     for (int j = 0; j < 2 * KP; ++j)
@@ -408,10 +446,10 @@ __device__ __forceinline__ void scan_exact_all(const uint32_t *row, int W, int k
 // ------------------------------------------------------------------------------------------------
 // A chunk is CH consecutive windows handled by one lane. Even windows 2e use the nibbles at bit
 // 4(e+p) of the chunk's aligned bit string, odd windows those at bit 4(e+p)+2, so CH/2 + KP - 1
-// nibble extractions per parity serve CH/2 windows x KP lookups. key = (sum << 8) | (255 - local).
+// nibble extractions per parity serve CH/2 windows x KP lookups. Returns the chunk maximum of
+// key = (sum << 8) | (255 - round), i.e. the low 8 bits identify the chunk among the lane's chunks.
 template <int KP, int CH, bool MASK>
-__device__ __forceinline__ void score_chunk(const uint32_t *a, const uint32_t *b, const int32_t *ptab, int idx0, int lim,
-                                            int32_t &m1, int32_t &m2) {
+__device__ __forceinline__ int32_t score_chunk(const uint32_t *a, const uint32_t *b, const int32_t *ptab, int idx, int lim) {
     constexpr int NE = CH / 2 + KP - 1;
     int nibE[NE], nibO[NE];
 #pragma unroll
@@ -419,23 +457,28 @@ __device__ __forceinline__ void score_chunk(const uint32_t *a, const uint32_t *b
         nibE[t] = (a[t >> 3] >> (4 * (t & 7))) & 15;
         nibO[t] = (b[t >> 3] >> (4 * (t & 7))) & 15;
     }
+    int32_t key[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
         const int e = i >> 1;
-        int32_t key = idx0 - i;
+        int32_t v = idx;
 #pragma unroll
-        for (int p = 0; p < KP; ++p) key += ptab[p * 16 + ((i & 1) ? nibO[e + p] : nibE[e + p])];
-        if (MASK) key = (i < lim) ? key : INT32_MIN;
-        m2 = max(m2, min(m1, key));
-        m1 = max(m1, key);
+        for (int p = 0; p < KP; ++p) v += ptab[p * 16 + ((i & 1) ? nibO[e + p] : nibE[e + p])];
+        if (MASK) v = (i < lim) ? v : INT32_MIN;
+        key[i] = v;
     }
+#pragma unroll
+    for (int st = 1; st < CH; st *= 2) // max tree (the compiler fuses pairs into 3-input VIMNMX3)
+#pragma unroll
+        for (int i = 0; i + st < CH; i += 2 * st) key[i] = max(key[i], key[i + st]);
+    return key[0];
 }
 
 template <int KP, int CH>
 struct ScanGeom {
     static constexpr int NB = CH + 2 * KP - 1;  // bases a chunk touches
     static constexpr int NWA = (NB + 15) / 16;  // aligned words
-    static constexpr int RPS = 256 / CH;        // rounds per segment (local index fits 8 bits)
+    static constexpr int RPS = 256;             // rounds per segment (round index fits 8 bits)
     static constexpr int CPS = 32 * RPS;        // chunks per segment
 };
 
@@ -445,7 +488,7 @@ struct ScanGeom {
 template <int CH>
 __device__ __forceinline__ int chunk_base(int c, int W) { return max(0, min(c * CH, W - CH)); }
 
-// per-lane best key M1 (from segment S1), second best M2, over all windows of the row
+// per-lane best chunk key M1 (from segment S1), best key among the lane's OTHER chunks M2
 template <int KP, int CH>
 __device__ __forceinline__ void scan_fast(const uint32_t *row, int W, const int32_t *ptab, int lane, int32_t &M1,
                                           int32_t &M2, int &S1) {
@@ -455,10 +498,9 @@ __device__ __forceinline__ void scan_fast(const uint32_t *row, int W, const int3
     M2 = INT32_MIN;
     S1 = 0;
     for (int seg = 0, c0 = 0; c0 < n_chunks; ++seg, c0 += G::CPS) {
-        int32_t m1 = INT32_MIN, m2 = INT32_MIN;
         const int c_end = min(n_chunks, c0 + G::CPS);
-        int r = 0;
-        for (int c = c0 + lane; c < c_end; c += 32, ++r) {
+        int idx = 255;
+        for (int c = c0 + lane; c < c_end; c += 32, --idx) {
             const int base0 = chunk_base<CH>(c, W);
             const uint32_t *p = row + (base0 >> 4);
             const int sh = (base0 & 15) * 2;
@@ -470,26 +512,18 @@ __device__ __forceinline__ void scan_fast(const uint32_t *row, int W, const int3
             a[G::NWA] = 0;
 #pragma unroll
             for (int i = 0; i < G::NWA; ++i) b[i] = __funnelshift_r(a[i], a[i + 1], 2);
-            const int idx0 = 255 - r * CH;
-            if (W >= CH) score_chunk<KP, CH, false>(a, b, ptab, idx0, CH, m1, m2); // warp-uniform branch
-            else score_chunk<KP, CH, true>(a, b, ptab, idx0, W, m1, m2);
-        }
-        if (m1 > M1) {
-            M2 = max(max(M2, M1), m2);
-            M1 = m1;
-            S1 = seg;
-        } else {
-            M2 = max(M2, m1);
+            int32_t cm;
+            if (W >= CH) cm = score_chunk<KP, CH, false>(a, b, ptab, idx, CH); // warp-uniform branch
+            else cm = score_chunk<KP, CH, true>(a, b, ptab, idx, W);
+            if (cm > M1) {
+                M2 = max(M2, M1);
+                M1 = cm;
+                S1 = seg;
+            } else {
+                M2 = max(M2, cm);
+            }
         }
     }
-}
-
-template <int KP, int CH>
-__device__ __forceinline__ int decode_window(int32_t key, int seg, int lane, int W) {
-    using G = ScanGeom<KP, CH>;
-    const int local = 255 - (key & 255);
-    const int r = local / CH, i = local % CH;
-    return chunk_base<CH>(seg * G::CPS + lane + 32 * r, W) + i;
 }
 
 // getBestPWMSsWithBPV (fs:301-314) for the staged row: (raw float64 maximum, first argmax).
@@ -497,24 +531,39 @@ __device__ __forceinline__ int decode_window(int32_t key, int seg, int lane, int
 template <int KP, int CH>
 __device__ __forceinline__ bool pick_argmax_ch(const WarpTables &T, const uint32_t *row, int W, int k, int lane,
                                                double &hv_out, int &w_out) {
+    using G = ScanGeom<KP, CH>;
     int32_t M1, M2;
     int S1;
     scan_fast<KP, CH>(row, W, T.ptab, lane, M1, M2, S1);
     const int32_t M = __reduce_max_sync(FULL, M1);
     // |key/256 - true log2 score * 2^11| <= k/2 units for every window, so any window whose exact
-    // product can reach the maximum has key >= M - (k + 1) units (index bits: 255 more)
+    // product can reach the maximum lies in a chunk whose key >= M - (k + 1) units (index bits: 255 more)
     const int32_t thr = M - (((k + 1) << KEY_IDX_BITS) + 255);
-    if (__ballot_sync(FULL, M2 >= thr)) return true; // two candidates in one lane: rescan exactly
-    const bool is_cand = M1 >= thr;
-    const unsigned cand = __ballot_sync(FULL, is_cand);
+    if (__ballot_sync(FULL, M2 >= thr)) return true; // a lane with two candidate chunks: rescan exactly
+    unsigned cand = __ballot_sync(FULL, M1 >= thr);
+    // every window of every candidate chunk is re-scored in float64, one window per lane
+    const bool single = (cand & (cand - 1)) == 0;
     double p = 0.0;
     int w = INT32_MAX;
-    if (is_cand) {
-        w = decode_window<KP, CH>(M1, S1, lane, W);
-        p = exact_window<KP>(row, w, k, T.wcol);
-    }
-    if (__popc(cand) == 1) {
+    while (cand) {
         const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int32_t key = __shfl_sync(FULL, M1, src);
+        const int seg = __shfl_sync(FULL, S1, src);
+        const int base0 = chunk_base<CH>(seg * G::CPS + src + 32 * (255 - (key & 255)), W);
+        const int wi = base0 + lane;
+        if (lane < CH && wi < W) {
+            const double pi = exact_window<KP>(row, wi, k, T.wcol);
+            if (better(pi, wi, p, w)) {
+                p = pi;
+                w = wi;
+            }
+        }
+    }
+    if (single) { // lanes hold ascending windows: the first lane with the largest product is the first maximum
+        const uint32_t hi = (uint32_t)__double2hiint(p), mh = __reduce_max_sync(FULL, hi);
+        const uint32_t lo = (hi == mh) ? (uint32_t)__double2loint(p) : 0u, ml = __reduce_max_sync(FULL, lo);
+        const int src = __ffs(__ballot_sync(FULL, hi == mh && lo == ml)) - 1;
         p = __shfl_sync(FULL, p, src);
         w = __shfl_sync(FULL, w, src);
     } else {

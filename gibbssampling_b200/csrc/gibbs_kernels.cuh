@@ -83,7 +83,7 @@ __global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, 
 // length / row loads overlap.
 template <int KP>
 __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
-                                                  int32_t *counts, int lane) {
+                                                  int32_t *counts, const uint32_t *lut, int lane) {
     const int N = a.s.n, k = a.k;
     for (int e = lane; e < MAX_COLS * 4; e += 32) counts[e] = 0;
     __syncwarp();
@@ -106,12 +106,12 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
                 wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
             }
             uint64_t kmer[4];
-            uint32_t valid[4];
+            bool valid[4];
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const uint64_t d = blk * 4 + x;
                 const bool ok = blk < blk1 && d >= base && d < d_end;
-                valid[x] = ok ? 1u : 0u;
+                valid[x] = ok;
                 const int r = ok ? (int)(d - base) : 0;
                 const int i = r + (r >= n ? 1 : 0); // always a valid sequence index (N >= 2)
                 const int range = __ldg(a.s.len + i) - k + 1;
@@ -127,8 +127,10 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
                 }
                 kmer[x] = kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos);
             }
+            h.maybe_spill(4);
 #pragma unroll
-            for (int x = 0; x < 4; ++x) h.add(kmer[x], valid[x]);
+            for (int x = 0; x < 4; ++x)
+                if (valid[x]) h.add(kmer[x], lut); // invalid only at the two ends of the draw range
         }
         h.template flush_add<false>(counts, k, lane);
     }
@@ -163,14 +165,15 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const 
     double *scores = a.scores + (size_t)chain * N;
     const uint64_t chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
 
-    RowRing ring;
-    ring.init(S, a.s, R, tid);
+    RowRing<R> ring;
+    ring.init(S, a.s, 0, tid);
+    if (tid < 16) S.lut[tid] = hist_lut_entry(tid);
     team_sync<T>();
-    if (tid == 0) ring.fill(R, 0);
+    if (tid == 0) ring.fill(R);
 
     unsigned long long st_updates = 0, st_windows = 0, st_slow = 0, st_spec = 0;
     int st_sweeps = 0, capped = 0;
-    long long vbase = 0; // visit index of n = 0 in the current sweep
+    uint32_t vbase = 0; // visit index of n = 0 in the current sweep (wraps harmlessly)
 
     int phase = next_phase(PH_INIT, a.phase_mask);
     int sweeps_in_phase = 0;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const 
         // all-sites counts: once when the greedy phase starts (then kept incrementally: -old site,
         // +new site), once per sweep for the shift phases (they read the shifted snapshot, fs:357)
         if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && sweeps_in_phase == 0))
-            site_counts<KP, T>(a.s, sites, -1, k, mode, S.total, tid);
+            site_counts<KP, T>(a.s, sites, -1, k, mode, S.total, S.lut, tid);
         // state of two 32-sequence blocks (lengths, sites, raw scores): coalesced loads, kept one block ahead
         auto load_block = [&](int b) {
             const int i = b * 32 + tid;
@@ -210,13 +213,13 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const 
             uint64_t own = 0;
             const uint32_t *row = nullptr;
             if (active) {
-                row = ring.wait(vbase + n);
+                row = ring.wait(vbase + (uint32_t)n);
                 const int o = ((n >> 5) & 1) * 32 + (n & 31);
                 const int len_n = S.blk_len[o];
                 Wn = len_n - k + 1;
                 double hv_n = 0.0;
                 if (phase == PH_INIT) {
-                    random_loo_counts<KP>(a, chain_uid, chain, n, WT.counts, lane);
+                    random_loo_counts<KP>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
                     build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                 } else {
                     site_n = S.blk_site[o];
@@ -274,9 +277,9 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const 
             }
             n0 += min(last_commit + 1, N - n0);
             team_sync<T>(); // counts updated; rows of the committed visits are free
-            if (tid == 0) ring.fill(vbase + n0 + R, 0);
+            if (tid == 0) ring.fill(vbase + (uint32_t)n0 + R);
         }
-        vbase += N;
+        vbase += (uint32_t)N;
         st_sweeps += 1;
         if (phase == PH_INIT) {
             phase = next_phase(PH_GREEDY, a.phase_mask);
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const 
         }
     }
     if (tid == 0) // the ring always has R rows in flight: let them land before the CTA exits
-        for (int i = 0; i < R; ++i) ring.wait(vbase + i);
+        for (int i = 0; i < R; ++i) ring.wait(vbase + (uint32_t)i);
     team_sync<T>();
 
     // (log2 highValue, highIndex), fs:303
@@ -341,7 +344,9 @@ __global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
-    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
+    if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
+    __syncwarp();
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, lane);
     for (int e = lane; e < a.k * 4; e += 32) a.counts_out[e] = S.total[e];
 }
 
@@ -352,11 +357,12 @@ __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
     const WarpTables WT = warp_tables(S, 0);
-    RowRing ring;
-    ring.init(S, a.s, 4, lane);
+    RowRing<4> ring;
+    ring.init(S, a.s, a.heldout, lane);
+    if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
     __syncwarp();
-    if (lane == 0) ring.fill(1, a.heldout);
-    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, lane);
+    if (lane == 0) ring.fill(1);
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, lane);
     const uint32_t *row = ring.wait(0);
     build_tables<KP>(WT, S.total, false, 0, a.k, a.wtab, lane);
     const int W = __ldg(a.s.len + a.heldout) - a.k + 1;
@@ -385,7 +391,9 @@ __global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
-    site_counts<KP, 1>(s, sites, -1, k, SHIFT_NONE, S.total, lane);
+    if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
+    __syncwarp();
+    site_counts<KP, 1>(s, sites, -1, k, SHIFT_NONE, S.total, S.lut, lane);
     for (int e = lane; e < k * 4; e += 32) counts_out[e] = S.total[e];
 }
 

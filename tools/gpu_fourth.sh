@@ -31,6 +31,3 @@ for cid in range(0,64):
     r = eng.run(p, 1, seed=1, chain_id_base=cid, want_counts=False, want_sites=False, want_scores=False); sw.append(r.stats['sweeps'])
 print("sweeps per chain: mean",np.mean(sw),"max",max(sw),"min",min(sw),sorted(sw))
 PY
-timeout 300 python tools/prof_probe.py 1 4 > gpurun_out/probe_plain.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:chain_kernel -c 1 -o gpurun_out/prof_chain_t4 -f python tools/prof_probe.py 1 4 > gpurun_out/ncu_full.log 2>&1
-echo "ncu rc=$?" >> gpurun_out/ncu_full.log
