@@ -1,0 +1,150 @@
+// fsharp/GibbsSamplingB200.fs -- the reference-side binding (NOT compiled in this repository: the
+// image has no .NET toolchain; the Python twin of this file is gibbssampling_b200/SiteSampler.py).
+//
+// Drop-in for the WithBPV family of GibbsSampling.fs: same module names, function names, argument
+// order and result types; the body of each function marshals its arguments to libgibbs_b200.so
+// (include/gibbs_b200.h) with P/Invoke instead of running the F# loops. `seed` is the one addition:
+// the reference builds `System.Random()` from the clock (fs:144, fs:829), which cannot be reproduced.
+namespace GibbsSampling
+
+open System
+open System.Runtime.InteropServices
+open BioFSharp
+
+module Native =
+
+    [<Struct; StructLayout(LayoutKind.Sequential)>]
+    type GibbsParams =
+        val mutable k             : int
+        val mutable alphabetSize  : int
+        val mutable pseudocount   : float
+        val mutable bgA           : float
+        val mutable bgC           : float
+        val mutable bgG           : float
+        val mutable bgT           : float
+        val mutable cutoff        : float
+        val mutable sampler       : int
+        val mutable phaseShifts   : int
+        val mutable maxSweeps     : int
+        val mutable phaseMask     : int
+
+    [<Struct; StructLayout(LayoutKind.Sequential)>]
+    type GibbsRunStats =
+        val mutable siteUpdates   : int64
+        val mutable windowScores  : int64
+        val mutable sweeps        : int64
+        val mutable exactRescans  : int64
+        val mutable cappedChains  : int64
+        val mutable specDiscards  : int64
+        val mutable kernelLaunches: int
+        val mutable fastPath      : int
+        val mutable teamWarps     : int
+        val mutable reserved      : int
+        val mutable kernelMs      : float
+
+    [<Literal>]
+    let Lib = "gibbs_b200" // libgibbs_b200.so next to GibbsSampling.dll
+
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern IntPtr gibbs_last_error()
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_create(byte[] seqs, int64[] offsets, int nSeqs, int device, IntPtr& handle)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_destroy(IntPtr handle)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_set_start_state(IntPtr handle, int nChains, int[] sites, float[] scores)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_pick_argmax(IntPtr handle, int[] sites, int heldout, GibbsParams& p, float& score, int& site)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_run(IntPtr handle, GibbsParams& p, int nChains, int64 chainIdBase, uint64 seed, int rngMode,
+                         float[] uniformsOrNull, int64 uniformsPerChain, int[] sitesOut, float[] scoresOut,
+                         float[] sumsOut, int& bestChain, int[] countsOut, GibbsRunStats& stats)
+
+    /// status code -> the exception the reference would have thrown (SURVEY.md section 8b)
+    let check (rc:int) =
+        if rc <> 0 then
+            let msg = Marshal.PtrToStringAnsi(gibbs_last_error())
+            match rc with
+            | 1 -> raise (ArgumentException msg)
+            | 2 -> raise (IndexOutOfRangeException msg)        // symbol outside the table, fs:17
+            | 3 -> raise (InvalidOperationException msg)       // Array.take on a short sequence, fs:152
+            | 7 -> raise (ArgumentException msg)               // roulette pick beyond the mass, fs:753
+            | 8 -> raise (NotSupportedException msg)
+            | _ -> raise (ExternalException(msg, rc))          // CUDA failure; there is no CPU fallback
+
+    /// sources : BioArray<#IBioItem>[] -> one ASCII buffer + offsets (BioItem.symbol, fs:17)
+    let flatten (sources:BioArray.BioArray<#IBioItem>[]) =
+        let offsets = Array.zeroCreate<int64> (sources.Length + 1)
+        sources |> Array.iteri (fun i s -> offsets.[i + 1] <- offsets.[i] + int64 s.Length)
+        let buf = Array.zeroCreate<byte> (int offsets.[sources.Length])
+        sources |> Array.iteri (fun i s -> s |> Array.iteri (fun j b -> buf.[int offsets.[i] + j] <- byte (BioItem.symbol b)))
+        buf, offsets
+
+    let makeParams (k:int) (pc:float) (alphabet:#IBioItem[]) (pcv:CompositeVector.ProbabilityCompositeVector) phaseMask =
+        let sym c = pcv.Array.[int c - 42]
+        let mutable p = GibbsParams()
+        p.k <- k; p.alphabetSize <- alphabet.Length; p.pseudocount <- pc
+        p.bgA <- sym 'A'; p.bgC <- sym 'C'; p.bgG <- sym 'G'; p.bgT <- sym 'T'
+        p.sampler <- 0; p.phaseShifts <- 1; p.maxSweeps <- 0; p.phaseMask <- phaseMask
+        p
+
+    /// n restarts as n chains of one launch; returns (scores, sites, sums) per restart
+    let runChains (phaseMask:int) (nChains:int) (seed:uint64) k pc alphabet sources pcv (start:((float*int)[]) option) =
+        let buf, offsets = flatten sources
+        let mutable h = IntPtr.Zero
+        check (gibbs_create(buf, offsets, sources.Length, 0, &h))
+        try
+            let n = sources.Length
+            match start with
+            | Some st ->
+                let sites  = Array.init (nChains * n) (fun i -> snd st.[i % n])
+                let scores = Array.init (nChains * n) (fun i -> fst st.[i % n])
+                check (gibbs_set_start_state(h, nChains, sites, scores))
+            | None -> ()
+            let mutable p = makeParams k pc alphabet pcv phaseMask
+            let sites, scores, sums = Array.zeroCreate (nChains * n), Array.zeroCreate (nChains * n), Array.zeroCreate nChains
+            let mutable best = 0
+            let mutable stats = GibbsRunStats()
+            check (gibbs_run(h, &p, nChains, 0L, seed, 0, null, 0L, sites, scores, sums, &best, null, &stats))
+            Array.init nChains (fun c -> Array.init n (fun i -> scores.[c * n + i], sites.[c * n + i])), sums
+        finally
+            gibbs_destroy h |> ignore
+
+open CompositeVector
+
+module SiteSampler =
+
+    let private seedOf (seed:uint64 option) = defaultArg seed (uint64 DateTime.Now.Ticks)
+
+    /// fs:412-430
+    let getPWMOfRandomStartsWithBPV motifLength pseudoCount alphabet sources (pcv:ProbabilityCompositeVector) =
+        (Native.runChains 1 1 (seedOf None) motifLength pseudoCount alphabet sources pcv None |> fst).[0]
+    /// fs:381-408
+    let findBestMotifWithStartPosition motifLength pseudoCount alphabet sources pcv (startPositions:(float*int)[]) =
+        (Native.runChains 2 1 0UL motifLength pseudoCount alphabet sources pcv (Some startPositions) |> fst).[0]
+    /// fs:350-377
+    let getLeftShiftedBestPWMSsWithBPV motifLength pseudoCount alphabet sources pcv (startPositions:(float*int)[]) =
+        (Native.runChains 4 1 0UL motifLength pseudoCount alphabet sources pcv (Some startPositions) |> fst).[0]
+    /// fs:318-346
+    let getRightShiftedBestPWMSsWithBPV motifLength pseudoCount alphabet sources pcv (startPositions:(float*int)[]) =
+        (Native.runChains 8 1 0UL motifLength pseudoCount alphabet sources pcv (Some startPositions) |> fst).[0]
+    /// fs:691-695
+    let doSiteSamplingWithBPV motifLength pseudoCount alphabet sources (pcv:ProbabilityCompositeVector) =
+        (Native.runChains 15 1 (seedOf None) motifLength pseudoCount alphabet sources pcv None |> fst).[0]
+
+    /// fs:434-459. The numberOfRepetitions + 1 restarts the loop can consume run as parallel chains;
+    /// the loop itself (promote-or-restart, quirk A.6-8) is replayed over their results unchanged.
+    let getMotifsWithBestInformationContentWithBPV (numberOfRepetitions:int) motifLength pseudoCount alphabet sources (pcv:ProbabilityCompositeVector) =
+        let restarts, _ = Native.runChains 15 (numberOfRepetitions + 1) (seedOf None) motifLength pseudoCount alphabet sources pcv None
+        let mutable next = 0
+        let rec loop (n:int) (acc:(float*int)[]) (bestPWMS:(float*int)[]) =
+            if n > numberOfRepetitions then bestPWMS
+            elif acc = bestPWMS then bestPWMS
+            else
+                let ic (x:(float*int)[]) = x |> Array.map fst |> Array.sum
+                if ic acc > ic bestPWMS then loop (n + 1) [||] (if Array.isEmpty acc then bestPWMS else acc)
+                else
+                    let pwms = restarts.[next]
+                    next <- next + 1
+                    loop (n + 1) pwms bestPWMS
+        loop 0 [||] [|0., 0|]

@@ -117,35 +117,51 @@ def doSiteSamplingWithBPV(motifLength, pseudoCount, alphabet, sources, pcv, **kw
     return _run_phases(mask, motifLength, pseudoCount, alphabet, sources, pcv, **kw)
 
 
-def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, restart_sites: np.ndarray) -> SiteArray:
+def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, restart_sites: np.ndarray,
+                        restart_sums: Optional[np.ndarray] = None) -> SiteArray:
     """The promote-or-restart loop of fs:435-459 (quirk A.6-8) over restarts that already ran.
 
     The reference runs restarts one after another; here restart r is chain r of one kernel launch,
     and this function replays the loop's decisions over their results in the same order, so the
-    returned array is the one the sequential loop would return.
+    returned array is the one the sequential loop would return. `restart_sums` = the left-to-right
+    Array.sum of each restart's scores (computed on the GPU in that order); recomputed here if absent.
+    State is kept as restart indices (None = [||], -1 = the initial [|(0., 0)|]).
     """
-    acc: list = []
-    best: list = [(0.0, 0)]
-    r = 0
-    n = 0
-    while True:
-        if n > numberOfRepetitions:
-            return best
-        if acc == best:  # structural equality of (float*int)[]
-            return best
-        ia = 0.0
-        for s, _ in acc:
-            ia = ia + s
-        ib = 0.0
-        for s, _ in best:
-            ib = ib + s
-        if ia > ib:
-            best = acc if acc else best
-            acc = []
+    def total(i) -> float:
+        if i is None:
+            return 0.0
+        if i < 0:
+            return 0.0
+        if restart_sums is not None:
+            return float(restart_sums[i])
+        t = 0.0
+        for v in restart_scores[i]:
+            t = t + float(v)
+        return t
+
+    def same(a, b) -> bool:  # structural equality of two (float*int)[]
+        if a is None or b is None:
+            return a is None and b is None
+        if a < 0 or b < 0:
+            i = a if b < 0 else b
+            if i < 0:
+                return True
+            return restart_scores.shape[1] == 1 and restart_scores[i][0] == 0.0 and restart_sites[i][0] == 0
+        return bool(np.array_equal(restart_sites[a], restart_sites[b]) and
+                    np.array_equal(restart_scores[a], restart_scores[b]))
+
+    acc, best, r, n = None, -1, 0, 0
+    while n <= numberOfRepetitions and not same(acc, best):
+        if total(acc) > total(best):
+            best = acc if acc is not None else best
+            acc = None
         else:
-            acc = _to_site_array(restart_scores[r], restart_sites[r])
+            acc = r
             r += 1
         n += 1
+    if best < 0:
+        return [(0.0, 0)]
+    return _to_site_array(restart_scores[best], restart_sites[best])
 
 
 def getMotifsWithBestInformationContentWithBPV(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, pcv, *,
@@ -161,7 +177,7 @@ def getMotifsWithBestInformationContentWithBPV(numberOfRepetitions, motifLength,
         if uniforms is not None:
             u = np.asarray(uniforms, dtype=np.float64).reshape(n_restarts, -1)  # restart r consumes row r
         res = eng.run(params, n_restarts, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
-        return replay_restart_loop(int(numberOfRepetitions), res.scores, res.sites)
+        return replay_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
     finally:
         if own:
             eng.close()
