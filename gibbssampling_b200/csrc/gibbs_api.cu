@@ -171,9 +171,19 @@ template <int KPV>
 int32_t launch_chain_kp(gibbs_handle *h, const ChainArgs &a) {
     int team = h->team_warps;
     const int smem4 = team_smem_bytes(a.s.row_words, 4), smem1 = team_smem_bytes(a.s.row_words, 1);
-    if (team == 0) team = (a.s.n >= 4 && smem4 <= 200 * 1024) ? 4 : 1;
+    if (team == 0) { // 8 warps pay off only while the GPU has idle warp slots (few chains); measured on C2-shaped input
+        const int smem8 = team_smem_bytes(a.s.row_words, 8);
+        if (a.s.n >= 8 && a.n_chains <= 2 * h->sm_count && smem8 <= 200 * 1024) team = 8;
+        else team = (a.s.n >= 4 && smem4 <= 200 * 1024) ? 4 : 1;
+    }
     h->run_team = team;
-    if (team == 4) {
+    if (team == 8) {
+        const int smem8 = team_smem_bytes(a.s.row_words, 8);
+        if (smem8 > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for 8 warps per chain");
+        int32_t rc = set_smem(chain_kernel<KPV, 8>, smem8);
+        if (rc) return rc;
+        chain_kernel<KPV, 8><<<a.n_chains, 256, smem8, h->stream>>>(a);
+    } else if (team == 4) {
         if (smem4 > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for 4 warps per chain");
         int32_t rc = set_smem(chain_kernel<KPV, 4>, smem4);
         if (rc) return rc;
@@ -424,7 +434,7 @@ int32_t gibbs_num_sequences(const gibbs_handle *h) { return h ? h->n : 0; }
 
 int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps) {
     if (!h) return fail(GIBBS_ERR_ARG, "null handle");
-    if (warps != 0 && warps != 1 && warps != 4) return fail(GIBBS_ERR_ARG, "team size must be 0 (auto), 1 or 4 warps");
+    if (warps != 0 && warps != 1 && warps != 4 && warps != 8) return fail(GIBBS_ERR_ARG, "team size must be 0 (auto), 1, 4 or 8 warps");
     h->team_warps = warps;
     return GIBBS_OK;
 }

@@ -80,7 +80,7 @@ constexpr int WARP_TABLE_BYTES = 1024 + 1024 + 512 + 512;
 struct TeamSmem {
     uint64_t *bar;        // [ring] mbarriers of the staged rows
     int32_t *total;       // [32*4] counts over ALL current sites of the chain
-    int32_t *flags;       // [8]  per-warp outcome of a round
+    int32_t *flags;       // [2][8] per-warp outcome of a round (double-buffered)
     uint32_t *lut;        // [16] histogram increments per nibble (hist_lut_entry)
     double *blk_hv;       // [2][32] state of two 32-sequence blocks
     int32_t *blk_site;    // [2][32]
@@ -90,7 +90,7 @@ struct TeamSmem {
 };
 
 constexpr int MAX_RING = 16;
-constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 32 + 512 + 256 + 256 + 64; // bar, total, flags, blk_hv, blk_site, blk_len, lut
+constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 64 + 512 + 256 + 256 + 64; // bar, total, flags, blk_hv, blk_site, blk_len, lut
 
 __host__ __device__ constexpr int ring_slots(int team_warps) { return 2 * team_warps < 4 ? 4 : 2 * team_warps; }
 __host__ __device__ inline int team_smem_bytes(int row_words, int team_warps) {
@@ -102,10 +102,10 @@ __device__ __forceinline__ TeamSmem carve_smem(unsigned char *base, int team_war
     s.bar = reinterpret_cast<uint64_t *>(base);
     s.total = reinterpret_cast<int32_t *>(base + 128);
     s.flags = reinterpret_cast<int32_t *>(base + 640);
-    s.blk_hv = reinterpret_cast<double *>(base + 672);
-    s.blk_site = reinterpret_cast<int32_t *>(base + 1184);
-    s.blk_len = reinterpret_cast<int32_t *>(base + 1440);
-    s.lut = reinterpret_cast<uint32_t *>(base + 1696);
+    s.blk_hv = reinterpret_cast<double *>(base + 704);
+    s.blk_site = reinterpret_cast<int32_t *>(base + 1216);
+    s.blk_len = reinterpret_cast<int32_t *>(base + 1472);
+    s.lut = reinterpret_cast<uint32_t *>(base + 1728);
     s.warp_tables = base + TEAM_FIXED_BYTES;
     s.row0 = reinterpret_cast<uint32_t *>(base + TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES);
     return s;

@@ -150,7 +150,7 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
 //     in the next round, which starts right after the mover. The committed sequence of site updates is
 //     therefore exactly the reference's sequential sweep.
 template <int KP, int T>
-__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const ChainArgs a) {
+__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
@@ -201,19 +201,23 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const 
         bool changed = false;
         int cur_blk = 0;
         int n0 = 0;
+        // greedy sweeps: how many sequences a round attempts. Halved after a round that discarded work
+        // (a site moved), doubled after a quiet round: early sweeps, where almost every update moves a
+        // site, run nearly sequentially and waste no issue slots; late sweeps run T wide.
+        int width = (phase == PH_GREEDY) ? 1 : T;
+        unsigned round = 0;
         while (n0 < N) {
             if ((n0 >> 5) != cur_blk) { // entering a new block: fetch the one after it (not read this round)
                 cur_blk = n0 >> 5;
                 load_block(cur_blk + 1);
             }
             const int n = n0 + warp;
-            const bool active = n < N;
+            const bool active = n < N && warp < width;
             int flag = 0, site_n = 0, w = 0, Wn = 0;
             double p = 0.0;
-            uint64_t own = 0;
-            const uint32_t *row = nullptr;
+            uint64_t own = 0, neu = 0;
             if (active) {
-                row = ring.wait(vbase + (uint32_t)n);
+                const uint32_t *row = ring.wait(vbase + (uint32_t)n);
                 const int o = ((n >> 5) & 1) * 32 + (n & 31);
                 const int len_n = S.blk_len[o];
                 Wn = len_n - k + 1;
@@ -232,52 +236,54 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : 7)) chain_kernel(const 
                 if (phase != PH_INIT) {
                     accept = score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0); // fs:402
                     moved = accept && (w != site_n);
+                    if (moved && phase == PH_GREEDY) neu = kmer_shared<KP>(row, w); // rows are not read after the sync
                 }
                 flag = (accept ? 1 : 0) | (moved ? 2 : 0) | (slow ? 4 : 0);
             }
-            if (lane == 0) S.flags[warp] = flag;
+            int32_t *flags = S.flags + (round & 1) * T; // double-buffered: one team sync per round suffices
+            ++round;
+            if (lane == 0) flags[warp] = flag;
             team_sync<T>();
             int first_mover = T; // greedy only: later warps of the round saw stale counts
             bool any_moved = false;
 #pragma unroll
             for (int t = T - 1; t >= 0; --t) {
-                const bool mv = (S.flags[t] & 2) != 0;
+                const bool mv = (flags[t] & 2) != 0;
                 if (mv && phase == PH_GREEDY) first_mover = t;
                 any_moved |= mv;
             }
-            const int last_commit = min(first_mover, T - 1);
-            if (phase == PH_GREEDY) {
-                any_moved = first_mover < T;
-            }
-            changed |= any_moved;
+            const int last_commit = min(first_mover, width - 1);
+            changed |= any_moved; // (greedy: any mover of the round implies a committed mover)
             if (active) {
                 if (warp <= last_commit) {
                     st_updates += 1;
                     st_windows += (unsigned long long)Wn;
                     st_slow += (flag & 4) ? 1 : 0;
-                    if (flag & 1) {
-                        if (lane == 0) {
-                            sites[n] = w;
-                            hv[n] = p;
-                        }
-                        if (phase == PH_GREEDY && (flag & 2)) { // in-place sweep: later n see the new site (fs:388)
-                            const uint64_t neu = kmer_shared<KP>(row, w);
-                            if (lane < k) {
-                                const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
-                                if (bo != bn) {
-                                    S.total[lane * 4 + bo] -= 1;
-                                    S.total[lane * 4 + bn] += 1;
-                                }
-                            }
-                        }
+                    if ((flag & 1) && lane == 0) {
+                        sites[n] = w;
+                        hv[n] = p;
                     }
                 } else {
                     st_spec += 1;
                 }
             }
             n0 += min(last_commit + 1, N - n0);
-            team_sync<T>(); // counts updated; rows of the committed visits are free
-            if (tid == 0) ring.fill(vbase + (uint32_t)n0 + R);
+            if (tid == 0) ring.fill(vbase + (uint32_t)n0 + R); // rows of the committed visits are free
+            if (phase == PH_GREEDY) {
+                if (first_mover < T) { // in-place sweep: later n see the new site (fs:388): -old k-mer, +new k-mer
+                    if (warp == first_mover && lane < k) {
+                        const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
+                        if (bo != bn) {
+                            S.total[lane * 4 + bo] -= 1;
+                            S.total[lane * 4 + bn] += 1;
+                        }
+                    }
+                    team_sync<T>(); // counts updated before the next round builds its tables
+                    width = max(1, width >> 1);
+                } else {
+                    width = min(T, width * 2);
+                }
+            }
         }
         vbase += (uint32_t)N;
         st_sweeps += 1;
