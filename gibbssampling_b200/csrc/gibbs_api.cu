@@ -6,6 +6,7 @@
 // point returns GIBBS_ERR_CUDA.
 #include "../../include/gibbs_b200.h"
 #include "gibbs_kernels.cuh"
+#include "gibbs_motif.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -91,6 +92,13 @@ struct gibbs_handle {
     int32_t run_chains = 0, run_k = 0, run_fast = 0, run_launches = 0;
     bool run_done = false;
     int32_t start_chains = 0; // chains covered by gibbs_set_start_state (0 = none pending)
+    // MotifSampler: background-only window probabilities (depend on sequences, k and pcv only)
+    DevBuf<double> bg_g, bg_sum, bg_max, cand_l;
+    DevBuf<int32_t> bg_max_i, cand_w, err_flag;
+    bool bg_valid = false;
+    int32_t bg_k = 0, bg_wstride = 0;
+    double bg_q[4] = {0, 0, 0, 0};
+    int32_t run_sampler = 0;
     int32_t team_warps = 0;   // 0 = choose per launch; 1 or 4 = forced (gibbs_set_team_warps)
     int32_t run_team = 0;
     int sm_count = 0;
@@ -264,6 +272,76 @@ int32_t launch_all_counts(gibbs_handle *h, const DeviceSeqs &s, const int32_t *s
     return GIBBS_OK;
 }
 
+DeviceSeqs dev_seqs(const gibbs_handle *h);
+
+int32_t ensure_bgtab(gibbs_handle *h, const gibbs_params *p, int *launches) {
+    bool same = h->bg_valid && h->bg_k == p->k;
+    for (int b = 0; b < 4 && same; ++b) same = h->bg_q[b] == p->bg[b];
+    if (same) return GIBBS_OK;
+    const int wstride = h->max_len - p->k + 1;
+    CUDA_TRY(h->bg_g.reserve((size_t)h->n * wstride));
+    CUDA_TRY(h->bg_sum.reserve((size_t)h->n));
+    CUDA_TRY(h->bg_max.reserve((size_t)h->n));
+    CUDA_TRY(h->bg_max_i.reserve((size_t)h->n));
+    bg_setup_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(dev_seqs(h), p->k, p->bg[0], p->bg[1], p->bg[2], p->bg[3],
+                                                                wstride, h->bg_g.p, h->bg_sum.p, h->bg_max.p, h->bg_max_i.p);
+    CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    h->bg_k = p->k;
+    h->bg_wstride = wstride;
+    memcpy(h->bg_q, p->bg, sizeof h->bg_q);
+    h->bg_valid = true;
+    return GIBBS_OK;
+}
+
+BgTables bg_tables(const gibbs_handle *h) {
+    BgTables b;
+    b.g = h->bg_g.p;
+    b.gsum = h->bg_sum.p;
+    b.gmax = h->bg_max.p;
+    b.gmax_i = h->bg_max_i.p;
+    b.wstride = h->bg_wstride;
+    return b;
+}
+
+int32_t launch_motif(gibbs_handle *h, const MotifArgs &m) {
+    const int kp = (m.c.k + 1) / 2;
+    const int smem = team_smem_bytes(m.c.s.row_words, 1);
+    switch (kp) {
+#define X(KPV)                                                                          \
+    case KPV: {                                                                         \
+        int32_t rc = set_smem(motif_kernel<KPV>, smem);                                 \
+        if (rc) return rc;                                                              \
+        motif_kernel<KPV><<<m.c.n_chains, 32, smem, h->stream>>>(m);                    \
+        break;                                                                          \
+    }
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
+int32_t launch_roulette(gibbs_handle *h, const RouletteArgs &r) {
+    const int kp = (r.p.k + 1) / 2;
+    const int smem = team_smem_bytes(r.p.s.row_words, 1);
+    switch (kp) {
+#define X(KPV)                                                                          \
+    case KPV: {                                                                         \
+        int32_t rc = set_smem(roulette_kernel<KPV>, smem);                              \
+        if (rc) return rc;                                                              \
+        roulette_kernel<KPV><<<1, 32, smem, h->stream>>>(r);                            \
+        break;                                                                          \
+    }
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
 DeviceSeqs dev_seqs(const gibbs_handle *h) {
     DeviceSeqs s;
     s.packed = h->packed.p;
@@ -309,6 +387,7 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
     CUDA_TRY(cudaStreamSynchronize(h->stream)); // also keeps `rel` alive until the copy is done
     h->n = 0;
     h->wtab_valid = false;
+    h->bg_valid = false;
     h->run_done = false;
     if (bad)
         return fail(GIBBS_ERR_SYMBOL, "symbol '%c' (0x%02x) is outside A,C,G,T (IndexOutOfRangeException analogue, fs:17)",
@@ -407,6 +486,8 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->wtab.release(); h->prim_sites.release(); h->prim_i32.release(); h->prim_f64.release();
     h->sites.release(); h->hv.release(); h->scores.release(); h->sums.release(); h->uniforms.release();
     h->stats.release(); h->best.release();
+    h->bg_g.release(); h->bg_sum.release(); h->bg_max.release(); h->bg_max_i.release();
+    h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -525,8 +606,46 @@ int32_t gibbs_pick_argmax(gibbs_handle *h, const int32_t *sites, int32_t heldout
 
 int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldout, const gibbs_params *p, double u,
                             double *pwms_out, int32_t *site_out) {
-    (void)h; (void)sites; (void)heldout; (void)p; (void)u; (void)pwms_out; (void)site_out;
-    return fail(GIBBS_ERR_UNSUPPORTED, "gibbs_pick_roulette: MotifSampler kernels are not built yet");
+    int32_t rc = check_params(h, p);
+    if (rc) return rc;
+    if (heldout < 0 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
+    rc = set_device(h);
+    if (rc) return rc;
+    rc = stage_sites(h, sites, heldout, p->k);
+    if (rc) return rc;
+    rc = ensure_wtab(h, p, nullptr);
+    if (rc) return rc;
+    rc = ensure_bgtab(h, p, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(h->cand_l.reserve((size_t)h->bg_wstride));
+    CUDA_TRY(h->cand_w.reserve((size_t)h->bg_wstride));
+    CUDA_TRY(h->prim_f64.reserve(8));
+    CUDA_TRY(h->prim_i32.reserve(GIBBS_MAX_K * 4 + 8));
+    RouletteArgs r{};
+    r.p.s = dev_seqs(h);
+    r.p.wtab = h->wtab.p;
+    r.p.sites = h->prim_sites.p;
+    r.p.heldout = heldout;
+    r.p.k = p->k;
+    r.p.fast_ok = fast_path_ok(h, p->k);
+    r.bg = bg_tables(h);
+    r.cutoff = p->cutoff;
+    r.u = u;
+    r.cand_l = h->cand_l.p;
+    r.cand_w = h->cand_w.p;
+    r.pwms_out = h->prim_f64.p;
+    r.site_out = h->prim_i32.p;
+    rc = launch_roulette(h, r);
+    if (rc) return rc;
+    double pw = 0.0;
+    int32_t so[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(&pw, r.pwms_out, sizeof pw, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(so, r.site_out, sizeof so, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!so[1]) return fail(GIBBS_ERR_ROULETTE, "roulette pick %.17g lies beyond the accumulated mass (ArgumentException, fs:753)", u);
+    if (pwms_out) *pwms_out = pw;
+    if (site_out) *site_out = so[0];
+    return GIBBS_OK;
 }
 
 int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base, uint64_t seed,
@@ -534,7 +653,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     int32_t rc = check_params(h, p);
     if (rc) return rc;
     if (n_chains < 1) return fail(GIBBS_ERR_ARG, "n_chains must be >= 1");
-    if (p->sampler != GIBBS_SITE_SAMPLER) return fail(GIBBS_ERR_UNSUPPORTED, "sampler %d: MotifSampler kernels are not built yet", p->sampler);
+    if (p->sampler != GIBBS_SITE_SAMPLER && p->sampler != GIBBS_MOTIF_SAMPLER) return fail(GIBBS_ERR_ARG, "unknown sampler %d", p->sampler);
     if (rng_mode != GIBBS_RNG_PHILOX && rng_mode != GIBBS_RNG_INJECTED) return fail(GIBBS_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (rng_mode == GIBBS_RNG_INJECTED && (!uniforms || uniforms_per_chain < 0)) return fail(GIBBS_ERR_ARG, "injected uniforms missing");
     rc = set_device(h);
@@ -558,10 +677,16 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     a.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 1000000;
     a.fast_ok = fast_path_ok(h, p->k);
     a.sampler = p->sampler;
-    a.phase_mask = p->phase_mask ? p->phase_mask
-                                 : (GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | (p->phase_shifts ? (GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT) : 0));
-    if (a.phase_mask & ~(GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT))
-        return fail(GIBBS_ERR_UNSUPPORTED, "phase_mask 0x%x: MotifSampler phases are not built yet", a.phase_mask);
+    const int site_phases = GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT;
+    const int motif_phases = GIBBS_PHASE_INIT | GIBBS_PHASE_STOCHASTIC | GIBBS_PHASE_MOTIF_GREEDY;
+    if (p->sampler == GIBBS_SITE_SAMPLER) {
+        a.phase_mask = p->phase_mask ? p->phase_mask
+                                     : (GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | (p->phase_shifts ? (GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT) : 0));
+        if (a.phase_mask & ~site_phases) return fail(GIBBS_ERR_ARG, "phase_mask 0x%x has phases that are not SiteSampler phases", a.phase_mask);
+    } else {
+        a.phase_mask = p->phase_mask ? p->phase_mask : motif_phases;
+        if (a.phase_mask & ~motif_phases) return fail(GIBBS_ERR_ARG, "phase_mask 0x%x has phases that are not MotifSampler phases", a.phase_mask);
+    }
     if (!(a.phase_mask & GIBBS_PHASE_INIT) && h->start_chains != n_chains)
         return fail(GIBBS_ERR_ARG, "phase_mask without GIBBS_PHASE_INIT needs gibbs_set_start_state for %d chains", n_chains);
     h->start_chains = 0;
@@ -585,9 +710,29 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     a.stats = h->stats.p;
     a.cutoff = p->cutoff;
     memcpy(a.bg, p->bg, sizeof a.bg);
-    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    rc = launch_chain(h, a);
-    if (rc) return rc;
+    if (p->sampler == GIBBS_MOTIF_SAMPLER) {
+        rc = ensure_bgtab(h, p, &launches);
+        if (rc) return rc;
+        CUDA_TRY(h->cand_l.reserve((size_t)n_chains * h->bg_wstride));
+        CUDA_TRY(h->cand_w.reserve((size_t)n_chains * h->bg_wstride));
+        CUDA_TRY(h->err_flag.reserve(1));
+        CUDA_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int32_t), h->stream));
+        MotifArgs m{};
+        m.c = a;
+        m.bg = bg_tables(h);
+        m.cand_l = h->cand_l.p;
+        m.cand_w = h->cand_w.p;
+        m.error = h->err_flag.p;
+        CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+        rc = launch_motif(h, m);
+        if (rc) return rc;
+        h->run_team = 1;
+    } else {
+        CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+        rc = launch_chain(h, a);
+        if (rc) return rc;
+    }
+    h->run_sampler = p->sampler;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     ++launches;
     best_chain_kernel<<<1, 32, 0, h->stream>>>(h->sums.p, n_chains, h->best.p);
@@ -643,7 +788,11 @@ int32_t gibbs_fetch(gibbs_handle *h, int32_t *sites_out, double *scores_out, dou
     if (sums_out) CUDA_TRY(cudaMemcpyAsync(sums_out, h->sums.p, (size_t)h->run_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     unsigned long long st[ST_NSLOTS];
     CUDA_TRY(cudaMemcpyAsync(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    int32_t roulette_error = 0;
+    if (h->run_sampler == GIBBS_MOTIF_SAMPLER)
+        CUDA_TRY(cudaMemcpyAsync(&roulette_error, h->err_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (roulette_error) return fail(GIBBS_ERR_ROULETTE, "a roulette pick lay beyond the accumulated mass (ArgumentException, fs:753)");
     int extra_launches = 0;
     if (counts_out) {
         rc = launch_all_counts(h, dev_seqs(h), h->sites.p + (size_t)best * h->n, h->run_k, h->best.p + 1);

@@ -1,0 +1,323 @@
+// gibbssampling_b200/csrc/gibbs_motif.cuh -- MotifSampler with a fixed background, motifAmount = 1
+// (fs:709-881): candidate list, roulette-wheel pick, the synchronous stochastic sweep and the greedy
+// sweeps. One warp runs one chain sequentially; every window is scored in float64 because the candidate
+// list needs every window above the cut-off, not just the maximum.
+//
+// MotifIndex state per sequence: site (-1 = Positions []) and PWMS (log2 score of the site, or the raw
+// background probability of a window when "no site" was picked, fs:774-777).
+#pragma once
+#include "gibbs_device.cuh"
+#include "gibbs_kernels.cuh"
+
+namespace gibbs {
+
+enum MotifPhase { MPH_INIT = 0, MPH_STOCH = 1, MPH_GREEDY = 2, MPH_DONE = 3 };
+
+// background-only window probabilities depend on the sequence and the fixed pcv only: computed once
+struct BgTables {
+    const double *g;       // [n][wstride] calculateSegmentScoreBy pcv window (fs:123-124, fs:776)
+    const double *gsum;    // [n] sequential sum of g (the List.sum partial after the background entries, fs:748)
+    const double *gmax;    // [n] first maximum of g ...
+    const int32_t *gmax_i; // [n] ... and its window (List.sortByDescending is stable, fs:812)
+    int32_t wstride;
+};
+
+struct MotifArgs {
+    ChainArgs c;
+    BgTables bg;
+    double *cand_l;        // [chains][wstride] candidate PWMS scratch (ascending window order)
+    int32_t *cand_w;       // [chains][wstride]
+    int32_t *error;        // set to 1 when a roulette pick ran past the list (fs:753)
+};
+
+// one thread per sequence
+__global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1, double q2, double q3, int wstride, double *g,
+                                double *gsum, double *gmax, int32_t *gmax_i) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= s.n) return;
+    const uint32_t *row = s.packed + (size_t)n * s.row_words;
+    const int W = s.len[n] - k + 1;
+    double sum = 0.0, best = 0.0;
+    int best_i = 0;
+    for (int w = 0; w < W; ++w) {
+        double v = 1.0;
+        for (int j = 0; j < k; ++j) {
+            const int pos = w + j;
+            const int b = (row[pos >> 4] >> ((pos & 15) * 2)) & 3;
+            v = __dmul_rn(v, b == 0 ? q0 : b == 1 ? q1 : b == 2 ? q2 : q3);
+        }
+        g[(size_t)n * wstride + w] = v;
+        sum = __dadd_rn(sum, v);
+        if (w == 0 || v > best) {
+            best = v;
+            best_i = w;
+        }
+    }
+    gsum[n] = sum;
+    gmax[n] = best;
+    gmax_i[n] = best_i;
+}
+
+// calculateNormalizedSegmentScores (fs:759-784), motifAmount = 1: the size-1 candidates, ascending
+// position, each with log2(score) > cutOff (fs:735). Written to cand_l / cand_w; returns their number.
+// Also returns the first maximum by PWMS among them (best_l = -inf when there is none).
+template <int KP>
+__device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint32_t *row, int W, int k, double cutoff,
+                                                double raw_gate, double *cand_l, int32_t *cand_w, int lane,
+                                                double &best_l, int &best_w) {
+    int count = 0;
+    double bl = -INFINITY;
+    int bw = INT32_MAX;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+        const int w = w0 + lane;
+        bool is_c = false;
+        double l = 0.0;
+        if (w < W) {
+            const double s = exact_window<KP>(row, w, k, T.wcol);
+            if (s > raw_gate) { // cheap gate just below 2^cutOff; the decision itself is made on the log
+                l = log2_ref(s);
+                is_c = l > cutoff;
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, is_c);
+        if (is_c) {
+            const int at = count + __popc(m & ((1u << lane) - 1u));
+            cand_l[at] = l;
+            cand_w[at] = w;
+            if (l > bl) { // ascending windows per lane: strict > keeps the first maximum
+                bl = l;
+                bw = w;
+            }
+        }
+        count += __popc(m);
+    }
+    warp_argmax(bl, bw); // (largest PWMS, lowest window)
+    best_l = bl;
+    best_w = bw;
+    __syncwarp();
+    return count;
+}
+
+// rouletteWheelSelection (fs:746-754) over [W background entries] ++ [candidates]: exact sequential
+// float64 semantics (sum from 0.0 in list order, weights PWMS/sum, inclusive bounds on both sides).
+// Returns false when the pick ran past the list (the reference throws, fs:753).
+__device__ __forceinline__ bool motif_roulette(const double *g, double gsum, int W, const double *cand_l,
+                                               const int32_t *cand_w, int n_cand, double pick, int lane, double &pwms_out,
+                                               int &site_out) {
+    double sum = gsum; // the background entries come first in the list; gsum was accumulated in that order
+    for (int i = 0; i < n_cand; ++i) sum = __dadd_rn(sum, cand_l[i]);
+    double acc = 0.0;
+    const int total = W + n_cand;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        const int i = i0 + lane;
+        double v = 0.0;
+        if (i < total) v = (i < W) ? g[i] : cand_l[i - W];
+        const double wgt = __ddiv_rn(v, sum); // divisions in parallel, accumulation in list order
+        const int lim = min(32, total - i0);
+        for (int j = 0; j < lim; ++j) {
+            const double wj = __shfl_sync(FULL, wgt, j);
+            const double hi = __dadd_rn(acc, wj);
+            if (acc <= pick && pick <= hi) {
+                const int idx = i0 + j;
+                if (idx < W) {
+                    pwms_out = g[idx];
+                    site_out = -1;
+                } else {
+                    pwms_out = cand_l[idx - W];
+                    site_out = cand_w[idx - W];
+                }
+                return true;
+            }
+            acc = hi;
+        }
+    }
+    return false;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ChainArgs &a = m.c;
+    const int lane = threadIdx.x;
+    const int chain = blockIdx.x;
+    const TeamSmem S = carve_smem(smem_raw, 1);
+    const WarpTables WT = warp_tables(S, 0);
+    const int N = a.s.n, k = a.k;
+    int32_t *sites = a.sites + (size_t)chain * N;
+    double *pw = a.scores + (size_t)chain * N; // PWMS of the MotifIndex state
+    double *hv = a.hv + (size_t)chain * N;
+    double *cand_l = m.cand_l + (size_t)chain * m.bg.wstride;
+    int32_t *cand_w = m.cand_w + (size_t)chain * m.bg.wstride;
+    const uint64_t chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
+    const double raw_gate = exp2(a.cutoff) * (1.0 - 0x1p-30);
+
+    RowRing<4> ring;
+    ring.init(S, a.s, 0, lane);
+    if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
+    __syncwarp();
+    if (lane == 0) ring.fill(4);
+
+    unsigned long long st_updates = 0, st_windows = 0;
+    int st_sweeps = 0, capped = 0;
+    uint32_t v = 0;
+
+    int phase = MPH_INIT;
+    while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_INIT ? 0 : phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
+    int sweeps_in_phase = 0;
+    while (phase != MPH_DONE) {
+        if (phase != MPH_INIT && (phase == MPH_STOCH || sweeps_in_phase == 0))
+            site_counts<KP, 1>(a.s, sites, -1, k, SHIFT_NONE, S.total, S.lut, lane);
+        bool changed = false;
+        for (int n = 0; n < N; ++n, ++v) {
+            const uint32_t *row = ring.wait(v);
+            const int len_n = __ldg(a.s.len + n);
+            const int W = len_n - k + 1;
+            if (phase == MPH_INIT) { // getPWMOfRandomStartsWithBPV |> createMotifIndex prob [position] (fs:876-877)
+                random_loo_counts<KP>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
+                build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+                double p;
+                int w;
+                pick_argmax<KP>(WT, row, W, k, a.fast_ok, lane, p, w);
+                if (lane == 0) {
+                    sites[n] = w;
+                    pw[n] = log2_ref(p);
+                }
+            } else {
+                const int site_n = __ldcg(sites + n);
+                const double pw_n = __ldcg(pw + n);
+                const bool has_own = site_n >= 0;
+                const uint64_t own = has_own ? kmer_shared<KP>(row, site_n) : 0;
+                build_tables<KP>(WT, S.total, has_own, own, k, a.wtab, lane);
+                double best_l;
+                int best_w;
+                const int n_cand = motif_candidates<KP>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w);
+                double new_pw;
+                int new_site;
+                bool take;
+                if (phase == MPH_STOCH) { // fs:828-853: one uniform per n, every n reads the input state
+                    const uint64_t d = (uint64_t)N * (uint64_t)(N - 1) + (uint64_t)n;
+                    double u;
+                    if (a.rng_mode == 0) {
+                        const uint64_t blk = d >> 2;
+                        const uint4 r = philox4x32_10(
+                            make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                        const uint32_t word = (d & 3) == 0 ? r.x : (d & 3) == 1 ? r.y : (d & 3) == 2 ? r.z : r.w;
+                        u = (double)word * (1.0 / 4294967296.0);
+                    } else {
+                        u = ((int64_t)d < a.uniforms_per_chain) ? __ldg(a.uniforms + (size_t)chain * a.uniforms_per_chain + d) : 0.0;
+                    }
+                    const bool ok = motif_roulette(m.bg.g + (size_t)n * m.bg.wstride, __ldg(m.bg.gsum + n), W, cand_l, cand_w,
+                                                   n_cand, u, lane, new_pw, new_site);
+                    if (!ok) {
+                        if (lane == 0) atomicExch(m.error, 1);
+                        new_pw = pw_n;
+                        new_site = site_n;
+                    }
+                    take = true;
+                } else { // fs:788-822: first maximum by PWMS over background entries ++ candidates
+                    const double gmax = __ldg(m.bg.gmax + n);
+                    if (n_cand > 0 && best_l > gmax) {
+                        new_pw = best_l;
+                        new_site = best_w;
+                    } else {
+                        new_pw = gmax;
+                        new_site = -1;
+                    }
+                    take = new_pw > pw_n; // fs:816
+                }
+                if (take) {
+                    if (phase == MPH_GREEDY && new_site != site_n) {
+                        changed = true;
+                        const uint64_t neu = new_site >= 0 ? kmer_shared<KP>(row, new_site) : 0;
+                        if (lane < k) { // in-place sweep: -old k-mer, +new k-mer
+                            if (has_own) S.total[lane * 4 + (int)((own >> (2 * lane)) & 3u)] -= 1;
+                            if (new_site >= 0) S.total[lane * 4 + (int)((neu >> (2 * lane)) & 3u)] += 1;
+                        }
+                    }
+                    if (lane == 0) {
+                        sites[n] = new_site;
+                        pw[n] = new_pw;
+                    }
+                }
+            }
+            st_updates += 1;
+            st_windows += (unsigned long long)W;
+            __syncwarp();
+            if (lane == 0) ring.fill(v + 1 + 4);
+        }
+        st_sweeps += 1;
+        bool next = true;
+        if (phase == MPH_GREEDY) {
+            ++sweeps_in_phase;
+            next = !changed; // Positions(acc) = Positions(bestMotif), fs:791
+            if (!next && sweeps_in_phase >= a.max_sweeps) {
+                next = true;
+                capped = 1;
+            }
+        }
+        if (next) {
+            sweeps_in_phase = 0;
+            ++phase;
+            while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
+        }
+    }
+    if (lane == 0)
+        for (int i = 0; i < 4; ++i) ring.wait(v + (uint32_t)i);
+    __syncwarp();
+    for (int n = lane; n < N; n += 32) hv[n] = __ldcg(pw + n);
+    if (lane == 0) {
+        double sum = 0.0;
+        for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(pw + n));
+        a.sums[chain] = sum;
+        atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
+        atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
+        atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
+        atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
+    }
+}
+
+// primitive: candidate list + one roulette pick for a given state (gibbs_pick_roulette)
+struct RouletteArgs {
+    PrimArgs p;
+    BgTables bg;
+    double cutoff;
+    double u;
+    double *cand_l;
+    int32_t *cand_w;
+    double *pwms_out;
+    int32_t *site_out; // [2]: site, ok flag
+};
+
+template <int KP>
+__global__ void __launch_bounds__(32) roulette_kernel(const RouletteArgs r) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const PrimArgs &a = r.p;
+    const int lane = threadIdx.x;
+    const TeamSmem S = carve_smem(smem_raw, 1);
+    const WarpTables WT = warp_tables(S, 0);
+    RowRing<4> ring;
+    ring.init(S, a.s, a.heldout, lane);
+    if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
+    __syncwarp();
+    if (lane == 0) ring.fill(1);
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, lane);
+    const uint32_t *row = ring.wait(0);
+    build_tables<KP>(WT, S.total, false, 0, a.k, a.wtab, lane);
+    const int W = __ldg(a.s.len + a.heldout) - a.k + 1;
+    double best_l;
+    int best_w;
+    const int n_cand = motif_candidates<KP>(WT, row, W, a.k, r.cutoff, exp2(r.cutoff) * (1.0 - 0x1p-30), r.cand_l, r.cand_w,
+                                            lane, best_l, best_w);
+    double pwms = 0.0;
+    int site = -1;
+    const bool ok = motif_roulette(r.bg.g + (size_t)a.heldout * r.bg.wstride, __ldg(r.bg.gsum + a.heldout), W, r.cand_l,
+                                   r.cand_w, n_cand, r.u, lane, pwms, site);
+    if (lane == 0) {
+        *r.pwms_out = pwms;
+        r.site_out[0] = site;
+        r.site_out[1] = ok ? 1 : 0;
+    }
+}
+
+} // namespace gibbs

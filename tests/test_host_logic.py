@@ -138,3 +138,5 @@ def test_unbuilt_reference_entry_points_say_so():
     with pytest.raises(_abi.GibbsUnsupportedError):
         SiteSampler.doSiteSamplingWithBPV(6, 1e-4, list("AT"), ["ACGTACGT"], ProbabilityCompositeVector())
     assert MotifSampler.createMotifIndex(1.5, [3]) == MotifSampler.MotifIndex(1.5, (3,))
+    with pytest.raises(_abi.GibbsUnsupportedError):
+        MotifSampler.doMotifSamplingWithPCV(2, 6, 1e-4, 1.0, DNA, ["ACGTACGT"], ProbabilityCompositeVector.ofACGT(.25, .25, .25, .25))
