@@ -7,7 +7,6 @@
 #include "../../include/gibbs_b200.h"
 #include "gibbs_kernels.cuh"
 #include "gibbs_motif.cuh"
-#include "gibbs_pool.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -186,21 +185,6 @@ int32_t launch_chain_kp(gibbs_handle *h, const ChainArgs &a) {
         else team = (a.s.n >= 4 && smem4 <= 200 * 1024) ? 4 : 1;
     }
     h->run_team = team;
-    if (team == 32) { // warp pool: one persistent CTA per SM
-        const int smem = pool_smem_bytes(a.s.row_words);
-        if (smem > 220 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for the warp-pool kernel");
-        int32_t rc = set_smem(pool_kernel<KPV>, smem);
-        if (rc) return rc;
-        const int grid = a.n_chains < h->sm_count ? a.n_chains : h->sm_count;
-        const int first_free = grid * POOL_SLOTS;
-        CUDA_TRY(cudaMemcpyAsync(h->flags.p + 4, &first_free, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        PoolArgs pa{};
-        pa.c = a;
-        pa.next_chain = h->flags.p + 4;
-        pool_kernel<KPV><<<grid, POOL_WARPS * 32, smem, h->stream>>>(pa);
-        CUDA_TRY(cudaGetLastError());
-        return GIBBS_OK;
-    }
     if (team == 8) {
         const int smem8 = team_smem_bytes(a.s.row_words, 8);
         if (smem8 > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for 8 warps per chain");
@@ -531,8 +515,7 @@ int32_t gibbs_num_sequences(const gibbs_handle *h) { return h ? h->n : 0; }
 
 int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps) {
     if (!h) return fail(GIBBS_ERR_ARG, "null handle");
-    if (warps != 0 && warps != 1 && warps != 4 && warps != 8 && warps != 32)
-        return fail(GIBBS_ERR_ARG, "team size must be 0 (auto), 1, 4, 8 warps per chain or 32 (warp pool)");
+    if (warps != 0 && warps != 1 && warps != 4 && warps != 8) return fail(GIBBS_ERR_ARG, "team size must be 0 (auto), 1, 4 or 8 warps per chain");
     h->team_warps = warps;
     return GIBBS_OK;
 }
