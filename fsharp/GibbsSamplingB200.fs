@@ -27,6 +27,8 @@ module Native =
         val mutable phaseShifts   : int
         val mutable maxSweeps     : int
         val mutable phaseMask     : int
+        val mutable background    : int   // 0 = fixed pcv (WithBPV), 1 = data-derived (fs:697)
+        val mutable reserved      : int
 
     [<Struct; StructLayout(LayoutKind.Sequential)>]
     type GibbsRunStats =
@@ -85,7 +87,7 @@ module Native =
         let mutable p = GibbsParams()
         p.k <- k; p.alphabetSize <- alphabet.Length; p.pseudocount <- pc
         p.bgA <- sym 'A'; p.bgC <- sym 'C'; p.bgG <- sym 'G'; p.bgT <- sym 'T'
-        p.sampler <- 0; p.phaseShifts <- 1; p.maxSweeps <- 0; p.phaseMask <- phaseMask
+        p.sampler <- 0; p.phaseShifts <- 1; p.maxSweeps <- 0; p.phaseMask <- phaseMask; p.background <- 0
         p
 
     /// n restarts as n chains of one launch; returns (scores, sites, sums) per restart

@@ -53,14 +53,22 @@ def _split_state(startPositions) -> tuple[np.ndarray, np.ndarray]:
     return scores, sites
 
 
+def _params(phase_mask: int, motifLength: int, pseudoCount: float, alphabet, pcv, max_sweeps: int = 0):
+    """pcv given -> the WithBPV family (fixed background); pcv None -> the data-derived family (fs:462, fs:697)."""
+    if pcv is None:
+        _bg_of(alphabet, ProbabilityCompositeVector.ofACGT(1, 1, 1, 1))   # only checks that A,C,G,T are in the alphabet
+        return make_params(motifLength, pseudoCount, len(alphabet), [0.25] * 4, phase_mask=phase_mask,
+                           max_sweeps=max_sweeps, background=_abi.GIBBS_BG_DATA)
+    return make_params(motifLength, pseudoCount, len(alphabet), _bg_of(alphabet, pcv), phase_mask=phase_mask,
+                       max_sweeps=max_sweeps)
+
+
 def _run_phases(phase_mask: int, motifLength: int, pseudoCount: float, alphabet, sources, pcv, *, start=None,
                 seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
                 max_sweeps: int = 0) -> SiteArray:
-    bg = _bg_of(alphabet, pcv)
+    params = _params(phase_mask, motifLength, pseudoCount, alphabet, pcv, max_sweeps)
     eng, own = _engine_for(sources, engine)
     try:
-        params = make_params(motifLength, pseudoCount, len(alphabet), bg, phase_mask=phase_mask,
-                             max_sweeps=max_sweeps)
         if start is not None:
             scores, sites = _split_state(start)
             eng.set_start_state(sites, scores)
@@ -164,15 +172,12 @@ def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, re
     return _to_site_array(restart_scores[best], restart_sites[best])
 
 
-def getMotifsWithBestInformationContentWithBPV(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, pcv, *,
-                                               seed: int = 0, chain: int = 0, uniforms=None,
-                                               engine: Optional[GibbsEngine] = None, max_sweeps: int = 0) -> SiteArray:
-    """fs:434-459. At most numberOfRepetitions + 1 restarts can run; they run as parallel chains."""
-    bg = _bg_of(alphabet, pcv)
+def _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, pcv, *, seed: int = 0, chain: int = 0,
+                  uniforms=None, engine: Optional[GibbsEngine] = None, max_sweeps: int = 0) -> SiteArray:
+    params = _params(0, motifLength, pseudoCount, alphabet, pcv, max_sweeps)
     eng, own = _engine_for(sources, engine)
     try:
         n_restarts = max(int(numberOfRepetitions) + 1, 1)
-        params = make_params(motifLength, pseudoCount, len(alphabet), bg, max_sweeps=max_sweeps)
         u = None
         if uniforms is not None:
             u = np.asarray(uniforms, dtype=np.float64).reshape(n_restarts, -1)  # restart r consumes row r
@@ -183,28 +188,58 @@ def getMotifsWithBestInformationContentWithBPV(numberOfRepetitions, motifLength,
             eng.close()
 
 
+def getMotifsWithBestInformationContentWithBPV(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, pcv,
+                                               **kw) -> SiteArray:
+    """fs:434-459. At most numberOfRepetitions + 1 restarts can run; they run as parallel chains."""
+    if pcv is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "pcv is null (ArgumentNullException)")
+    return _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, pcv, **kw)
+
+
+# ---- data-derived background (the background counts drift from window to window, fs:470-473) --------
+def getPWMOfRandomStarts(motifLength, pseudoCount, alphabet, sources, **kw) -> SiteArray:
+    """fs:589-611."""
+    return _run_phases(_abi.PHASE_INIT, motifLength, pseudoCount, alphabet, sources, None, **kw)
+
+
+def getBestPWMSsWithStartPositions(motifLength, pseudoCount, alphabet, sources, startPositions, **kw) -> SiteArray:
+    """fs:554-585."""
+    return _run_phases(_abi.PHASE_GREEDY, motifLength, pseudoCount, alphabet, sources, None, start=startPositions, **kw)
+
+
+def getLeftShiftedBestPWMSs(motifLength, pseudoCount, alphabet, sources, startPositions, **kw) -> SiteArray:
+    """fs:519-550."""
+    return _run_phases(_abi.PHASE_LEFT, motifLength, pseudoCount, alphabet, sources, None, start=startPositions, **kw)
+
+
+def getRightShiftedBestPWMSs(motifLength, pseudoCount, alphabet, sources, startPositions, **kw) -> SiteArray:
+    """fs:483-515."""
+    return _run_phases(_abi.PHASE_RIGHT, motifLength, pseudoCount, alphabet, sources, None, start=startPositions, **kw)
+
+
+def doSiteSampling(motifLength, pseudoCount, alphabet, sources, **kw) -> SiteArray:
+    """fs:697-701."""
+    mask = _abi.PHASE_INIT | _abi.PHASE_GREEDY | _abi.PHASE_LEFT | _abi.PHASE_RIGHT
+    return _run_phases(mask, motifLength, pseudoCount, alphabet, sources, None, **kw)
+
+
+def getMotifsWithBestInformationContent(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, **kw) -> SiteArray:
+    """fs:615-640 -- the call the reference script makes (fsx:384: reps 1, k 6, pc 1e-4, dnaBases)."""
+    return _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, None, **kw)
+
+
 def _unsupported(name: str, where: str):
     raise _abi.GibbsUnsupportedError(
         _abi.GIBBS_ERR_UNSUPPORTED,
-        f"{name} ({where}) derives its background from the data (per-window drifting counts, fs:470-473); "
-        "only the fixed-background WithBPV family is built on the GPU so far (SURVEY.md section 8f, rank 1)")
-
-
-def doSiteSampling(motifLength, pseudoCount, alphabet, sources, **kw):
-    """fs:697-701 -- data-derived background: not built yet."""
-    _unsupported("doSiteSampling", "fs:697")
-
-
-def getMotifsWithBestInformationContent(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, **kw):
-    """fs:615-640 -- data-derived background: not built yet."""
-    _unsupported("getMotifsWithBestInformationContent", "fs:615")
+        f"{name} ({where}) starts from a caller-supplied PositionProbabilityMatrix, which never crosses this "
+        "boundary (the PPM lives on the GPU); not built")
 
 
 def doSiteSamplingWithPPM(motifLength, pseudoCount, alphabet, sources, ppM, **kw):
-    """fs:703-707 -- data-derived background: not built yet."""
+    """fs:703-707 -- not built."""
     _unsupported("doSiteSamplingWithPPM", "fs:703")
 
 
 def getBestInformationContentOfPPM(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, ppM, **kw):
-    """fs:664-689 -- data-derived background: not built yet."""
+    """fs:664-689 -- not built."""
     _unsupported("getBestInformationContentOfPPM", "fs:664")

@@ -24,6 +24,8 @@ GIBBS_SITE_SAMPLER = 0
 GIBBS_MOTIF_SAMPLER = 1
 GIBBS_RNG_PHILOX = 0
 GIBBS_RNG_INJECTED = 1
+GIBBS_BG_FIXED = 0
+GIBBS_BG_DATA = 1
 GIBBS_MAX_K = 32
 PHASE_INIT, PHASE_GREEDY, PHASE_LEFT, PHASE_RIGHT, PHASE_STOCHASTIC, PHASE_MOTIF_GREEDY = 1, 2, 4, 8, 16, 32
 
@@ -91,6 +93,8 @@ class Params(C.Structure):
         ("phase_shifts", C.c_int32),
         ("max_sweeps", C.c_int32),
         ("phase_mask", C.c_int32),
+        ("background", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -7,6 +7,7 @@
 #include "../../include/gibbs_b200.h"
 #include "gibbs_kernels.cuh"
 #include "gibbs_motif.cuh"
+#include "gibbs_drift.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -99,6 +100,13 @@ struct gibbs_handle {
     int32_t bg_k = 0, bg_wstride = 0;
     double bg_q[4] = {0, 0, 0, 0};
     int32_t run_sampler = 0;
+    // data-derived background (doSiteSampling): normalizePPM values per count, base counts per sequence
+    DevBuf<double> pvals;
+    DevBuf<int32_t> basecnt;
+    bool drift_valid = false;
+    double drift_pc = 0;
+    int32_t drift_alen = 0;
+    int32_t gcnt[4] = {0, 0, 0, 0};
     int32_t team_warps = 0;   // 0 = choose per launch; 1 or 4 = forced (gibbs_set_team_warps)
     int32_t run_team = 0;
     int sm_count = 0;
@@ -120,8 +128,10 @@ int32_t check_params(const gibbs_handle *h, const gibbs_params *p) {
         return fail(GIBBS_ERR_SHORT_SEQ, "a sequence of length %d is shorter than k=%d (Array.take, fs:152)", h->min_len, p->k);
     if (p->alphabet_size < 1) return fail(GIBBS_ERR_ARG, "alphabet_size must be >= 1");
     if (!(p->pseudocount >= 0.0)) return fail(GIBBS_ERR_ARG, "pseudocount must be >= 0");
-    for (int b = 0; b < 4; ++b)
-        if (!(p->bg[b] > 0.0)) return fail(GIBBS_ERR_ARG, "background probability bg[%d] must be > 0", b);
+    if (p->background != GIBBS_BG_FIXED && p->background != GIBBS_BG_DATA) return fail(GIBBS_ERR_ARG, "unknown background mode %d", p->background);
+    if (p->background == GIBBS_BG_FIXED)
+        for (int b = 0; b < 4; ++b)
+            if (!(p->bg[b] > 0.0)) return fail(GIBBS_ERR_ARG, "background probability bg[%d] must be > 0", b);
     return GIBBS_OK;
 }
 
@@ -294,6 +304,51 @@ int32_t ensure_bgtab(gibbs_handle *h, const gibbs_params *p, int *launches) {
     return GIBBS_OK;
 }
 
+int32_t ensure_drift(gibbs_handle *h, const gibbs_params *p, int *launches) {
+    if (h->drift_valid && h->drift_pc == p->pseudocount && h->drift_alen == p->alphabet_size) return GIBBS_OK;
+    CUDA_TRY(h->pvals.reserve((size_t)h->n));
+    CUDA_TRY(h->basecnt.reserve((size_t)h->n * 4));
+    const double den = (double)(h->n - 1) + ((double)p->alphabet_size * p->pseudocount); // fs:257
+    pvals_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->n, p->pseudocount, den, h->pvals.p);
+    CUDA_TRY(cudaGetLastError());
+    basecount_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(dev_seqs(h), h->basecnt.p);
+    CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 2;
+    std::vector<int32_t> bc((size_t)h->n * 4);
+    CUDA_TRY(cudaMemcpyAsync(bc.data(), h->basecnt.p, bc.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    long long g[4] = {0, 0, 0, 0};
+    for (int32_t i = 0; i < h->n; ++i)
+        for (int b = 0; b < 4; ++b) g[b] += bc[(size_t)i * 4 + b];
+    for (int b = 0; b < 4; ++b) {
+        if (g[b] > INT32_MAX) return fail(GIBBS_ERR_ARG, "more than 2^31 bases of one kind: background counts overflow int32 (the reference counts in int32, fs:34)");
+        h->gcnt[b] = (int32_t)g[b];
+    }
+    h->drift_pc = p->pseudocount;
+    h->drift_alen = p->alphabet_size;
+    h->drift_valid = true;
+    return GIBBS_OK;
+}
+
+int32_t launch_drift(gibbs_handle *h, const DriftArgs &d) {
+    const int kp = (d.c.k + 1) / 2;
+    const int smem = team_smem_bytes(d.c.s.row_words, 1);
+    switch (kp) {
+#define X(KPV)                                                                          \
+    case KPV: {                                                                         \
+        int32_t rc = set_smem(drift_kernel<KPV>, smem);                                 \
+        if (rc) return rc;                                                              \
+        drift_kernel<KPV><<<d.c.n_chains, 32, smem, h->stream>>>(d);                    \
+        break;                                                                          \
+    }
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
 BgTables bg_tables(const gibbs_handle *h) {
     BgTables b;
     b.g = h->bg_g.p;
@@ -388,6 +443,7 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
     h->n = 0;
     h->wtab_valid = false;
     h->bg_valid = false;
+    h->drift_valid = false;
     h->run_done = false;
     if (bad)
         return fail(GIBBS_ERR_SYMBOL, "symbol '%c' (0x%02x) is outside A,C,G,T (IndexOutOfRangeException analogue, fs:17)",
@@ -488,6 +544,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->stats.release(); h->best.release();
     h->bg_g.release(); h->bg_sum.release(); h->bg_max.release(); h->bg_max_i.release();
     h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
+    h->pvals.release(); h->basecnt.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -555,6 +612,7 @@ static int32_t scan_common(gibbs_handle *h, const int32_t *sites, int32_t heldou
                            double *raw_out, double *log2_out, double *score_out, int32_t *site_out) {
     int32_t rc = check_params(h, p);
     if (rc) return rc;
+    if (p->background != GIBBS_BG_FIXED) return fail(GIBBS_ERR_UNSUPPORTED, "the scan primitives take a fixed background (WithBPV)");
     if (heldout < 0 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
     rc = set_device(h);
     if (rc) return rc;
@@ -656,11 +714,14 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     if (p->sampler != GIBBS_SITE_SAMPLER && p->sampler != GIBBS_MOTIF_SAMPLER) return fail(GIBBS_ERR_ARG, "unknown sampler %d", p->sampler);
     if (rng_mode != GIBBS_RNG_PHILOX && rng_mode != GIBBS_RNG_INJECTED) return fail(GIBBS_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (rng_mode == GIBBS_RNG_INJECTED && (!uniforms || uniforms_per_chain < 0)) return fail(GIBBS_ERR_ARG, "injected uniforms missing");
+    if (p->background == GIBBS_BG_DATA && p->sampler != GIBBS_SITE_SAMPLER)
+        return fail(GIBBS_ERR_UNSUPPORTED, "MotifSampler with a data-derived background (fs:885-970) is not built yet");
     rc = set_device(h);
     if (rc) return rc;
     h->run_done = false;
     int launches = 0;
-    rc = ensure_wtab(h, p, &launches);
+    if (p->background == GIBBS_BG_FIXED) rc = ensure_wtab(h, p, &launches);
+    else rc = ensure_drift(h, p, &launches);
     if (rc) return rc;
     const size_t cells = (size_t)n_chains * h->n;
     CUDA_TRY(h->sites.reserve(cells));
@@ -675,7 +736,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     a.wtab = h->wtab.p;
     a.k = p->k;
     a.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 1000000;
-    a.fast_ok = fast_path_ok(h, p->k);
+    a.fast_ok = p->background == GIBBS_BG_FIXED ? fast_path_ok(h, p->k) : 0;
     a.sampler = p->sampler;
     const int site_phases = GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT;
     const int motif_phases = GIBBS_PHASE_INIT | GIBBS_PHASE_STOCHASTIC | GIBBS_PHASE_MOTIF_GREEDY;
@@ -725,6 +786,18 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         m.error = h->err_flag.p;
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_motif(h, m);
+        if (rc) return rc;
+        h->run_team = 1;
+    } else if (p->background == GIBBS_BG_DATA) {
+        DriftArgs d{};
+        d.c = a;
+        d.pvals = h->pvals.p;
+        d.basecnt = h->basecnt.p;
+        memcpy(d.gcnt, h->gcnt, sizeof d.gcnt);
+        d.alpha_pc = (double)p->alphabet_size * p->pseudocount; // float alphabet.Length * pseudoCount, fs:117
+        d.pc = p->pseudocount;
+        CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+        rc = launch_drift(h, d);
         if (rc) return rc;
         h->run_team = 1;
     } else {

@@ -75,7 +75,7 @@ class RunResult:
 
 def make_params(k: int, pseudocount: float, alphabet_size: int, bg: Sequence[float], *, cutoff: float = 0.0,
                 sampler: int = _abi.GIBBS_SITE_SAMPLER, phase_shifts: bool = True, max_sweeps: int = 0,
-                phase_mask: int = 0) -> Params:
+                phase_mask: int = 0, background: int = _abi.GIBBS_BG_FIXED) -> Params:
     p = Params()
     p.k = int(k)
     p.alphabet_size = int(alphabet_size)
@@ -87,6 +87,8 @@ def make_params(k: int, pseudocount: float, alphabet_size: int, bg: Sequence[flo
     p.phase_shifts = 1 if phase_shifts else 0
     p.max_sweeps = int(max_sweeps)
     p.phase_mask = int(phase_mask)
+    p.background = int(background)
+    p.reserved = 0
     return p
 
 

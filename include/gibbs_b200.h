@@ -64,7 +64,13 @@ typedef struct gibbs_params {
     int32_t max_sweeps;    /* safety cap per phase (the reference has none); 0 = 1000000        */
     int32_t phase_mask;    /* 0 = the whole pipeline of `sampler`; else a set of GIBBS_PHASE_* bits,  */
                            /* run in pipeline order from the state given to gibbs_set_start_state    */
+    int32_t background;    /* GIBBS_BG_FIXED: bg[] (WithBPV family) | GIBBS_BG_DATA: derived from the */
+                           /* sequences like doSiteSampling does (fs:697; per-window counts, fs:470)  */
+    int32_t reserved;
 } gibbs_params;
+
+#define GIBBS_BG_FIXED 0
+#define GIBBS_BG_DATA 1
 
 /* phases = the reference functions a pipeline is made of */
 #define GIBBS_PHASE_INIT 1        /* getPWMOfRandomStartsWithBPV, fs:412-430                          */

@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_struct_layouts_match_the_header():
     # gibbs_params: 2*int32 + 6 doubles + 4*int32; gibbs_run_stats: 5*int64 + 2*int32 + double
-    assert C.sizeof(_abi.Params) == 8 + 6 * 8 + 16
+    assert C.sizeof(_abi.Params) == 8 + 6 * 8 + 24
     assert C.sizeof(_abi.RunStats) == 6 * 8 + 16 + 8
     assert _abi.Params.bg.offset == 16 and _abi.Params.cutoff.offset == 48 and _abi.Params.sampler.offset == 56
 

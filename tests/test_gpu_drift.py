@@ -1,0 +1,76 @@
+"""GPU parity of the data-derived-background SiteSampler (doSiteSampling fs:697, getBestPWMSs fs:462): the
+background counts drift from window to window (quirk A.6-1). This is the family the reference script calls
+(fsx:384: getMotifsWithBestInformationContent 1 6 0.0001 dnaBases bioTests)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from gibbssampling_b200 import SiteSampler, _abi
+from gibbssampling_b200.engine import GibbsEngine, draws_per_chain, make_params
+from gibbssampling_b200.synthetic import planted_motif_set
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+DNA = list("ATGC-")
+
+
+def _cases():
+    # (n, L, Lmin, k, alen, pc, seed)
+    return [
+        (4, 21, None, 6, 5, 1e-4, 1),
+        (9, 70, 40, 7, 5, 1e-4, 2),
+        (12, 130, None, 12, 4, 1e-2, 3),
+        (6, 300, 150, 16, 5, 1e-4, 4),
+        (5, 90, None, 31, 5, 1.0, 5),
+        (7, 33, 9, 1, 5, 1e-4, 6),
+    ]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: f"n{c[0]}_L{c[1]}_k{c[3]}")
+def test_data_background_restarts_match_oracle(case):
+    n, L, Lmin, k, alen, pc, seed = case
+    ps = planted_motif_set(n, L, k, seed=300 + seed, min_length=Lmin)
+    seqs = ps.sequences()
+    S = O.sources(seqs)
+    alphabet = b"ATGC-"[:alen]
+    params = make_params(k, pc, alen, [0.25] * 4, background=_abi.GIBBS_BG_DATA)
+    with GibbsEngine(seqs) as eng:
+        res = eng.run(params, 5, chain_id_base=10, seed=seed, want_counts=False)
+    total = 0
+    for c in range(5):
+        rng, _ = O.make_rng(seed=seed, chain=10 + c)
+        score, pos, st = O.site_step("do_site_sampling", S, k, pc, rng=rng, alphabet=alphabet)
+        assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"
+        np.testing.assert_allclose(res.scores[c], score, rtol=RTOL)
+        total += st.site_updates
+    assert res.stats["site_updates"] == total and res.stats["fast_path"] == 0
+
+
+def test_script_call_and_phase_functions(golden):
+    """The reference script's live call shape on its own toy input (fsx:29-35, fsx:384)."""
+    seqs, k, pc = golden["sequences"], golden["k"], golden["pc"]
+    S = O.sources(seqs)
+    n = len(seqs)
+    for reps in (1, 4):
+        got = SiteSampler.getMotifsWithBestInformationContent(reps, k, pc, DNA, seqs, seed=2024, chain=3)
+        rng, _ = O.make_rng(seed=2024, chain=3)
+        ws, wp, _ = O.best_information_content(1, reps, S, k, pc, rng)
+        assert [p for _, p in got] == wp.tolist()
+        np.testing.assert_allclose([s for s, _ in got], ws, rtol=RTOL)
+    # KAT-1 of SURVEY Appendix B: the converged state scores 11.81 / 11.98 / 11.85 / 11.84 with the drifting background
+    u = np.random.default_rng(1).random(draws_per_chain(n))
+    steps = [("random_starts", SiteSampler.getPWMOfRandomStarts), ("best_pwms_with_start_positions", SiteSampler.getBestPWMSsWithStartPositions),
+             ("left_shifted", SiteSampler.getLeftShiftedBestPWMSs), ("right_shifted", SiteSampler.getRightShiftedBestPWMSs)]
+    state = None
+    for name, fn in steps:
+        rng, _ = O.make_rng(uniforms=u)
+        o_score, o_pos, _ = O.site_step(name, S, k, pc, state=state, rng=rng)
+        got = fn(k, pc, DNA, seqs, uniforms=u) if state is None else fn(k, pc, DNA, seqs, [(float(a), int(b)) for a, b in zip(*state)])
+        assert [p for _, p in got] == o_pos.tolist(), name
+        np.testing.assert_allclose([s for s, _ in got], o_score, rtol=RTOL)
+        state = (o_score, o_pos)
+    kat = golden["kat1"]
+    start = [(0.0, p) for p in kat["sites"]]
+    got = SiteSampler.getBestPWMSsWithStartPositions(k, pc, DNA, seqs, start)
+    assert [p for _, p in got] == kat["sites"]
+    np.testing.assert_allclose([s for s, _ in got], [v for v, _ in kat["best_drifting"]], rtol=1e-12)

@@ -49,7 +49,7 @@ def test_flatten_sources_and_symbols():
 def test_params_struct_roundtrip():
     p = make_params(12, 1e-4, 5, [0.1, 0.2, 0.3, 0.4], cutoff=1.0, sampler=1, phase_shifts=False, max_sweeps=7, phase_mask=6)
     assert (p.k, p.alphabet_size, p.pseudocount, list(p.bg), p.cutoff) == (12, 5, 1e-4, [0.1, 0.2, 0.3, 0.4], 1.0)
-    assert (p.sampler, p.phase_shifts, p.max_sweeps, p.phase_mask) == (1, 0, 7, 6)
+    assert (p.sampler, p.phase_shifts, p.max_sweeps, p.phase_mask, p.background) == (1, 0, 7, 6, 0)
     assert draws_per_chain(1000) == 999000 and draws_per_chain(10, _abi.GIBBS_MOTIF_SAMPLER) == 100
 
 
@@ -132,9 +132,9 @@ def test_select_best_is_strict_max_with_lowest_chain_id():
 
 def test_unbuilt_reference_entry_points_say_so():
     with pytest.raises(_abi.GibbsUnsupportedError):
-        SiteSampler.doSiteSampling(6, 1e-4, DNA, ["ACGTACGT"])
+        SiteSampler.doSiteSamplingWithPPM(6, 1e-4, DNA, ["ACGTACGT"], None)
     with pytest.raises(_abi.GibbsUnsupportedError):
-        SiteSampler.getMotifsWithBestInformationContent(1, 6, 1e-4, DNA, ["ACGTACGT"])
+        SiteSampler.doSiteSampling(6, 1e-4, list("AT"), ["ACGTACGT"])
     with pytest.raises(_abi.GibbsUnsupportedError):
         SiteSampler.doSiteSamplingWithBPV(6, 1e-4, list("AT"), ["ACGTACGT"], ProbabilityCompositeVector())
     assert MotifSampler.createMotifIndex(1.5, [3]) == MotifSampler.MotifIndex(1.5, (3,))
