@@ -2,8 +2,8 @@
 
 `MotifIndex` = {PWMS: float; Positions: int list} (fs:712-716). Only motifAmount = 1 is in scope
 (SURVEY.md section 2, row 8): combinations of m >= 2 windows are an exponential enumeration, not
-data-parallel window scoring. The fixed-background (`...ByPCV` / `...WithPCV`) family runs on the GPU;
-the data-derived-background family (fs:885-1038) is not built yet.
+data-parallel window scoring. Both the fixed-background (`...ByPCV` / `...WithPCV`) family and the
+data-derived-background family (fs:885-1038) run on the GPU.
 """
 from __future__ import annotations
 
@@ -13,6 +13,7 @@ from typing import Optional
 import numpy as np
 
 from . import _abi
+from .CompositeVector import ProbabilityCompositeVector
 from .engine import GibbsEngine, make_params
 from .SiteSampler import _bg_of, _engine_for
 
@@ -55,11 +56,16 @@ def _split_motif_state(motifMem) -> tuple[np.ndarray, np.ndarray]:
 def _run(phase_mask: int, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, *, start=None,
          n_chains: int = 1, seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
          max_sweeps: int = 0):
+    """pcv given -> the PCV family (fixed background); pcv None -> the data-derived family (fs:885-1038)."""
     _check_m(motifAmount)
-    bg = _bg_of(alphabet, pcv)
+    if pcv is None:
+        _bg_of(alphabet, ProbabilityCompositeVector.ofACGT(1, 1, 1, 1))   # only checks A,C,G,T are in the alphabet
+        bg, background = [0.25] * 4, _abi.GIBBS_BG_DATA
+    else:
+        bg, background = _bg_of(alphabet, pcv), _abi.GIBBS_BG_FIXED
     eng, own = _engine_for(sources, engine)
     try:
-        params = make_params(motifLength, pseudoCount, len(alphabet), bg, cutoff=cutOff,
+        params = make_params(motifLength, pseudoCount, len(alphabet), bg, cutoff=cutOff, background=background,
                              sampler=_abi.GIBBS_MOTIF_SAMPLER, phase_mask=phase_mask, max_sweeps=max_sweeps)
         if start is not None:
             scores, sites = _split_motif_state(start)
@@ -149,29 +155,51 @@ def findBestInormationContentContainingMotifsWithPCV(numberOfRepetitions, motifA
     return replay_motif_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
 
 
-def _not_built(name: str, where: str):
-    raise _abi.GibbsUnsupportedError(
-        _abi.GIBBS_ERR_UNSUPPORTED,
-        f"{name} ({where}) derives its background from the data (fs:896-905); only the fixed-background PCV family "
-        "is built on the GPU so far (SURVEY.md section 8f, rank 1)")
+# ---- data-derived background (fs:885-1038): one background per held-out sequence (fs:896-905) -------------
+def findBestMotifIndicesByWithStartPositions(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, motifMem,
+                                             **kw) -> list:
+    """fs:935-970: the synchronous stochastic sweep."""
+    res = _run(_abi.PHASE_STOCHASTIC, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None,
+               start=motifMem, **kw)
+    return _to_motif_array(res.scores[0], res.sites[0])
 
 
-def doMotifSampling(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, **kw):
-    """fs:1034-1038 -- data-derived background: not built yet."""
-    _not_built("doMotifSampling", "fs:1034")
+def findBestMotifIndicesWithStartPositions(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, motifMem,
+                                           **kw) -> list:
+    """fs:885-929: greedy in-place sweeps."""
+    res = _run(_abi.PHASE_MOTIF_GREEDY, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None,
+               start=motifMem, **kw)
+    return _to_motif_array(res.scores[0], res.sites[0])
+
+
+def doMotifSampling(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, **kw) -> list:
+    """fs:1034-1038."""
+    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, **kw)
+    return _to_motif_array(res.scores[0], res.sites[0])
 
 
 def getMotifsWithBestInformationContents(numberOfRepetitions, motifAmount, motifLength, pseudoCount, cutOff, alphabet,
-                                         sources, **kw):
-    """fs:973-998 -- data-derived background: not built yet."""
-    _not_built("getMotifsWithBestInformationContents", "fs:973")
+                                         sources, *, seed: int = 0, chain: int = 0, uniforms=None,
+                                         engine: Optional[GibbsEngine] = None, max_sweeps: int = 0) -> list:
+    """fs:973-998 -- the reference script's second live call (fsx:407; there with motifAmount = 2, out of scope)."""
+    n_restarts = max(int(numberOfRepetitions) + 1, 1)
+    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
+               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps)
+    return replay_motif_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
+
+
+def _not_built(name: str, where: str):
+    raise _abi.GibbsUnsupportedError(
+        _abi.GIBBS_ERR_UNSUPPORTED,
+        f"{name} ({where}) starts from a caller-supplied PositionProbabilityMatrix, which never crosses this "
+        "boundary (the PPM lives on the GPU); not built")
 
 
 def doMotifSamplingWithPPM(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, **kw):
-    """fs:1028-1032 -- data-derived background: not built yet."""
+    """fs:1028-1032 -- not built."""
     _not_built("doMotifSamplingWithPPM", "fs:1028")
 
 
 def getBestPWMSsOfPPM(numberOfRepetitions, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, **kw):
-    """fs:1001-1026 -- data-derived background: not built yet."""
+    """fs:1001-1026 -- not built."""
     _not_built("getBestPWMSsOfPPM", "fs:1001")

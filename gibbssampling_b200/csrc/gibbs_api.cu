@@ -101,7 +101,7 @@ struct gibbs_handle {
     double bg_q[4] = {0, 0, 0, 0};
     int32_t run_sampler = 0;
     // data-derived background (doSiteSampling): normalizePPM values per count, base counts per sequence
-    DevBuf<double> pvals;
+    DevBuf<double> pvals, gbuf;
     DevBuf<int32_t> basecnt;
     bool drift_valid = false;
     double drift_pc = 0;
@@ -544,7 +544,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->stats.release(); h->best.release();
     h->bg_g.release(); h->bg_sum.release(); h->bg_max.release(); h->bg_max_i.release();
     h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
-    h->pvals.release(); h->basecnt.release();
+    h->pvals.release(); h->basecnt.release(); h->gbuf.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -714,8 +714,6 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     if (p->sampler != GIBBS_SITE_SAMPLER && p->sampler != GIBBS_MOTIF_SAMPLER) return fail(GIBBS_ERR_ARG, "unknown sampler %d", p->sampler);
     if (rng_mode != GIBBS_RNG_PHILOX && rng_mode != GIBBS_RNG_INJECTED) return fail(GIBBS_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (rng_mode == GIBBS_RNG_INJECTED && (!uniforms || uniforms_per_chain < 0)) return fail(GIBBS_ERR_ARG, "injected uniforms missing");
-    if (p->background == GIBBS_BG_DATA && p->sampler != GIBBS_SITE_SAMPLER)
-        return fail(GIBBS_ERR_UNSUPPORTED, "MotifSampler with a data-derived background (fs:885-970) is not built yet");
     rc = set_device(h);
     if (rc) return rc;
     h->run_done = false;
@@ -772,8 +770,14 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     a.cutoff = p->cutoff;
     memcpy(a.bg, p->bg, sizeof a.bg);
     if (p->sampler == GIBBS_MOTIF_SAMPLER) {
-        rc = ensure_bgtab(h, p, &launches);
-        if (rc) return rc;
+        if (p->background == GIBBS_BG_FIXED) {
+            rc = ensure_bgtab(h, p, &launches);
+            if (rc) return rc;
+        } else {
+            h->bg_valid = false; // the fixed-background tables are not used; only the window stride is
+            h->bg_wstride = h->max_len - p->k + 1;
+            CUDA_TRY(h->gbuf.reserve((size_t)n_chains * h->bg_wstride));
+        }
         CUDA_TRY(h->cand_l.reserve((size_t)n_chains * h->bg_wstride));
         CUDA_TRY(h->cand_w.reserve((size_t)n_chains * h->bg_wstride));
         CUDA_TRY(h->err_flag.reserve(1));
@@ -784,6 +788,15 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         m.cand_l = h->cand_l.p;
         m.cand_w = h->cand_w.p;
         m.error = h->err_flag.p;
+        m.data_bg = p->background == GIBBS_BG_DATA ? 1 : 0;
+        if (m.data_bg) {
+            m.pvals = h->pvals.p;
+            m.basecnt = h->basecnt.p;
+            memcpy(m.gcnt, h->gcnt, sizeof m.gcnt);
+            m.alpha_pc = (double)p->alphabet_size * p->pseudocount;
+            m.pc = p->pseudocount;
+            m.gbuf = h->gbuf.p;
+        }
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_motif(h, m);
         if (rc) return rc;

@@ -8,6 +8,7 @@
 #pragma once
 #include "gibbs_device.cuh"
 #include "gibbs_kernels.cuh"
+#include "gibbs_drift.cuh"
 
 namespace gibbs {
 
@@ -24,10 +25,18 @@ struct BgTables {
 
 struct MotifArgs {
     ChainArgs c;
-    BgTables bg;
+    BgTables bg;           // fixed background: run constants
     double *cand_l;        // [chains][wstride] candidate PWMS scratch (ascending window order)
     int32_t *cand_w;       // [chains][wstride]
     int32_t *error;        // set to 1 when a roulette pick ran past the list (fs:753)
+    // data-derived background (fs:885-970): one background per held-out sequence, built from the others'
+    // bases outside their sites plus the whole held-out sequence (fs:896-905)
+    int32_t data_bg;
+    const double *pvals;   // [n] (c + pc) / ((N-1) + |A| pc)
+    const int32_t *basecnt; // [n][4]
+    int32_t gcnt[4];
+    double alpha_pc, pc;
+    double *gbuf;          // [chains][wstride] background window probabilities of the current held-out sequence
 };
 
 // one thread per sequence
@@ -148,6 +157,8 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
     double *hv = a.hv + (size_t)chain * N;
     double *cand_l = m.cand_l + (size_t)chain * m.bg.wstride;
     int32_t *cand_w = m.cand_w + (size_t)chain * m.bg.wstride;
+    double *gbuf = m.data_bg ? m.gbuf + (size_t)chain * m.bg.wstride : nullptr;
+    int bsum[4] = {0, 0, 0, 0}; // data background: base counts summed over the sequences that have a site
     const uint64_t chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
     const double raw_gate = exp2(a.cutoff) * (1.0 - 0x1p-30);
 
@@ -165,19 +176,47 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
     while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_INIT ? 0 : phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
     int sweeps_in_phase = 0;
     while (phase != MPH_DONE) {
-        if (phase != MPH_INIT && (phase == MPH_STOCH || sweeps_in_phase == 0))
+        if (phase != MPH_INIT && (phase == MPH_STOCH || sweeps_in_phase == 0)) {
             site_counts<KP, 1>(a.s, sites, -1, k, SHIFT_NONE, S.total, S.lut, lane);
+            if (m.data_bg) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    int s = 0;
+                    for (int i = lane; i < N; i += 32)
+                        if (__ldcg(sites + i) >= 0) s += __ldg(m.basecnt + i * 4 + b);
+                    bsum[b] = __reduce_add_sync(FULL, s);
+                }
+            }
+        }
         bool changed = false;
         for (int n = 0; n < N; ++n, ++v) {
             const uint32_t *row = ring.wait(v);
             const int len_n = __ldg(a.s.len + n);
             const int W = len_n - k + 1;
-            if (phase == MPH_INIT) { // getPWMOfRandomStartsWithBPV |> createMotifIndex prob [position] (fs:876-877)
+            if (phase == MPH_INIT) { // getPWMOfRandomStarts[WithBPV] |> createMotifIndex prob [position] (fs:876-877, fs:993-994)
                 random_loo_counts<KP>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
-                build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                 double p;
                 int w;
-                pick_argmax<KP>(WT, row, W, k, a.fast_ok, lane, p, w);
+                if (!m.data_bg) {
+                    build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+                    pick_argmax<KP>(WT, row, W, k, a.fast_ok, lane, p, w);
+                } else { // SiteSampler.getPWMOfRandomStarts: drifting background (fs:589-611)
+                    for (int e = lane; e < 4 * k; e += 32) {
+                        const int c = WT.counts[e];
+                        WT.wcol[e] = __ldg(m.pvals + c);
+                        WT.lgcol[e] = c;
+                    }
+                    __syncwarp();
+                    int f0[4], cn[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        int s = 0;
+                        for (int j = lane; j < k; j += 32) s += WT.lgcol[j * 4 + b];
+                        cn[b] = __ldg(m.basecnt + n * 4 + b);
+                        f0[b] = (m.gcnt[b] - cn[b]) - __reduce_add_sync(FULL, s);
+                    }
+                    scan_drifting(row, W, k, WT.wcol, f0, cn, m.pc, m.alpha_pc, lane, p, w);
+                }
                 if (lane == 0) {
                     sites[n] = w;
                     pw[n] = log2_ref(p);
@@ -187,7 +226,69 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                 const double pw_n = __ldcg(pw + n);
                 const bool has_own = site_n >= 0;
                 const uint64_t own = has_own ? kmer_shared<KP>(row, site_n) : 0;
-                build_tables<KP>(WT, S.total, has_own, own, k, a.wtab, lane);
+                const double *g_n = m.bg.g + (size_t)n * m.bg.wstride;
+                double gsum_n = 0.0, gmax_n = 0.0;
+                int cn[4] = {0, 0, 0, 0};
+                if (!m.data_bg) {
+                    build_tables<KP>(WT, S.total, has_own, own, k, a.wtab, lane);
+                    gsum_n = __ldg(m.bg.gsum + n);
+                    gmax_n = __ldg(m.bg.gmax + n);
+                } else {
+                    // background of this held-out sequence (fs:896-905): the OTHER sequences that have a site, outside
+                    // those sites (fused over the alphabet), plus every base of the held-out sequence
+                    for (int e = lane; e < 4 * k; e += 32) {
+                        int c = S.total[e];
+                        if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3)) c -= 1;
+                        WT.lgcol[e] = c;
+                    }
+                    __syncwarp();
+                    int F[4], fs = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        int s = 0;
+                        for (int j = lane; j < k; j += 32) s += WT.lgcol[j * 4 + b];
+                        cn[b] = __ldg(m.basecnt + n * 4 + b);
+                        F[b] = bsum[b] - (has_own ? cn[b] : 0) - __reduce_add_sync(FULL, s) + cn[b];
+                        fs += F[b];
+                    }
+                    const double den = __dadd_rn((double)fs, m.alpha_pc);
+                    double q[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) q[b] = __ddiv_rn(__dadd_rn((double)F[b], m.pc), den); // fs:119
+                    for (int e = lane; e < 8 * KP; e += 32) { // PWM = PPM / pcv (fs:286); dummy column of an odd k = 1.0
+                        const int b = e & 3;
+                        const double qb = b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3];
+                        WT.wcol[e] = (e >> 2) < k ? __ddiv_rn(__ldg(m.pvals + WT.lgcol[e]), qb) : 1.0;
+                    }
+                    // background-only probability of every window (fs:776), first maximum, and their sum in list order
+                    double bestg = 0.0;
+                    for (int w0 = 0; w0 < W; w0 += 32) {
+                        const int w = w0 + lane;
+                        if (w < W) {
+                            double v = 1.0;
+                            for (int j = 0; j < k; ++j) {
+                                const int b = base_at(row, w + j);
+                                v = __dmul_rn(v, b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3]);
+                            }
+                            gbuf[w] = v;
+                            bestg = fmax(bestg, v);
+                        }
+                    }
+                    __syncwarp();
+                    {
+                        const uint32_t hi = (uint32_t)__double2hiint(bestg), mh = __reduce_max_sync(FULL, hi);
+                        const uint32_t lo = (hi == mh) ? (uint32_t)__double2loint(bestg) : 0u, ml = __reduce_max_sync(FULL, lo);
+                        gmax_n = __hiloint2double((int)mh, (int)ml);
+                    }
+                    if (phase == MPH_STOCH) { // List.sum visits the background entries first, in window order (fs:748)
+                        for (int w0 = 0; w0 < W; w0 += 32) {
+                            const double v = (w0 + lane < W) ? gbuf[w0 + lane] : 0.0;
+                            const int lim = min(32, W - w0);
+                            for (int j = 0; j < lim; ++j) gsum_n = __dadd_rn(gsum_n, __shfl_sync(FULL, v, j));
+                        }
+                    }
+                    g_n = gbuf;
+                }
                 double best_l;
                 int best_w;
                 const int n_cand = motif_candidates<KP>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w);
@@ -207,8 +308,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                     } else {
                         u = ((int64_t)d < a.uniforms_per_chain) ? __ldg(a.uniforms + (size_t)chain * a.uniforms_per_chain + d) : 0.0;
                     }
-                    const bool ok = motif_roulette(m.bg.g + (size_t)n * m.bg.wstride, __ldg(m.bg.gsum + n), W, cand_l, cand_w,
-                                                   n_cand, u, lane, new_pw, new_site);
+                    const bool ok = motif_roulette(g_n, gsum_n, W, cand_l, cand_w, n_cand, u, lane, new_pw, new_site);
                     if (!ok) {
                         if (lane == 0) atomicExch(m.error, 1);
                         new_pw = pw_n;
@@ -216,12 +316,11 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                     }
                     take = true;
                 } else { // fs:788-822: first maximum by PWMS over background entries ++ candidates
-                    const double gmax = __ldg(m.bg.gmax + n);
-                    if (n_cand > 0 && best_l > gmax) {
+                    if (n_cand > 0 && best_l > gmax_n) {
                         new_pw = best_l;
                         new_site = best_w;
                     } else {
-                        new_pw = gmax;
+                        new_pw = gmax_n;
                         new_site = -1;
                     }
                     take = new_pw > pw_n; // fs:816
@@ -233,6 +332,10 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                         if (lane < k) { // in-place sweep: -old k-mer, +new k-mer
                             if (has_own) S.total[lane * 4 + (int)((own >> (2 * lane)) & 3u)] -= 1;
                             if (new_site >= 0) S.total[lane * 4 + (int)((neu >> (2 * lane)) & 3u)] += 1;
+                        }
+                        if (m.data_bg && has_own != (new_site >= 0)) { // the sequence gained or lost its site
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) bsum[b] += (new_site >= 0 ? cn[b] : -cn[b]);
                         }
                     }
                     if (lane == 0) {

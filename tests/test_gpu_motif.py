@@ -132,4 +132,48 @@ def test_motif_restart_loop_and_scope():
     with pytest.raises(_abi.GibbsUnsupportedError):
         MotifSampler.doMotifSamplingWithPCV(2, k, pc, cutoff, DNA, seqs, pcv)
     with pytest.raises(_abi.GibbsUnsupportedError):
-        MotifSampler.doMotifSampling(1, k, pc, cutoff, DNA, seqs)
+        MotifSampler.doMotifSamplingWithPPM(1, k, pc, cutoff, DNA, seqs, None)
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: f"n{c[0]}_L{c[1]}_k{c[3]}_cut{c[5]}")
+def test_data_background_motif_restarts_match_oracle(case):
+    """doMotifSampling (fs:1034): random starts with the drifting background, then sweeps whose background is
+    rebuilt once per held-out sequence from the others' non-site bases (fs:896-905)."""
+    n, L, Lmin, k, pc, cutoff, seed = case
+    ps, seqs, bg = _setup(case)
+    S = O.sources(seqs)
+    n_chains = 4
+    with GibbsEngine(seqs) as eng:
+        params = make_params(k, pc, 5, [0.25] * 4, cutoff=cutoff, sampler=_abi.GIBBS_MOTIF_SAMPLER, background=_abi.GIBBS_BG_DATA)
+        res = eng.run(params, n_chains, chain_id_base=70, seed=31 + seed, want_counts=False)
+    for c in range(n_chains):
+        rng, _ = O.make_rng(seed=31 + seed, chain=70 + c)
+        want, st = O.motif_step("do_motif_sampling", 1, S, 1, k, pc, cutoff, rng=rng)
+        _same_state(res.sites[c], res.scores[c], want)
+
+
+def test_data_background_motif_functions(golden):
+    """The script's second call shape (fsx:407) with motifAmount = 1, on its own multi-sample toy input (fsx:49-57)."""
+    seqs, k, pc, cutoff = golden["multi_sequences"], 6, 1e-4, 1.0
+    S = O.sources(seqs)
+    for reps in (1, 3):
+        got = MotifSampler.getMotifsWithBestInformationContents(reps, 1, k, pc, cutoff, DNA, seqs, seed=8, chain=2)
+        rng, _ = O.make_rng(seed=8, chain=2)
+        want, _ = O.best_motif_information_content(1, reps, S, 1, k, pc, cutoff, rng)
+        assert [list(m.Positions) for m in got] == [p for _, p in want]
+        np.testing.assert_allclose([m.PWMS for m in got], [v for v, _ in want], rtol=RTOL)
+    n = len(seqs)
+    start = [MotifSampler.createMotifIndex(1.5, [3]) for _ in range(n)]
+    start[4] = MotifSampler.createMotifIndex(1e-9, [])          # the poly-T sequence has no site
+    ostart = [(m.PWMS, list(m.Positions)) for m in start]
+    picks = np.random.default_rng(6).random(n)
+    full = np.concatenate([np.zeros(n * (n - 1)), picks])
+    got_s = MotifSampler.findBestMotifIndicesByWithStartPositions(1, k, pc, cutoff, DNA, seqs, start, uniforms=full)
+    rng, _ = O.make_rng(uniforms=picks)
+    want_s, _ = O.motif_step("stochastic", 1, S, 1, k, pc, cutoff, state=ostart, rng=rng)
+    assert [list(m.Positions) for m in got_s] == [p for _, p in want_s]
+    np.testing.assert_allclose([m.PWMS for m in got_s], [v for v, _ in want_s], rtol=RTOL)
+    got_g = MotifSampler.findBestMotifIndicesWithStartPositions(1, k, pc, cutoff, DNA, seqs, start)
+    want_g, _ = O.motif_step("greedy", 1, S, 1, k, pc, cutoff, state=ostart)
+    assert [list(m.Positions) for m in got_g] == [p for _, p in want_g]
+    np.testing.assert_allclose([m.PWMS for m in got_g], [v for v, _ in want_g], rtol=RTOL)
