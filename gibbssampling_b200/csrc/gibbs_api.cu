@@ -107,7 +107,9 @@ struct gibbs_handle {
     double drift_pc = 0;
     int32_t drift_alen = 0;
     int32_t gcnt[4] = {0, 0, 0, 0};
-    int32_t team_warps = 0;   // 0 = choose per launch; 1 or 4 = forced (gibbs_set_team_warps)
+    DevBuf<int32_t> ctl, resume, pending; // pause / resume of straggler chains
+    int32_t run_extra_launches = 0;
+    int32_t team_warps = 0;   // 0 = choose per launch; 1, 4 or 8 = forced (gibbs_set_team_warps)
     int32_t run_team = 0;
     int sm_count = 0;
 };
@@ -185,33 +187,63 @@ int32_t set_smem(K kernel, int bytes) {
 // shortens every chain's critical path (measured faster than one warp per chain both when all chains
 // are resident at once -- C2 -- and when they run in several waves); one warp is kept for sets with
 // fewer than 4 sequences or rows too long for four sets of staging buffers.
+template <int KPV, int TV>
+int32_t launch_team(gibbs_handle *h, const ChainArgs &a, int grid) {
+    const int smem = team_smem_bytes(a.s.row_words, TV);
+    if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for %d warps per chain", TV);
+    int32_t rc = set_smem(chain_kernel<KPV, TV>, smem);
+    if (rc) return rc;
+    chain_kernel<KPV, TV><<<grid, 32 * TV, smem, h->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return GIBBS_OK;
+}
+
 template <int KPV>
-int32_t launch_chain_kp(gibbs_handle *h, const ChainArgs &a) {
+int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
     int team = h->team_warps;
-    const int smem4 = team_smem_bytes(a.s.row_words, 4), smem1 = team_smem_bytes(a.s.row_words, 1);
-    if (team == 0) { // 8 warps pay off only while the GPU has idle warp slots (few chains); measured on C2-shaped input
-        const int smem8 = team_smem_bytes(a.s.row_words, 8);
+    const int smem4 = team_smem_bytes(a.s.row_words, 4), smem8 = team_smem_bytes(a.s.row_words, 8);
+    const bool auto_team = team == 0;
+    if (auto_team) { // 8 warps pay off only while the GPU has idle warp slots (few chains); measured on C2-shaped input
         if (a.s.n >= 8 && a.n_chains <= 2 * h->sm_count && smem8 <= 200 * 1024) team = 8;
         else team = (a.s.n >= 4 && smem4 <= 200 * 1024) ? 4 : 1;
     }
     h->run_team = team;
-    if (team == 8) {
-        const int smem8 = team_smem_bytes(a.s.row_words, 8);
-        if (smem8 > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for 8 warps per chain");
-        int32_t rc = set_smem(chain_kernel<KPV, 8>, smem8);
-        if (rc) return rc;
-        chain_kernel<KPV, 8><<<a.n_chains, 256, smem8, h->stream>>>(a);
-    } else if (team == 4) {
-        if (smem4 > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for 4 warps per chain");
-        int32_t rc = set_smem(chain_kernel<KPV, 4>, smem4);
-        if (rc) return rc;
-        chain_kernel<KPV, 4><<<a.n_chains, 128, smem4, h->stream>>>(a);
-    } else {
-        int32_t rc = set_smem(chain_kernel<KPV, 1>, smem1);
-        if (rc) return rc;
-        chain_kernel<KPV, 1><<<a.n_chains, 32, smem1, h->stream>>>(a);
+    // control words: [0] chains still running, [1] / [2] number of paused chains after pass 1 / 2
+    CUDA_TRY(h->ctl.reserve(4));
+    const int32_t ctl0[4] = {a.n_chains, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h->ctl.p, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, h->stream));
+    a.active = h->ctl.p;
+    a.pause_below = 0;
+    a.from_list = 0;
+    // Straggler hand-over: chains need very different numbers of sweeps, so a one-wave launch ends with a
+    // few chains running on a mostly idle GPU. Once <= 2 chains per SM are left they pause at their next
+    // sweep boundary and a second launch on the same stream continues them with 8 warps each.
+    const bool two_pass = auto_team && team == 4 && a.s.n >= 8 && smem8 <= 200 * 1024 && a.n_chains > 2 * h->sm_count;
+    if (two_pass) {
+        CUDA_TRY(h->resume.reserve((size_t)a.n_chains));
+        CUDA_TRY(h->pending.reserve((size_t)a.n_chains));
+        a.pause_below = 2 * h->sm_count;
+        a.resume = h->resume.p;
+        a.pending_out = h->pending.p;
+        a.pending_out_n = h->ctl.p + 1;
     }
-    CUDA_TRY(cudaGetLastError());
+    int32_t rc;
+    if (team == 8) rc = launch_team<KPV, 8>(h, a, a.n_chains);
+    else if (team == 4) rc = launch_team<KPV, 4>(h, a, a.n_chains);
+    else rc = launch_team<KPV, 1>(h, a, a.n_chains);
+    if (rc) return rc;
+    if (two_pass) {
+        ChainArgs b = a;
+        b.pause_below = 0;
+        b.from_list = 1;
+        b.pending_in = h->pending.p;
+        b.pending_in_n = h->ctl.p + 1;
+        b.pending_out = nullptr;
+        b.pending_out_n = nullptr;
+        rc = launch_team<KPV, 8>(h, b, a.pause_below);
+        if (rc) return rc;
+        h->run_extra_launches = 1;
+    }
     return GIBBS_OK;
 }
 
@@ -545,6 +577,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->bg_g.release(); h->bg_sum.release(); h->bg_max.release(); h->bg_max_i.release();
     h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
     h->pvals.release(); h->basecnt.release(); h->gbuf.release();
+    h->ctl.release(); h->resume.release(); h->pending.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -815,8 +848,10 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         h->run_team = 1;
     } else {
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+        h->run_extra_launches = 0;
         rc = launch_chain(h, a);
         if (rc) return rc;
+        launches += h->run_extra_launches;
     }
     h->run_sampler = p->sampler;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));

@@ -64,6 +64,16 @@ struct ChainArgs {
     unsigned long long *stats;
     double cutoff;
     double bg[4];
+    // pause / resume at sweep boundaries: once few chains are still running they are continued by a
+    // second launch with wider teams (see launch_chain_kp)
+    int32_t *active;          // chains not finished yet
+    int32_t pause_below;      // pause when *active <= pause_below (0 = never)
+    int32_t from_list;        // 1 = this launch continues the chains listed in pending_in
+    int32_t *resume;          // [chains] phase | sweeps_in_phase << 8 of a paused chain
+    const int32_t *pending_in;
+    const int32_t *pending_in_n;
+    int32_t *pending_out;
+    int32_t *pending_out_n;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -80,7 +90,7 @@ constexpr int WARP_TABLE_BYTES = 1024 + 1024 + 512 + 512;
 struct TeamSmem {
     uint64_t *bar;        // [ring] mbarriers of the staged rows
     int32_t *total;       // [32*4] counts over ALL current sites of the chain
-    int32_t *flags;       // [2][8] per-warp outcome of a round (double-buffered)
+    int32_t *flags;       // [2][8] per-warp outcome of a round (double-buffered) + [16] pause decision
     uint32_t *lut;        // [16] histogram increments per nibble (hist_lut_entry)
     double *blk_hv;       // [2][32] state of two 32-sequence blocks
     int32_t *blk_site;    // [2][32]
@@ -90,7 +100,7 @@ struct TeamSmem {
 };
 
 constexpr int MAX_RING = 16;
-constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 64 + 512 + 256 + 256 + 64; // bar, total, flags, blk_hv, blk_site, blk_len, lut
+constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 96 + 512 + 256 + 256 + 64; // bar, total, flags, blk_hv, blk_site, blk_len, lut
 
 __host__ __device__ constexpr int ring_slots(int team_warps) { return 2 * team_warps < 4 ? 4 : 2 * team_warps; }
 __host__ __device__ inline int team_smem_bytes(int row_words, int team_warps) {
@@ -102,10 +112,10 @@ __device__ __forceinline__ TeamSmem carve_smem(unsigned char *base, int team_war
     s.bar = reinterpret_cast<uint64_t *>(base);
     s.total = reinterpret_cast<int32_t *>(base + 128);
     s.flags = reinterpret_cast<int32_t *>(base + 640);
-    s.blk_hv = reinterpret_cast<double *>(base + 704);
-    s.blk_site = reinterpret_cast<int32_t *>(base + 1216);
-    s.blk_len = reinterpret_cast<int32_t *>(base + 1472);
-    s.lut = reinterpret_cast<uint32_t *>(base + 1728);
+    s.blk_hv = reinterpret_cast<double *>(base + 736);
+    s.blk_site = reinterpret_cast<int32_t *>(base + 1248);
+    s.blk_len = reinterpret_cast<int32_t *>(base + 1504);
+    s.lut = reinterpret_cast<uint32_t *>(base + 1760);
     s.warp_tables = base + TEAM_FIXED_BYTES;
     s.row0 = reinterpret_cast<uint32_t *>(base + TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES);
     return s;

@@ -155,7 +155,11 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chain = blockIdx.x;
+    int chain = blockIdx.x;
+    if (a.from_list) { // continuing paused chains: one CTA per list entry
+        if ((int)blockIdx.x >= *a.pending_in_n) return;
+        chain = a.pending_in[blockIdx.x];
+    }
     const TeamSmem S = carve_smem(smem_raw, T);
     const WarpTables WT = warp_tables(S, warp);
 
@@ -177,12 +181,20 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
 
     int phase = next_phase(PH_INIT, a.phase_mask);
     int sweeps_in_phase = 0;
+    bool resumed = false, paused = false;
+    if (a.from_list) {
+        const int r = a.resume[chain];
+        phase = r & 255;
+        sweeps_in_phase = r >> 8;
+        resumed = true;
+    }
     while (phase != PH_DONE) {
         const int mode = phase == PH_LEFT ? SHIFT_LEFT : phase == PH_RIGHT ? SHIFT_RIGHT : SHIFT_NONE;
         // all-sites counts: once when the greedy phase starts (then kept incrementally: -old site,
         // +new site), once per sweep for the shift phases (they read the shifted snapshot, fs:357)
-        if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && sweeps_in_phase == 0))
+        if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && (sweeps_in_phase == 0 || resumed)))
             site_counts<KP, T>(a.s, sites, -1, k, mode, S.total, S.lut, tid);
+        resumed = false;
         // state of two 32-sequence blocks (lengths, sites, raw scores): coalesced loads, kept one block ahead
         auto load_block = [&](int b) {
             const int i = b * 32 + tid;
@@ -302,16 +314,18 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
             sweeps_in_phase = 0;
             phase = next_phase(phase + 1, a.phase_mask);
         }
+        // sweep boundary: when few chains are still running, hand this one over to the wide-team launch
+        if (phase != PH_DONE && a.pause_below > 0) {
+            if (tid == 0) S.flags[2 * T] = (*(volatile int32_t *)a.active <= a.pause_below) ? 1 : 0;
+            team_sync<T>();
+            if (S.flags[2 * T]) {
+                paused = true;
+                break;
+            }
+        }
     }
     if (tid == 0) // the ring always has R rows in flight: let them land before the CTA exits
         for (int i = 0; i < R; ++i) ring.wait(vbase + (uint32_t)i);
-    team_sync<T>();
-
-    // (log2 highValue, highIndex), fs:303
-    for (int n = tid; n < N; n += THREADS) {
-        const double v = __ldcg(hv + n);
-        if (v == v) scores[n] = log2_ref(v); // NaN = untouched caller-supplied entry keeps its score
-    }
     team_sync<T>();
     if (lane == 0) {
         atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
@@ -320,11 +334,28 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
         atomicAdd(a.stats + ST_SPECULATED, st_spec);
     }
     if (tid == 0) {
+        atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
+        atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
+    }
+    if (paused) {
+        if (tid == 0) {
+            a.resume[chain] = phase | (sweeps_in_phase << 8);
+            a.pending_out[atomicAdd(a.pending_out_n, 1)] = chain;
+        }
+        return;
+    }
+
+    // (log2 highValue, highIndex), fs:303
+    for (int n = tid; n < N; n += THREADS) {
+        const double v = __ldcg(hv + n);
+        if (v == v) scores[n] = log2_ref(v); // NaN = untouched caller-supplied entry keeps its score
+    }
+    team_sync<T>();
+    if (tid == 0) {
         double sum = 0.0; // Array.sum, left to right (fs:445)
         for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(scores + n));
         a.sums[chain] = sum;
-        atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
-        atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
+        if (a.active) atomicSub(a.active, 1);
     }
 }
 
