@@ -37,6 +37,7 @@ CONFIGS = {
     "C3": (10000, 1000, 16, 1024, True),  # 8192 restarts over 8 GPUs = 1024 per GPU
     "C4": (100000, 200, 20, 148, True),   # ChIP-seq-peak-sized set with phase-shift moves
 }
+NCU_DRAM_BYTES_PER_STEP = int((0.310528 + 1.492224 + 3.389952 + 0.011776) * 1e6)  # ncu --set full, round 1, C2
 PSEUDOCOUNT = 1e-4      # fsx:384
 ALPHABET_SIZE = 5       # dnaBases = [A; T; G; C; Gap], fsx:368-369
 SEED = 0xB200
@@ -352,7 +353,10 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
             "sweeps_per_chain": g_sweeps / (args.steps * chains * world), "exact_rescans_per_step": g_rescans / args.steps,
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s", "frac": achieved / smem_gbs,
-                         "traffic": None, "peak_source": "measured live: LDS.128 streaming microbenchmark (gibbs_measure_smem_bandwidth)",
+                         "traffic": NCU_DRAM_BYTES_PER_STEP if cfg_name == "C2" else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of both chain_kernel launches of one C2 step, "
+                                           "profiles/r01_ncu_c2_final_summary.txt",
+                         "peak_source": "measured live: LDS.128 streaming microbenchmark (gibbs_measure_smem_bandwidth)",
                          "peak_theoretical": smem_theory, "frac_of_theoretical": achieved / smem_theory,
                          "algorithmic_bytes_per_window_score": algorithmic_smem_bytes_per_window(k),
                          "kernel": "gibbs::chain_kernel", "kernel_ms": k_ms,
