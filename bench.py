@@ -79,9 +79,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self) -> dict:
+    def mark(self) -> int:
+        """index of the next sample: brackets the timed region inside a sampler that started earlier"""
+        return len(self.lines)
+
+    def stop(self, first: int = 0, last: int | None = None) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)   # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -89,7 +94,8 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        lines = self.lines[max(first - 1, 0): (last + 2) if last is not None else None] or self.lines[-2:]
+        for line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -250,6 +256,8 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
             allgather_best(float(res.sums[b]), chain_base + b, res.sites[b], res.scores[b])
         return res
 
+    sampler = ClockSampler(local_rank)   # started early (nvidia-smi needs a moment); samples are cut to the timed region
+    sampler.start()
     # ---- warm-up ----
     for w in range(args.warmup):
         device_step(-1 - w)
@@ -257,12 +265,11 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
     barrier()
 
     # ---- timed: device-resident ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     tot_windows = tot_updates = tot_sweeps = tot_rescans = launches = 0
     kernel_ms = []
     barrier()
+    clk_first = sampler.mark()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.fill_(s)                      # L2 flush between steps, outside the per-step event window
@@ -280,7 +287,7 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
     barrier()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop()
+    clk_last = sampler.mark()
 
     # ---- timed: end to end through the public API with host buffers ----
     e2e_windows = 0
@@ -299,6 +306,7 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
         launches_e2e = r.stats["kernel_launches"] + 1
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(clk_first, clk_last)
     assert len(best) in (1, n)
 
     # ---- reduce over ranks: totals summed, times max ----
