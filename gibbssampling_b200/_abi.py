@@ -118,7 +118,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """GIBBS_B200_LIB selects another build of the same library (used to compare kernel variants)."""
+    return os.environ.get("GIBBS_B200_LIB") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

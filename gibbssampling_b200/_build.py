@@ -12,6 +12,8 @@ SOURCES = [os.path.join(CSRC, "gibbs_api.cu")]
 DEPS = SOURCES + [
     os.path.join(CSRC, "gibbs_device.cuh"),
     os.path.join(CSRC, "gibbs_kernels.cuh"),
+    os.path.join(CSRC, "gibbs_motif.cuh"),
+    os.path.join(CSRC, "gibbs_drift.cuh"),
     os.path.join(ROOT, "include", "gibbs_b200.h"),
 ]
 

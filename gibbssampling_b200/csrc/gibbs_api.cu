@@ -11,6 +11,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -200,6 +201,26 @@ int32_t launch_team(gibbs_handle *h, const ChainArgs &a, int grid) {
 
 template <int KPV>
 int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
+    h->run_extra_launches = 0;
+    const char *init_env = getenv("GIBBS_B200_INIT_KERNEL"); // measurement switch: "0" keeps the random starts in the chain kernel
+    // Random starts are N independent site updates of N-1 draws each. With many chains of few sequences the
+    // chain kernel's own INIT sweep already fills the GPU (measured 6.6 vs 7.5 ms on C2); with few chains or
+    // many sequences the grid-wide kernel is the only way to use all SMs (C4, 8 chains: 17.2 s -> 0.61 s).
+    const bool init_wide = init_env ? init_env[0] != '0' : (a.n_chains < 4 * h->sm_count || a.s.n >= 4096);
+    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide) {
+        const int smem = init_smem_bytes(a.s.row_words);
+        if (smem <= 200 * 1024) {
+            int32_t rc = set_smem(init_kernel<KPV>, smem);
+            if (rc) return rc;
+            const long long items = (long long)a.n_chains * a.s.n;
+            long long grid = (items + INIT_WARPS - 1) / INIT_WARPS;
+            if (grid > 4LL * h->sm_count) grid = 4LL * h->sm_count;
+            init_kernel<KPV><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            a.phase_mask &= ~GIBBS_PHASE_INIT; // the chain kernel continues from the state just written
+            h->run_extra_launches += 1;
+        }
+    }
     int team = h->team_warps;
     const int smem4 = team_smem_bytes(a.s.row_words, 4), smem8 = team_smem_bytes(a.s.row_words, 8);
     const bool auto_team = team == 0;
@@ -242,7 +263,7 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
         b.pending_out_n = nullptr;
         rc = launch_team<KPV, 8>(h, b, a.pause_below);
         if (rc) return rc;
-        h->run_extra_launches = 1;
+        h->run_extra_launches += 1;
     }
     return GIBBS_OK;
 }
@@ -435,6 +456,7 @@ DeviceSeqs dev_seqs(const gibbs_handle *h) {
     s.len = h->len.p;
     s.n = h->n;
     s.row_words = h->row_words;
+    s.uniform_len = h->min_len == h->max_len ? h->max_len : 0;
     return s;
 }
 
@@ -848,7 +870,6 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         h->run_team = 1;
     } else {
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        h->run_extra_launches = 0;
         rc = launch_chain(h, a);
         if (rc) return rc;
         launches += h->run_extra_launches;

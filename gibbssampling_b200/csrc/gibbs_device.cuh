@@ -41,6 +41,7 @@ struct DeviceSeqs {
     const int32_t *len;     // [n]
     int32_t n;
     int32_t row_words;      // multiple of 4 (16 B) and >= ceil(max_len/16) + 4 zero words
+    int32_t uniform_len;    // > 0: every sequence has this length (saves a dependent load per random draw)
 };
 
 struct ChainArgs {

@@ -81,7 +81,20 @@ __global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, 
 // which the reference's Array.map consumes System.Random (fs:419-421, quirk A.6-5). Each lane
 // takes one Philox block (4 draws) per round; the 4 draws are processed branch-free so their
 // length / row loads overlap.
-template <int KP>
+// NB = Philox blocks per lane per round: 4 NB independent gathers in flight per lane.
+#ifndef GIBBS_P0_NB_CHAIN
+#define GIBBS_P0_NB_CHAIN 1
+#endif
+#ifndef GIBBS_P0_NB_INIT_SMALL
+#define GIBBS_P0_NB_INIT_SMALL 4
+#endif
+#ifndef GIBBS_P0_NB_INIT_LARGE
+#define GIBBS_P0_NB_INIT_LARGE 2
+#endif
+#ifndef GIBBS_INIT_MIN_BLOCKS
+#define GIBBS_INIT_MIN_BLOCKS 2
+#endif
+template <int KP, int NB>
 __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
                                                   int32_t *counts, const uint32_t *lut, int lane) {
     const int N = a.s.n, k = a.k;
@@ -91,50 +104,144 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
     const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
     const uint64_t d_end = base + (uint64_t)(N - 1);
     const uint64_t blk0 = base >> 2, blk1 = (d_end + 3) >> 2;
-    const int iters = (int)((blk1 - blk0 + 31) >> 5);
+    const int iters = (int)((blk1 - blk0 + 32 * NB - 1) / (32 * NB));
+    const int ulen = a.s.uniform_len;
     Hist<KP> h;
     h.clear();
-    for (int it0 = 0; it0 < iters; it0 += 63) { // byte counters: 63 rounds x 4 draws per lane
-        const int it1 = min(iters, it0 + 63);
+    constexpr int FLUSH_ROUNDS = 255 / (4 * NB); // byte counters hold 255 adds per lane
+    for (int it0 = 0; it0 < iters; it0 += FLUSH_ROUNDS) {
+        const int it1 = min(iters, it0 + FLUSH_ROUNDS);
         for (int it = it0; it < it1; ++it) {
-            const uint64_t blk = blk0 + (uint64_t)it * 32 + lane;
-            uint32_t wd[4] = {0, 0, 0, 0};
-            if (a.rng_mode == 0) {
-                const uint4 r = philox4x32_10(
-                    make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
-                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-                wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
-            }
-            uint64_t kmer[4];
-            bool valid[4];
+            uint64_t kmer[4 * NB];
+            bool valid[4 * NB];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const uint64_t d = blk * 4 + x;
-                const bool ok = blk < blk1 && d >= base && d < d_end;
-                valid[x] = ok;
-                const int r = ok ? (int)(d - base) : 0;
-                const int i = r + (r >= n ? 1 : 0); // always a valid sequence index (N >= 2)
-                const int range = __ldg(a.s.len + i) - k + 1;
-                int pos;
+            for (int q = 0; q < NB; ++q) {
+                const uint64_t blk = blk0 + ((uint64_t)it * NB + q) * 32 + lane;
+                uint32_t wd[4] = {0, 0, 0, 0};
                 if (a.rng_mode == 0) {
-                    pos = (int)__umulhi(wd[x], (uint32_t)range); // floor(word * 2^-32 * range), exact
-                } else {
-                    const double u = (ok && (int64_t)d < a.uniforms_per_chain)
-                                         ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
-                                         : 0.0;
-                    pos = (int)(u * (double)range);      // rnd.Next(0, L-k+1), fs:145
-                    pos = min(max(pos, 0), range - 1);   // memory safety for u outside [0,1)
+                    const uint4 r = philox4x32_10(
+                        make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
                 }
-                kmer[x] = kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos);
-            }
-            h.maybe_spill(4);
+                // rank of draw x of this block among the held-out sequence's draws; valid iff 0 <= r < N-1
+                const int r0 = (int)((int64_t)(blk << 2) - (int64_t)base);
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
-                if (valid[x]) h.add(kmer[x], lut); // invalid only at the two ends of the draw range
+                for (int x = 0; x < 4; ++x) {
+                    const bool ok = (unsigned)(r0 + x) < (unsigned)(N - 1);
+                    valid[q * 4 + x] = ok;
+                    const int r = ok ? r0 + x : 0;
+                    const int i = r + (r >= n ? 1 : 0); // always a valid sequence index (N >= 2)
+                    const int range = (ulen > 0 ? ulen : __ldg(a.s.len + i)) - k + 1;
+                    int pos;
+                    if (a.rng_mode == 0) {
+                        pos = (int)__umulhi(wd[x], (uint32_t)range); // floor(word * 2^-32 * range), exact
+                    } else {
+                        const int64_t d = (int64_t)base + r;
+                        const double u = (ok && d < a.uniforms_per_chain)
+                                             ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
+                                             : 0.0;
+                        pos = (int)(u * (double)range);      // rnd.Next(0, L-k+1), fs:145
+                        pos = min(max(pos, 0), range - 1);   // memory safety for u outside [0,1)
+                    }
+                    kmer[q * 4 + x] = kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                h.maybe_spill(4);
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (valid[q * 4 + x]) h.add(kmer[q * 4 + x], lut); // invalid only at the two ends of the draw range
+            }
         }
         h.template flush_add<false>(counts, k, lane);
     }
     __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// random starts (fs:412-430) as a grid-wide kernel
+// ------------------------------------------------------------------------------------------------
+// Every (chain, held-out sequence) pair of the random-start sweep is an independent site update (each
+// draws fresh sites for all the other sequences), so the sweep is spread over the whole GPU instead of
+// over the few warps of the chain's own team: one warp per work item, grid-stride over chains x N items,
+// each warp staging its rows through a private two-slot TMA pipeline. This is what keeps the N(N-1)
+// draws per restart of large sets (C4: 1e10 per chain) from running on a handful of warps.
+constexpr int INIT_WARPS = 8;
+
+__host__ __device__ inline int init_smem_bytes(int row_words) {
+    return 64 + INIT_WARPS * 16 + INIT_WARPS * WARP_TABLE_BYTES + INIT_WARPS * 2 * row_words * 4;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_kernel(const ChainArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.s.n, k = a.k, row_words = a.s.row_words;
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + 64) + warp * 2;
+    WarpTables WT;
+    {
+        unsigned char *b = smem_raw + 64 + INIT_WARPS * 16 + warp * WARP_TABLE_BYTES;
+        WT.wcol = reinterpret_cast<double *>(b);
+        WT.ptab = reinterpret_cast<int32_t *>(b + 1024);
+        WT.lgcol = reinterpret_cast<int32_t *>(b + 2048);
+        WT.counts = reinterpret_cast<int32_t *>(b + 2560);
+    }
+    uint32_t *rows = reinterpret_cast<uint32_t *>(smem_raw + 64 + INIT_WARPS * 16 + INIT_WARPS * WARP_TABLE_BYTES) +
+                     warp * 2 * row_words;
+    if (tid < 16) lut[tid] = hist_lut_entry(tid);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const long long total = (long long)a.n_chains * N;
+    const long long stride = (long long)gridDim.x * INIT_WARPS;
+    long long item = (long long)blockIdx.x * INIT_WARPS + warp;
+    const uint32_t bytes = (uint32_t)row_words * 4u;
+    auto issue = [&](long long it, uint32_t v) {
+        if (lane == 0) {
+            const int slot = (int)(v & 1u);
+            mbar_expect_tx(bar + slot, bytes);
+            bulk_g2s(rows + slot * row_words, a.s.packed + (size_t)(it % N) * row_words, bytes, bar + slot);
+        }
+    };
+    unsigned long long st_updates = 0, st_windows = 0, st_slow = 0;
+    uint32_t v = 0;
+    if (item < total) issue(item, 0);
+    while (item < total) {
+        const long long next = item + stride;
+        if (next < total) issue(next, v + 1); // the other slot was released by the __syncwarp below
+        mbar_wait(bar + (v & 1u), (v >> 1) & 1u);
+        const uint32_t *row = rows + (v & 1u) * row_words;
+        const int chain = (int)(item / N), n = (int)(item % N);
+        const int Wn = __ldg(a.s.len + n) - k + 1;
+        random_loo_counts<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE)>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lut, lane);
+        build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+        double p;
+        int w;
+        const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
+        if (lane == 0) {
+            a.sites[(size_t)chain * N + n] = w;
+            a.hv[(size_t)chain * N + n] = p;
+        }
+        st_updates += 1;
+        st_windows += (unsigned long long)Wn;
+        st_slow += slow ? 1 : 0;
+        __syncwarp();
+        item = next;
+        ++v;
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
+        atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
+        atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
+    }
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)a.n_chains);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -235,7 +342,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
                 Wn = len_n - k + 1;
                 double hv_n = 0.0;
                 if (phase == PH_INIT) {
-                    random_loo_counts<KP>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
+                    random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
                     build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                 } else {
                     site_n = S.blk_site[o];

@@ -152,6 +152,34 @@ def test_chains_match_oracle_philox(case, team):
     assert res.counts.tolist() == want_counts.tolist()
 
 
+@pytest.mark.parametrize("wide", ["0", "1"])
+@pytest.mark.parametrize("shape", [(70, 64, 40, 9), (300, 90, None, 12), (1100, 40, 30, 16)],
+                         ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
+def test_random_starts_same_on_both_kernels(shape, wide, monkeypatch):
+    """Random starts (fs:412-430) run either inside the chain kernel or as the grid-wide init kernel
+    (gibbs_api.cu picks by shape; GIBBS_B200_INIT_KERNEL forces one). Both must consume the uniform
+    stream exactly as the oracle does: N(N-1) draws, several flushes of the per-lane byte counters."""
+    n, L, Lmin, k = shape
+    monkeypatch.setenv("GIBBS_B200_INIT_KERNEL", wide)
+    ps = planted_motif_set(n, L, k, seed=21, min_length=Lmin)
+    seqs = ps.sequences()
+    bg = background_of(ps.ascii, 1e-4, 5)
+    S = O.sources(seqs)
+    pcv = O.pcv_from_acgt(bg)
+    n_chains = 3
+    with GibbsEngine(seqs) as eng:
+        res = eng.run(make_params(k, 1e-4, 5, bg, phase_mask=_abi.PHASE_INIT), n_chains, chain_id_base=7, seed=99)
+        full = eng.run(make_params(k, 1e-4, 5, bg), n_chains, chain_id_base=7, seed=99)
+    assert res.stats["kernel_launches"] >= (2 if wide == "1" else 1)
+    for c in range(n_chains):
+        score, pos, _ = _oracle_chain(S, k, 1e-4, pcv, b"ATGC-", seed=99, chain=7 + c, name="random_starts_with_bpv")
+        assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"
+        np.testing.assert_allclose(res.scores[c], score, rtol=LOG2_RTOL)
+        if n <= 300 or c == 0:   # the oracle's full restart is O(N^2 L k): seconds at N = 1100
+            score, pos, _ = _oracle_chain(S, k, 1e-4, pcv, b"ATGC-", seed=99, chain=7 + c)
+            assert full.sites[c].tolist() == pos.tolist(), f"chain {c}"
+
+
 @pytest.mark.parametrize("team", TEAMS)
 def test_chains_match_oracle_injected_uniforms(team):
     """Same comparison with an injected stream of doubles (the parity definition of north_star)."""
