@@ -8,6 +8,7 @@ Layout (only what the hot path needs):
   SiteSampler.py       reference function names of fs:298-707
   MotifSampler.py      reference function names of fs:709-1038
   distributed.py       chain sharding + the single all_gather of each GPU's best result
+  Results.py           what the script does with results: countBy positions, segments, PWM / information content
 """
 from . import _abi
 from ._abi import (GibbsArgumentError, GibbsCudaError, GibbsError, GibbsRouletteError, GibbsShortSequenceError,
