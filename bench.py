@@ -297,7 +297,8 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
     t0 = time.perf_counter()
     for s in range(args.steps):
         eng.upload_flat(host_ascii.numpy(), host_off.numpy())      # H2D + GPU 2-bit pack
-        r = eng.run(params, chains, chain_id_base=chain_base, seed=SEED + 1000 + s, want_counts=False)
+        r = eng.run(params, chains, chain_id_base=chain_base, seed=SEED + 1000 + s, want_counts=False,
+                    pinned=True)   # results land in the engine's page-locked buffers (gibbs_host_alloc)
         best = SiteSampler.replay_restart_loop(chains - 1, r.scores, r.sites, r.sums)   # what fs:434 returns
         if world > 1:
             allgather_best(float(r.sums[r.best_chain]), chain_base + r.best_chain, r.sites[r.best_chain],

@@ -117,8 +117,10 @@ def doMotifSamplingWithPCV(motifAmount, motifLength, pseudoCount, cutOff, alphab
 
 def replay_motif_restart_loop(numberOfRepetitions: int, scores: np.ndarray, sites: np.ndarray, sums: np.ndarray) -> list:
     """fs:857-881 over restarts that already ran (same loop as SiteSampler.replay_restart_loop, over MotifIndex[])."""
+    sums = np.asarray(sums, dtype=np.float64).tolist()
+
     def total(i):
-        return 0.0 if (i is None or i < 0) else float(sums[i])
+        return 0.0 if (i is None or i < 0) else sums[i]
 
     def same(a, b):
         if a is None or b is None:
@@ -128,6 +130,8 @@ def replay_motif_restart_loop(numberOfRepetitions: int, scores: np.ndarray, site
             if i < 0:
                 return True
             return scores.shape[1] == 1 and scores[i][0] == 0.0 and sites[i][0] < 0   # [|{PWMS 0.; Positions []}|]
+        if sums[a] != sums[b]:
+            return False   # equal MotifIndex arrays have equal left-to-right sums
         return bool(np.array_equal(sites[a], sites[b]) and np.array_equal(scores[a], scores[b]))
 
     acc, best, r, n = None, -1, 0, 0

@@ -135,13 +135,16 @@ def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, re
     Array.sum of each restart's scores (computed on the GPU in that order); recomputed here if absent.
     State is kept as restart indices (None = [||], -1 = the initial [|(0., 0)|]).
     """
+    if restart_sums is not None:
+        sums = np.asarray(restart_sums, dtype=np.float64).tolist()
+    else:
+        sums = None
+
     def total(i) -> float:
-        if i is None:
+        if i is None or i < 0:
             return 0.0
-        if i < 0:
-            return 0.0
-        if restart_sums is not None:
-            return float(restart_sums[i])
+        if sums is not None:
+            return sums[i]
         t = 0.0
         for v in restart_scores[i]:
             t = t + float(v)
@@ -155,6 +158,8 @@ def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, re
             if i < 0:
                 return True
             return restart_scores.shape[1] == 1 and restart_scores[i][0] == 0.0 and restart_sites[i][0] == 0
+        if sums is not None and sums[a] != sums[b]:
+            return False   # equal score arrays have equal left-to-right sums (NaN sums are unequal either way)
         return bool(np.array_equal(restart_sites[a], restart_sites[b]) and
                     np.array_equal(restart_scores[a], restart_scores[b]))
 

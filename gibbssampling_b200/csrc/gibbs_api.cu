@@ -979,6 +979,24 @@ int32_t gibbs_device_results(gibbs_handle *h, void **sites_dev, void **scores_de
     return GIBBS_OK;
 }
 
+int32_t gibbs_host_alloc(size_t bytes, void **ptr_out) {
+    if (!ptr_out) return fail(GIBBS_ERR_ARG, "null output");
+    *ptr_out = nullptr;
+    if (bytes == 0) return GIBBS_OK;
+    const cudaError_t e = cudaHostAlloc(ptr_out, bytes, cudaHostAllocPortable);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return fail(GIBBS_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
+    }
+    CUDA_TRY(e);
+    return GIBBS_OK;
+}
+
+int32_t gibbs_host_free(void *ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return GIBBS_OK;
+}
+
 int32_t gibbs_measure_smem_bandwidth(int32_t device, int32_t iters, double *gbps_out, double *ms_out) {
     if (!gbps_out) return fail(GIBBS_ERR_ARG, "null output");
     if (iters < 1) iters = 1;

@@ -98,6 +98,7 @@ class GibbsEngine:
     def __init__(self, sources: Sequence, device: int = 0):
         self._lib = _abi.load()
         self._h = C.c_void_p()
+        self._host: dict[str, tuple[int, int]] = {}   # pinned result buffers: name -> (address, bytes)
         buf, off = flatten_sources(sources)
         self.n = len(off) - 1
         self.lengths = np.diff(off).astype(np.int64)
@@ -110,6 +111,9 @@ class GibbsEngine:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.gibbs_destroy(self._h)
             self._h = C.c_void_p()
+        for ptr, _ in getattr(self, "_host", {}).values():
+            self._lib.gibbs_host_free(C.c_void_p(ptr))
+        self._host = {}
 
     def __del__(self):
         try:
@@ -223,11 +227,34 @@ class GibbsEngine:
         _abi.check(self._lib.gibbs_set_start_state(self._h, C.c_int32(s.shape[0]), _ptr(s, C.c_int32),
                                                    _ptr(v, C.c_double)))
 
-    def fetch(self, *, want_sites: bool = True, want_scores: bool = True, want_counts: bool = True) -> RunResult:
+    def _pinned(self, name: str, shape: tuple, dtype) -> np.ndarray:
+        """Page-locked result buffer owned by this engine, grown on demand and reused by later fetches."""
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr, cap = self._host.get(name, (None, 0))
+        if cap < need:
+            if ptr:
+                _abi.check(self._lib.gibbs_host_free(C.c_void_p(ptr)))
+                self._host.pop(name)
+            p = C.c_void_p()
+            _abi.check(self._lib.gibbs_host_alloc(C.c_size_t(need), C.byref(p)))
+            ptr, cap = p.value, need
+            self._host[name] = (ptr, cap)
+        buf = (C.c_uint8 * need).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def fetch(self, *, want_sites: bool = True, want_scores: bool = True, want_counts: bool = True,
+              pinned: bool = False) -> RunResult:
+        """Results of the last run_device. pinned=True returns views of page-locked buffers that the
+        NEXT pinned fetch on this engine overwrites (and close() frees): copy what must outlive that."""
         n_chains, k = self._last
-        sites = np.zeros((n_chains, self.n), dtype=np.int32) if want_sites else None
-        scores = np.zeros((n_chains, self.n), dtype=np.float64) if want_scores else None
-        sums = np.zeros(n_chains, dtype=np.float64)
+        if pinned:
+            sites = self._pinned("sites", (n_chains, self.n), np.int32) if want_sites else None
+            scores = self._pinned("scores", (n_chains, self.n), np.float64) if want_scores else None
+            sums = self._pinned("sums", (n_chains,), np.float64)
+        else:
+            sites = np.zeros((n_chains, self.n), dtype=np.int32) if want_sites else None
+            scores = np.zeros((n_chains, self.n), dtype=np.float64) if want_scores else None
+            sums = np.zeros(n_chains, dtype=np.float64)
         counts = np.zeros((k, 4), dtype=np.int32) if want_counts else None
         best = C.c_int32()
         st = RunStats()

@@ -23,6 +23,7 @@
 #ifndef GIBBS_B200_H
 #define GIBBS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -187,6 +188,14 @@ int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int6
                   gibbs_run_stats *stats_out);
 /* device pointers of the last run, for zero-copy collectives in the host layer (may be NULL) */
 int32_t gibbs_device_results(gibbs_handle *h, void **sites_dev, void **scores_dev, void **sums_dev);
+
+/* ---- host buffers ------------------------------------------------------------------------------- */
+/* Page-locked host memory for the *_out arrays above (results of 1024 chains x 1000 sequences are
+ * 12 MB; into pageable memory the copy is staged by the driver and pays first-touch page faults).
+ * The reference keeps its results in GC arrays (fs:408 Array.copy); the shim may instead hand out
+ * spans over these buffers. Any host pointer is accepted by every call; this is only faster. */
+int32_t gibbs_host_alloc(size_t bytes, void **ptr_out);
+int32_t gibbs_host_free(void *ptr);
 
 /* ---- measurement support ------------------------------------------------------------------------ */
 /* Streams `bytes` of shared-memory loads per SM for `iters` rounds; returns the achieved GB/s. */

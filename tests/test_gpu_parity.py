@@ -253,6 +253,25 @@ def test_chain_results_do_not_depend_on_batching():
         assert again.sites.tolist() == full.sites.tolist() and again.sums.tobytes() == full.sums.tobytes()
 
 
+def test_pinned_fetch_returns_the_same_results():
+    """fetch(pinned=True) copies into page-locked buffers from gibbs_host_alloc and reuses them."""
+    ps = planted_motif_set(16, 90, 8, seed=3)
+    seqs = ps.sequences()
+    bg = background_of(ps.ascii, 1e-4, 5)
+    p = make_params(8, 1e-4, 5, bg)
+    with GibbsEngine(seqs) as eng:
+        a = eng.run(p, 5, seed=11)
+        b = eng.run(p, 5, seed=11, pinned=True)
+        assert a.sites.tolist() == b.sites.tolist() and a.scores.tolist() == b.scores.tolist()
+        assert a.sums.tolist() == b.sums.tolist() and a.best_chain == b.best_chain
+        first = b.sites.ctypes.data
+        keep = b.sites.copy()
+        c = eng.run(p, 3, seed=12, pinned=True)            # smaller run: same buffer, overwritten
+        assert c.sites.ctypes.data == first and c.sites.shape == (3, 16)
+        d = eng.run(p, 9, seed=11, pinned=True)            # larger run: buffer regrown
+        assert d.sites[:5].tolist() == keep.tolist()
+
+
 def test_errors_cross_the_boundary_as_status_codes():
     with pytest.raises(_abi.GibbsSymbolError):
         GibbsEngine([b"ACGTNACGT", b"ACGTACGT"])
