@@ -110,7 +110,7 @@ struct gibbs_handle {
     int32_t gcnt[4] = {0, 0, 0, 0};
     DevBuf<int32_t> ctl, resume, pending; // pause / resume of straggler chains
     int32_t run_extra_launches = 0;
-    int32_t team_warps = 0;   // 0 = choose per launch; 1, 4 or 8 = forced (gibbs_set_team_warps)
+    int32_t team_warps = 0;   // 0 = choose per launch; 1, 4, 8 or 16 = forced (gibbs_set_team_warps)
     int32_t run_team = 0;
     int sm_count = 0;
 };
@@ -221,49 +221,62 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
             h->run_extra_launches += 1;
         }
     }
-    int team = h->team_warps;
-    const int smem4 = team_smem_bytes(a.s.row_words, 4), smem8 = team_smem_bytes(a.s.row_words, 8);
-    const bool auto_team = team == 0;
-    if (auto_team) { // 8 warps pay off only while the GPU has idle warp slots (few chains); measured on C2-shaped input
-        if (a.s.n >= 8 && a.n_chains <= 2 * h->sm_count && smem8 <= 200 * 1024) team = 8;
-        else team = (a.s.n >= 4 && smem4 <= 200 * 1024) ? 4 : 1;
+    // Warps per chain and the straggler hand-over. Chains need very different numbers of sweeps, so a
+    // one-wave launch ends with a few chains running on a mostly idle GPU. Stage 1 runs every chain with 4
+    // warps (7 chains per SM); once <= 2 chains per SM are still running they pause at their next sweep
+    // boundary and stage 2 continues them with 8 warps; once <= 1 chain per SM is left, stage 3 continues
+    // with 16 warps. Late sweeps move few sites, so the wider speculative rounds are rarely discarded.
+    const int N = a.s.n, sms = h->sm_count;
+    auto fits = [&](int t) { return N >= t && team_smem_bytes(a.s.row_words, t) <= 200 * 1024; };
+    struct Stage { int team, pause_below; };
+    Stage stages[3];
+    int n_stages = 0;
+    if (h->team_warps != 0) {
+        stages[n_stages++] = {h->team_warps, 0};
+    } else {
+        int first = a.n_chains > 2 * sms ? 4 : a.n_chains > sms ? 8 : 16; // wider teams only while warp slots are idle
+        if (first == 16 && !fits(16)) first = 8;
+        if (first == 8 && !fits(8)) first = 4;
+        if (first == 4 && !fits(4)) first = 1;
+        stages[n_stages++] = {first, 0};
+        if (first == 4 && fits(8)) {
+            stages[n_stages - 1].pause_below = 2 * sms;
+            stages[n_stages++] = {8, 0};
+        }
+        if (stages[n_stages - 1].team == 8 && fits(16)) {
+            stages[n_stages - 1].pause_below = sms;
+            stages[n_stages++] = {16, 0};
+        }
     }
-    h->run_team = team;
-    // control words: [0] chains still running, [1] / [2] number of paused chains after pass 1 / 2
+    h->run_team = stages[0].team;
+    // control words: [0] chains still running, [1] / [2] number of chains paused by stage 1 / 2
     CUDA_TRY(h->ctl.reserve(4));
     const int32_t ctl0[4] = {a.n_chains, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(h->ctl.p, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, h->stream));
     a.active = h->ctl.p;
-    a.pause_below = 0;
-    a.from_list = 0;
-    // Straggler hand-over: chains need very different numbers of sweeps, so a one-wave launch ends with a
-    // few chains running on a mostly idle GPU. Once <= 2 chains per SM are left they pause at their next
-    // sweep boundary and a second launch on the same stream continues them with 8 warps each.
-    const bool two_pass = auto_team && team == 4 && a.s.n >= 8 && smem8 <= 200 * 1024 && a.n_chains > 2 * h->sm_count;
-    if (two_pass) {
+    if (n_stages > 1) {
         CUDA_TRY(h->resume.reserve((size_t)a.n_chains));
-        CUDA_TRY(h->pending.reserve((size_t)a.n_chains));
-        a.pause_below = 2 * h->sm_count;
+        CUDA_TRY(h->pending.reserve(2 * (size_t)a.n_chains));
         a.resume = h->resume.p;
-        a.pending_out = h->pending.p;
-        a.pending_out_n = h->ctl.p + 1;
     }
-    int32_t rc;
-    if (team == 8) rc = launch_team<KPV, 8>(h, a, a.n_chains);
-    else if (team == 4) rc = launch_team<KPV, 4>(h, a, a.n_chains);
-    else rc = launch_team<KPV, 1>(h, a, a.n_chains);
-    if (rc) return rc;
-    if (two_pass) {
+    for (int st = 0; st < n_stages; ++st) {
         ChainArgs b = a;
-        b.pause_below = 0;
-        b.from_list = 1;
-        b.pending_in = h->pending.p;
-        b.pending_in_n = h->ctl.p + 1;
-        b.pending_out = nullptr;
-        b.pending_out_n = nullptr;
-        rc = launch_team<KPV, 8>(h, b, a.pause_below);
+        b.pause_below = stages[st].pause_below;
+        b.from_list = st > 0;
+        b.pending_in = st > 0 ? h->pending.p + (size_t)(st - 1) * a.n_chains : nullptr;
+        b.pending_in_n = st > 0 ? h->ctl.p + st : nullptr;
+        b.pending_out = st + 1 < n_stages ? h->pending.p + (size_t)st * a.n_chains : nullptr;
+        b.pending_out_n = st + 1 < n_stages ? h->ctl.p + st + 1 : nullptr;
+        const int grid = st == 0 ? a.n_chains : stages[st - 1].pause_below; // at most that many chains were paused
+        int32_t rc;
+        switch (stages[st].team) {
+        case 16: rc = launch_team<KPV, 16>(h, b, grid); break;
+        case 8: rc = launch_team<KPV, 8>(h, b, grid); break;
+        case 4: rc = launch_team<KPV, 4>(h, b, grid); break;
+        default: rc = launch_team<KPV, 1>(h, b, grid); break;
+        }
         if (rc) return rc;
-        h->run_extra_launches += 1;
+        if (st > 0) h->run_extra_launches += 1;
     }
     return GIBBS_OK;
 }
@@ -627,7 +640,8 @@ int32_t gibbs_num_sequences(const gibbs_handle *h) { return h ? h->n : 0; }
 
 int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps) {
     if (!h) return fail(GIBBS_ERR_ARG, "null handle");
-    if (warps != 0 && warps != 1 && warps != 4 && warps != 8) return fail(GIBBS_ERR_ARG, "team size must be 0 (auto), 1, 4 or 8 warps per chain");
+    if (warps != 0 && warps != 1 && warps != 4 && warps != 8 && warps != 16)
+        return fail(GIBBS_ERR_ARG, "team size must be 0 (auto), 1, 4, 8 or 16 warps per chain");
     h->team_warps = warps;
     return GIBBS_OK;
 }

@@ -91,7 +91,7 @@ constexpr int WARP_TABLE_BYTES = 1024 + 1024 + 512 + 512;
 struct TeamSmem {
     uint64_t *bar;        // [ring] mbarriers of the staged rows
     int32_t *total;       // [32*4] counts over ALL current sites of the chain
-    int32_t *flags;       // [2][8] per-warp outcome of a round (double-buffered) + [16] pause decision
+    int32_t *flags;       // [2][T] per-warp outcome of a round (double-buffered) + [2T] pause decision, T <= 16
     uint32_t *lut;        // [16] histogram increments per nibble (hist_lut_entry)
     double *blk_hv;       // [2][32] state of two 32-sequence blocks
     int32_t *blk_site;    // [2][32]
@@ -100,8 +100,11 @@ struct TeamSmem {
     uint32_t *row0;       // ring of staged rows, slot s at row0 + s * row_words
 };
 
-constexpr int MAX_RING = 16;
-constexpr int TEAM_FIXED_BYTES = MAX_RING * 8 + 512 + 96 + 512 + 256 + 256 + 64; // bar, total, flags, blk_hv, blk_site, blk_len, lut
+constexpr int MAX_TEAM = 16;
+constexpr int MAX_RING = 2 * MAX_TEAM;
+// bar 256, total 512, flags 160, blk_hv 512, blk_site 256, blk_len 256, lut 64, pad to 16 B
+constexpr int TEAM_FIXED_BYTES = 2048;
+static_assert(MAX_RING * 8 + 512 + 160 + 512 + 256 + 256 + 64 <= TEAM_FIXED_BYTES, "fixed part of the team's shared memory");
 
 __host__ __device__ constexpr int ring_slots(int team_warps) { return 2 * team_warps < 4 ? 4 : 2 * team_warps; }
 __host__ __device__ inline int team_smem_bytes(int row_words, int team_warps) {
@@ -111,12 +114,12 @@ __host__ __device__ inline int team_smem_bytes(int row_words, int team_warps) {
 __device__ __forceinline__ TeamSmem carve_smem(unsigned char *base, int team_warps) {
     TeamSmem s;
     s.bar = reinterpret_cast<uint64_t *>(base);
-    s.total = reinterpret_cast<int32_t *>(base + 128);
-    s.flags = reinterpret_cast<int32_t *>(base + 640);
-    s.blk_hv = reinterpret_cast<double *>(base + 736);
-    s.blk_site = reinterpret_cast<int32_t *>(base + 1248);
-    s.blk_len = reinterpret_cast<int32_t *>(base + 1504);
-    s.lut = reinterpret_cast<uint32_t *>(base + 1760);
+    s.total = reinterpret_cast<int32_t *>(base + 256);
+    s.flags = reinterpret_cast<int32_t *>(base + 768);
+    s.blk_hv = reinterpret_cast<double *>(base + 928);
+    s.blk_site = reinterpret_cast<int32_t *>(base + 1440);
+    s.blk_len = reinterpret_cast<int32_t *>(base + 1696);
+    s.lut = reinterpret_cast<uint32_t *>(base + 1952);
     s.warp_tables = base + TEAM_FIXED_BYTES;
     s.row0 = reinterpret_cast<uint32_t *>(base + TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES);
     return s;
@@ -207,6 +210,19 @@ struct RowRing {
             bulk_g2s(row0 + slot * row_words, gpacked + (size_t)next_seq * row_words, bytes, bar + slot);
             next_seq = next_seq + 1 < n_seqs ? next_seq + 1 : 0;
             ++issued;
+        }
+    }
+    // Stateless variant for a whole warp: lane l < cnt requests visit first_visit + l, which reads sequence
+    // (first_seq + l) mod n_seqs. A round of T committed visits costs one issue sequence instead of T, and
+    // the caller derives first_visit / first_seq from its loop counters (no ring state in registers).
+    __device__ __forceinline__ void fill_span(uint32_t first_visit, int first_seq, int cnt, int lane) const {
+        if (lane < cnt) {
+            const uint32_t bytes = (uint32_t)row_words * 4u;
+            const int slot = (int)((first_visit + (uint32_t)lane) & (R - 1));
+            int seq = first_seq + lane;
+            if (seq >= n_seqs) seq %= n_seqs;
+            mbar_expect_tx(bar + slot, bytes);
+            bulk_g2s(row0 + slot * row_words, gpacked + (size_t)seq * row_words, bytes, bar + slot);
         }
     }
     __device__ __forceinline__ const uint32_t *wait(uint32_t v) const {

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_k
 //     in the next round, which starts right after the mover. The committed sequence of site updates is
 //     therefore exactly the reference's sequential sweep.
 template <int KP, int T>
-__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_kernel(const ChainArgs a) {
+__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3 : 1)) chain_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
     ring.init(S, a.s, 0, tid);
     if (tid < 16) S.lut[tid] = hist_lut_entry(tid);
     team_sync<T>();
-    if (tid == 0) ring.fill(R);
+    if (warp == 0) ring.fill_span(0u, 0, R, lane);
 
     unsigned long long st_updates = 0, st_windows = 0, st_slow = 0, st_spec = 0;
     int st_sweeps = 0, capped = 0;
@@ -363,14 +363,10 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
             ++round;
             if (lane == 0) flags[warp] = flag;
             team_sync<T>();
-            int first_mover = T; // greedy only: later warps of the round saw stale counts
-            bool any_moved = false;
-#pragma unroll
-            for (int t = T - 1; t >= 0; --t) {
-                const bool mv = (flags[t] & 2) != 0;
-                if (mv && phase == PH_GREEDY) first_mover = t;
-                any_moved |= mv;
-            }
+            // greedy only: warps after the first mover of the round saw stale counts
+            const unsigned movers = __ballot_sync(FULL, lane < T && (flags[lane < T ? lane : 0] & 2) != 0);
+            const bool any_moved = movers != 0;
+            const int first_mover = (phase == PH_GREEDY && any_moved) ? __ffs(movers) - 1 : T;
             const int last_commit = min(first_mover, width - 1);
             changed |= any_moved; // (greedy: any mover of the round implies a committed mover)
             if (active) {
@@ -386,8 +382,9 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : 3)) chain_
                     st_spec += 1;
                 }
             }
-            n0 += min(last_commit + 1, N - n0);
-            if (tid == 0) ring.fill(vbase + (uint32_t)n0 + R); // rows of the committed visits are free
+            const int committed = min(last_commit + 1, N - n0);
+            if (warp == 0) ring.fill_span(vbase + (uint32_t)(n0 + R), n0 + R, committed, lane); // their rows are free
+            n0 += committed;
             if (phase == PH_GREEDY) {
                 if (first_mover < T) { // in-place sweep: later n see the new site (fs:388): -old k-mer, +new k-mer
                     if (warp == first_mover && lane < k) {

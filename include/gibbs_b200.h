@@ -117,7 +117,8 @@ int32_t gibbs_destroy(gibbs_handle *h);
 /* run all work of this handle on an existing CUDA stream (cudaStream_t as void*; NULL = own stream) */
 int32_t gibbs_set_stream(gibbs_handle *h, void *cuda_stream);
 int32_t gibbs_num_sequences(const gibbs_handle *h);
-/* tuning knob: warps per chain. 0 = automatic (4 when all chains fit on the GPU at once, else 1) */
+/* tuning knob: warps per chain, 1 / 4 / 8 / 16. 0 = automatic: 4 warps while many chains run, the last
+ * 2 (1) chains per SM are handed over to launches with 8 (16) warps per chain */
 int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps);
 int32_t gibbs_synchronize(gibbs_handle *h);
 

@@ -51,7 +51,7 @@ def _oracle_site_update(S, seqs, sites, h, k, pc, bg, alphabet):
     return O.acgt_counts(pfm), raw, score, pos
 
 
-TEAMS = [1, 4, 8]   # warps per chain: every kernel variant must be bit-identical to the oracle
+TEAMS = [1, 4, 8, 16]  # warps per chain: every kernel variant must be bit-identical to the oracle
 
 
 @pytest.mark.parametrize("team", TEAMS)
