@@ -70,8 +70,13 @@ struct gibbs_handle {
     DevBuf<uint8_t> ascii;
     DevBuf<int64_t> off;
     DevBuf<uint32_t> packed;
+    DevBuf<uint32_t> mask;     // same geometry as packed: 0b11 at symbols outside A,C,G,T
+    DevBuf<int32_t> rowflag;   // [n] sequence holds such a symbol
     DevBuf<int32_t> len;
-    DevBuf<int> flags; // [0] bad symbol, [1..3] wtab range
+    DevBuf<int> flags;    // [1..3] wtab range
+    DevBuf<int> symflags; // pack_kernel: [0] 1 + byte outside '*'..'Z', [1] symbols outside A,C,G,T, [2] Gap seen
+    int64_t n_masked = 0;      // symbols outside A,C,G,T in the uploaded set
+    bool has_gap = false;
 
     // PWM value table, keyed by the parameters it was built for
     DevBuf<WEnt> wtab;
@@ -132,6 +137,12 @@ int32_t check_params(const gibbs_handle *h, const gibbs_params *p) {
     if (p->alphabet_size < 1) return fail(GIBBS_ERR_ARG, "alphabet_size must be >= 1");
     if (!(p->pseudocount >= 0.0)) return fail(GIBBS_ERR_ARG, "pseudocount must be >= 0");
     if (p->background != GIBBS_BG_FIXED && p->background != GIBBS_BG_DATA) return fail(GIBBS_ERR_ARG, "unknown background mode %d", p->background);
+    // An alphabet of >= 5 symbols is taken to hold Gap like the script's dnaBases (fsx:368-369). Gap then has
+    // a PWM row of its own (quirk A.6-2), which the 4-row tables cannot hold; any other symbol outside A,C,G,T
+    // is not in the alphabet, has a PWM row of 0 (fs:283-287) and is handled by the mask plane.
+    if (h->has_gap && p->alphabet_size >= 5)
+        return fail(GIBBS_ERR_UNSUPPORTED, "sequences hold Gap '-' and alphabet_size = %d includes it: a fifth PWM row is not built "
+                                           "(pass alphabet_size = 4 to score Gap like any other non-alphabet symbol)", p->alphabet_size);
     if (p->background == GIBBS_BG_FIXED)
         for (int b = 0; b < 4; ++b)
             if (!(p->bg[b] > 0.0)) return fail(GIBBS_ERR_ARG, "background probability bg[%d] must be > 0", b);
@@ -470,6 +481,8 @@ DeviceSeqs dev_seqs(const gibbs_handle *h) {
     s.n = h->n;
     s.row_words = h->row_words;
     s.uniform_len = h->min_len == h->max_len ? h->max_len : 0;
+    s.mask = h->n_masked > 0 ? h->mask.p : nullptr;
+    s.rowflag = h->n_masked > 0 ? h->rowflag.p : nullptr;
     return s;
 }
 
@@ -493,28 +506,37 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
     CUDA_TRY(h->ascii.reserve((size_t)(total > 0 ? total : 1)));
     CUDA_TRY(h->off.reserve((size_t)n_seqs + 1));
     CUDA_TRY(h->packed.reserve((size_t)n_seqs * row_words));
+    CUDA_TRY(h->mask.reserve((size_t)n_seqs * row_words));
+    CUDA_TRY(h->rowflag.reserve((size_t)n_seqs));
     CUDA_TRY(h->len.reserve((size_t)n_seqs));
     CUDA_TRY(h->flags.reserve(8));
+    CUDA_TRY(h->symflags.reserve(4));
     std::vector<int64_t> rel((size_t)n_seqs + 1);
     for (int32_t i = 0; i <= n_seqs; ++i) rel[i] = offsets[i] - offsets[0];
     CUDA_TRY(cudaMemcpyAsync(h->ascii.p, seqs + offsets[0], (size_t)total, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->off.p, rel.data(), rel.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->flags.p, 0, 8 * sizeof(int), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->symflags.p, 0, 4 * sizeof(int), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->rowflag.p, 0, (size_t)n_seqs * sizeof(int32_t), h->stream));
     const int64_t words = (int64_t)n_seqs * row_words;
     pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, h->stream>>>(h->ascii.p, h->off.p, n_seqs, row_words, h->packed.p,
-                                                                       h->len.p, h->flags.p);
+                                                                       h->mask.p, h->rowflag.p, h->len.p, h->symflags.p);
     CUDA_TRY(cudaGetLastError());
-    int bad = 0;
-    CUDA_TRY(cudaMemcpyAsync(&bad, h->flags.p, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    int sym[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(sym, h->symflags.p, sizeof sym, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream)); // also keeps `rel` alive until the copy is done
+    const int bad = sym[0];
     h->n = 0;
     h->wtab_valid = false;
     h->bg_valid = false;
     h->drift_valid = false;
     h->run_done = false;
     if (bad)
-        return fail(GIBBS_ERR_SYMBOL, "symbol '%c' (0x%02x) is outside A,C,G,T (IndexOutOfRangeException analogue, fs:17)",
+        return fail(GIBBS_ERR_SYMBOL, "symbol '%c' (0x%02x) is outside '*'..'Z', the range of the 49-slot tables "
+                                      "(IndexOutOfRangeException, fs:17-20)",
                     (bad - 1) >= 32 && (bad - 1) < 127 ? (char)(bad - 1) : '?', bad - 1);
+    h->n_masked = sym[1];
+    h->has_gap = sym[2] != 0;
     h->n = n_seqs;
     h->row_words = row_words;
     h->max_len = (int32_t)max_len;
@@ -606,6 +628,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->ascii.release(); h->off.release(); h->packed.release(); h->len.release(); h->flags.release();
+    h->mask.release(); h->rowflag.release(); h->symflags.release();
     h->wtab.release(); h->prim_sites.release(); h->prim_i32.release(); h->prim_f64.release();
     h->sites.release(); h->hv.release(); h->scores.release(); h->sums.release(); h->uniforms.release();
     h->stats.release(); h->best.release();
@@ -736,6 +759,7 @@ int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldo
     int32_t rc = check_params(h, p);
     if (rc) return rc;
     if (heldout < 0 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
+    if (h->n_masked > 0) return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler with a fixed background only");
     rc = set_device(h);
     if (rc) return rc;
     rc = stage_sites(h, sites, heldout, p->k);
@@ -783,6 +807,9 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     if (p->sampler != GIBBS_SITE_SAMPLER && p->sampler != GIBBS_MOTIF_SAMPLER) return fail(GIBBS_ERR_ARG, "unknown sampler %d", p->sampler);
     if (rng_mode != GIBBS_RNG_PHILOX && rng_mode != GIBBS_RNG_INJECTED) return fail(GIBBS_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (rng_mode == GIBBS_RNG_INJECTED && (!uniforms || uniforms_per_chain < 0)) return fail(GIBBS_ERR_ARG, "injected uniforms missing");
+    if (h->n_masked > 0 && (p->sampler != GIBBS_SITE_SAMPLER || p->background != GIBBS_BG_FIXED))
+        return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler with a fixed background only "
+                                           "(MotifSampler / data-derived backgrounds need ACGT-only sequences)");
     rc = set_device(h);
     if (rc) return rc;
     h->run_done = false;

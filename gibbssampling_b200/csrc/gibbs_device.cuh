@@ -42,6 +42,12 @@ struct DeviceSeqs {
     int32_t n;
     int32_t row_words;      // multiple of 4 (16 B) and >= ceil(max_len/16) + 4 zero words
     int32_t uniform_len;    // > 0: every sequence has this length (saves a dependent load per random draw)
+    // Symbols outside A,C,G,T (IUPAC codes, Gap, Ter: any index the reference's 49-slot tables accept but
+    // whose PWM row is 0 because it is not in `alphabet`, fs:283-287). Null when the set has none, so the
+    // pure-ACGT path pays one uniform branch. mask has the geometry of `packed` with 0b11 at such bases
+    // (their 2-bit code is 0); rowflag[i] != 0 iff sequence i holds at least one.
+    const uint32_t *mask;
+    const int32_t *rowflag;
 };
 
 struct ChainArgs {
@@ -93,6 +99,7 @@ struct TeamSmem {
     int32_t *total;       // [32*4] counts over ALL current sites of the chain
     int32_t *flags;       // [2][T] per-warp outcome of a round (double-buffered) + [2T] pause decision, T <= 16
     uint32_t *lut;        // [16] histogram increments per nibble (hist_lut_entry)
+    int32_t *fix;         // [32] per column: masked bases the histogram counted as code 0 (see hist_fix)
     double *blk_hv;       // [2][32] state of two 32-sequence blocks
     int32_t *blk_site;    // [2][32]
     int32_t *blk_len;     // [2][32]
@@ -102,9 +109,9 @@ struct TeamSmem {
 
 constexpr int MAX_TEAM = 16;
 constexpr int MAX_RING = 2 * MAX_TEAM;
-// bar 256, total 512, flags 160, blk_hv 512, blk_site 256, blk_len 256, lut 64, pad to 16 B
-constexpr int TEAM_FIXED_BYTES = 2048;
-static_assert(MAX_RING * 8 + 512 + 160 + 512 + 256 + 256 + 64 <= TEAM_FIXED_BYTES, "fixed part of the team's shared memory");
+// bar 256, total 512, flags 160, blk_hv 512, blk_site 256, blk_len 256, lut 64, fix 128, pad to 16 B
+constexpr int TEAM_FIXED_BYTES = 2176;
+static_assert(MAX_RING * 8 + 512 + 160 + 512 + 256 + 256 + 64 + 128 <= TEAM_FIXED_BYTES, "fixed part of the team's shared memory");
 
 __host__ __device__ constexpr int ring_slots(int team_warps) { return 2 * team_warps < 4 ? 4 : 2 * team_warps; }
 __host__ __device__ inline int team_smem_bytes(int row_words, int team_warps) {
@@ -120,6 +127,7 @@ __device__ __forceinline__ TeamSmem carve_smem(unsigned char *base, int team_war
     s.blk_site = reinterpret_cast<int32_t *>(base + 1440);
     s.blk_len = reinterpret_cast<int32_t *>(base + 1696);
     s.lut = reinterpret_cast<uint32_t *>(base + 1952);
+    s.fix = reinterpret_cast<int32_t *>(base + 2016);
     s.warp_tables = base + TEAM_FIXED_BYTES;
     s.row0 = reinterpret_cast<uint32_t *>(base + TEAM_FIXED_BYTES + team_warps * WARP_TABLE_BYTES);
     return s;
@@ -283,6 +291,31 @@ __device__ __forceinline__ int shifted_site(int pos, int len, int k, int mode) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// symbols outside A,C,G,T (rare path, kept out of line so the ACGT path keeps its registers)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool row_masked(const DeviceSeqs &s, int i) { return s.mask != nullptr && __ldg(s.rowflag + i) != 0; }
+
+// 2 bits per column of the k-mer at `pos` of sequence i: 0b11 where the base is not A,C,G,T
+__device__ __noinline__ uint64_t mask_kmer(const uint32_t *__restrict__ mask, int row_words, int i, int pos, int k) {
+    const uint32_t *p = mask + (size_t)i * row_words + (pos >> 4);
+    const int sh = (pos & 15) * 2;
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    const uint64_t m = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+    return k >= 32 ? m : (m & ((1ull << (2 * k)) - 1ull));
+}
+
+// The histogram counted every masked base of this k-mer as code 0 (A): note the columns in fix[] so the
+// caller can take them out again. The reference counts such a base in its own (dead) row, fs:211-215.
+__device__ __noinline__ void hist_fix(const uint32_t *__restrict__ mask, int row_words, int i, int pos, int k, int32_t *fix) {
+    uint64_t m = mask_kmer(mask, row_words, i, pos, k);
+    while (m) {
+        const int j = (__ffsll((long long)m) - 1) >> 1;
+        atomicAdd(&fix[j], 1);
+        m &= ~(3ull << (2 * j));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-thread packed histogram of k-mers (replaces createPFMOf + fusePositionFrequencyMatrices,
 // fs:211-226)
 // ------------------------------------------------------------------------------------------------
@@ -357,9 +390,10 @@ struct Hist {
 // of the team take part; ends with a team sync.
 template <int KP, int T>
 __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *sites, int exclude, int k, int mode,
-                                            int32_t *total, const uint32_t *lut, int tid) {
+                                            int32_t *total, const uint32_t *lut, int32_t *fix, int tid) {
     constexpr int THREADS = 32 * T;
     for (int e = tid; e < MAX_COLS * 4; e += THREADS) total[e] = 0;
+    if (s.mask != nullptr && tid < MAX_COLS) fix[tid] = 0;
     team_sync<T>();
     Hist<KP> h;
     h.clear();
@@ -374,12 +408,17 @@ __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *
                 if (site >= 0) {
                     const int pos = shifted_site(site, __ldg(s.len + i), k, mode);
                     h.add(kmer_global<KP>(s.packed + (size_t)i * s.row_words, pos), lut);
+                    if (row_masked(s, i)) hist_fix(s.mask, s.row_words, i, pos, k, fix);
                 }
             }
         }
         h.template flush_add<(T > 1)>(total, k, tid & 31);
     }
     team_sync<T>();
+    if (s.mask != nullptr) {
+        if (tid < k) total[tid * 4] -= fix[tid];
+        team_sync<T>();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -390,7 +429,7 @@ __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *
 // per distinct count instead of once per window).
 template <int KP>
 __device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
-                                             const WEnt *__restrict__ wtab, int lane) {
+                                             const WEnt *__restrict__ wtab, int lane, uint64_t own_mask = 0) {
 #pragma unroll
     for (int e = lane; e < 8 * KP; e += 32) {
         const int j = e >> 2, b = e & 3;
@@ -398,7 +437,7 @@ __device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t 
         int32_t lg = 0;
         if (j < k) {
             int c = counts[e];
-            if (has_own && (int)((own >> (2 * j)) & 3u) == b) c -= 1;
+            if (has_own && (int)((own >> (2 * j)) & 3u) == b && !((own_mask >> (2 * j)) & 1u)) c -= 1; // (a masked own base was never counted)
             const int4 raw = __ldg(reinterpret_cast<const int4 *>(wtab + (size_t)c * 4 + b));
             w = __hiloint2double(raw.y, raw.x);
             lg = raw.z;
@@ -457,6 +496,26 @@ __device__ __forceinline__ void scan_exact_all(const uint32_t *row, int W, int k
     double hv = 0.0;
     int hw = 0;
     for (int w = lane; w < W; w += 32) {
+        const double p = exact_window<KP>(row, w, k, wcol);
+        if (p > hv) {
+            hv = p;
+            hw = w;
+        }
+    }
+    warp_argmax(hv, hw);
+    hv_out = hv;
+    w_out = hw;
+}
+
+// the same loop for a sequence with symbols outside A,C,G,T: a window that holds one scores 0 (its PWM
+// row is 0, fs:283-287), every other window is scored as above
+template <int KP>
+__device__ __noinline__ void scan_exact_masked(const uint32_t *row, const uint32_t *__restrict__ mask, int row_words, int n,
+                                               int W, int k, const double *wcol, int lane, double &hv_out, int &w_out) {
+    double hv = 0.0;
+    int hw = 0;
+    for (int w = lane; w < W; w += 32) {
+        if (mask_kmer(mask, row_words, n, w, k) != 0) continue;
         const double p = exact_window<KP>(row, w, k, wcol);
         if (p > hv) {
             hv = p;
@@ -601,9 +660,14 @@ __device__ __forceinline__ bool pick_argmax_ch(const WarpTables &T, const uint32
     return false;
 }
 
+// masked_seq >= 0: the held-out sequence holds symbols outside A,C,G,T (s.mask != null)
 template <int KP>
 __device__ __forceinline__ bool pick_argmax(const WarpTables &T, const uint32_t *row, int W, int k, int fast_ok, int lane,
-                                            double &hv_out, int &w_out) {
+                                            double &hv_out, int &w_out, const DeviceSeqs *s = nullptr, int masked_seq = -1) {
+    if (masked_seq >= 0) {
+        scan_exact_masked<KP>(row, s->mask, s->row_words, masked_seq, W, k, T.wcol, lane, hv_out, w_out);
+        return true;
+    }
     bool slow = !fast_ok;
     if (!slow) {
         if (W > 256) slow = pick_argmax_ch<KP, 16>(T, row, W, k, lane, hv_out, w_out);

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(32) drift_kernel(const DriftArgs d) {
     while (phase != PH_DONE) {
         const int mode = phase == PH_LEFT ? SHIFT_LEFT : phase == PH_RIGHT ? SHIFT_RIGHT : SHIFT_NONE;
         if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && sweeps_in_phase == 0))
-            site_counts<KP, 1>(a.s, sites, -1, k, mode, S.total, S.lut, lane);
+            site_counts<KP, 1>(a.s, sites, -1, k, mode, S.total, S.lut, S.fix, lane);
         bool changed = false;
         for (int n = 0; n < N; ++n, ++v) {
             const uint32_t *row = ring.wait(v);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(32) drift_kernel(const DriftArgs d) {
             uint64_t own = 0;
             const int32_t *counts;
             if (phase == PH_INIT) {
-                random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
+                random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
                 counts = WT.counts;
             } else {
                 site_n = __ldcg(sites + n);

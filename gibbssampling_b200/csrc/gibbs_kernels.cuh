@@ -16,35 +16,48 @@ __device__ __forceinline__ int next_phase(int from, int mask) {
 // ------------------------------------------------------------------------------------------------
 // setup kernels
 // ------------------------------------------------------------------------------------------------
-// ASCII -> 2-bit rows. One thread per packed word. Any symbol outside A,C,G,T raises *bad.
+// ASCII -> 2-bit rows + mask plane. One thread per packed word.
+// flags[0] = 1 + a byte outside '*'..'Z' (the reference's 49-slot tables cannot index it: IndexOutOfRange, fs:17-20)
+// flags[1] = number of symbols inside that range but outside A,C,G,T (mask plane 0b11, code 0)
+// flags[2] = 1 if one of them is Gap '-' (a member of the script's alphabet, fsx:368-369)
 __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off, int n, int row_words,
-                            uint32_t *__restrict__ packed, int32_t *__restrict__ len_out, int *bad) {
+                            uint32_t *__restrict__ packed, uint32_t *__restrict__ mask, int32_t *__restrict__ rowflag,
+                            int32_t *__restrict__ len_out, int *flags) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)n * row_words) return;
     const int i = (int)(t / row_words), wd = (int)(t % row_words);
     const int64_t o = off[i];
     const int len = (int)(off[i + 1] - o);
     if (wd == 0) len_out[i] = len;
-    uint32_t v = 0;
+    uint32_t v = 0, m = 0;
+    int other = 0;
     const int b0 = wd * 16;
 #pragma unroll
     for (int x = 0; x < 16; ++x) {
         const int b = b0 + x;
         if (b < len) {
             const uint8_t c = ascii[o + b];
-            uint32_t code;
+            uint32_t code = 0;
             if (c == 'A') code = 0;
             else if (c == 'C') code = 1;
             else if (c == 'G') code = 2;
             else if (c == 'T') code = 3;
-            else {
-                code = 0;
-                atomicExch(bad, 1 + (int)c);
+            else if (c >= 42 && c <= 90) {
+                m |= 3u << (2 * x);
+                ++other;
+                if (c == '-') atomicExch(flags + 2, 1);
+            } else {
+                atomicExch(flags, 1 + (int)c);
             }
             v |= code << (2 * x);
         }
     }
     packed[t] = v;
+    mask[t] = m;
+    if (other) {
+        atomicAdd(flags + 1, other);
+        rowflag[i] = 1;
+    }
 }
 
 // W(c, b) = ((c + pc) / den) / q[b]   (normalizePPM fs:260, createPositionWeightMatrix fs:286)
@@ -96,9 +109,10 @@ __global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, 
 #endif
 template <int KP, int NB>
 __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
-                                                  int32_t *counts, const uint32_t *lut, int lane) {
+                                                  int32_t *counts, const uint32_t *lut, int lane, int32_t *fix) {
     const int N = a.s.n, k = a.k;
     for (int e = lane; e < MAX_COLS * 4; e += 32) counts[e] = 0;
+    if (a.s.mask != nullptr) fix[lane] = 0; // fix[] = the warp's lgcol, free until build_tables
     __syncwarp();
     if (N < 2) return;
     const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
@@ -145,6 +159,7 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
                         pos = min(max(pos, 0), range - 1);   // memory safety for u outside [0,1)
                     }
                     kmer[q * 4 + x] = kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos);
+                    if (ok && row_masked(a.s, i)) hist_fix(a.s.mask, a.s.row_words, i, pos, k, fix);
                 }
             }
 #pragma unroll
@@ -158,6 +173,10 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
         h.template flush_add<false>(counts, k, lane);
     }
     __syncwarp();
+    if (a.s.mask != nullptr) {
+        if (lane < k) counts[lane * 4] -= fix[lane];
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -220,11 +239,11 @@ __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_k
         const uint32_t *row = rows + (v & 1u) * row_words;
         const int chain = (int)(item / N), n = (int)(item % N);
         const int Wn = __ldg(a.s.len + n) - k + 1;
-        random_loo_counts<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE)>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lut, lane);
+        random_loo_counts<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE)>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lut, lane, WT.lgcol);
         build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
         double p;
         int w;
-        const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
+        const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w, &a.s, row_masked(a.s, n) ? n : -1);
         if (lane == 0) {
             a.sites[(size_t)chain * N + n] = w;
             a.hv[(size_t)chain * N + n] = p;
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3
         // all-sites counts: once when the greedy phase starts (then kept incrementally: -old site,
         // +new site), once per sweep for the shift phases (they read the shifted snapshot, fs:357)
         if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && (sweeps_in_phase == 0 || resumed)))
-            site_counts<KP, T>(a.s, sites, -1, k, mode, S.total, S.lut, tid);
+            site_counts<KP, T>(a.s, sites, -1, k, mode, S.total, S.lut, S.fix, tid);
         resumed = false;
         // state of two 32-sequence blocks (lengths, sites, raw scores): coalesced loads, kept one block ahead
         auto load_block = [&](int b) {
@@ -332,17 +351,18 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3
             }
             const int n = n0 + warp;
             const bool active = n < N && warp < width;
-            int flag = 0, site_n = 0, w = 0, Wn = 0;
+            int flag = 0, site_n = 0, w = 0, Wn = 0, masked_n = -1;
             double p = 0.0;
-            uint64_t own = 0, neu = 0;
+            uint64_t own = 0, neu = 0, own_mk = 0;
             if (active) {
                 const uint32_t *row = ring.wait(vbase + (uint32_t)n);
                 const int o = ((n >> 5) & 1) * 32 + (n & 31);
                 const int len_n = S.blk_len[o];
                 Wn = len_n - k + 1;
                 double hv_n = 0.0;
+                masked_n = row_masked(a.s, n) ? n : -1; // the held-out sequence holds symbols outside A,C,G,T
                 if (phase == PH_INIT) {
-                    random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
+                    random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
                     build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                 } else {
                     site_n = S.blk_site[o];
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3
                     own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
                     build_tables<KP>(WT, S.total, true, own, k, a.wtab, lane);
                 }
-                const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
+                const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w, &a.s, row_masked(a.s, n) ? n : -1);
                 bool accept = true, moved = false;
                 if (phase != PH_INIT) {
                     accept = score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0); // fs:402
@@ -387,7 +407,14 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3
             n0 += committed;
             if (phase == PH_GREEDY) {
                 if (first_mover < T) { // in-place sweep: later n see the new site (fs:388): -old k-mer, +new k-mer
-                    if (warp == first_mover && lane < k) {
+                    if (warp == first_mover && masked_n >= 0) { // rare: masked bases were never counted
+                        const uint64_t neu_mk = mask_kmer(a.s.mask, a.s.row_words, n, w, k);
+                        if (lane < k) {
+                            const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
+                            if (!((own_mk >> (2 * lane)) & 1u)) S.total[lane * 4 + bo] -= 1;
+                            if (!((neu_mk >> (2 * lane)) & 1u)) S.total[lane * 4 + bn] += 1;
+                        }
+                    } else if (warp == first_mover && lane < k) {
                         const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
                         if (bo != bn) {
                             S.total[lane * 4 + bo] -= 1;
@@ -487,7 +514,7 @@ __global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
     const TeamSmem S = carve_smem(smem_raw, 1);
     if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
     __syncwarp();
-    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, lane);
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, S.fix, lane);
     for (int e = lane; e < a.k * 4; e += 32) a.counts_out[e] = S.total[e];
 }
 
@@ -503,20 +530,22 @@ __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
     if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
     __syncwarp();
     if (lane == 0) ring.fill(1);
-    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, lane);
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, S.fix, lane);
     const uint32_t *row = ring.wait(0);
     build_tables<KP>(WT, S.total, false, 0, a.k, a.wtab, lane);
     const int W = __ldg(a.s.len + a.heldout) - a.k + 1;
+    const int masked_n = row_masked(a.s, a.heldout) ? a.heldout : -1;
     if (mode == 0) {
         for (int w = lane; w < W; w += 32) {
-            const double p = exact_window<KP>(row, w, a.k, WT.wcol);
+            double p = exact_window<KP>(row, w, a.k, WT.wcol);
+            if (masked_n >= 0 && mask_kmer(a.s.mask, a.s.row_words, masked_n, w, a.k) != 0) p = 0.0; // PWM row of the symbol is 0
             if (a.raw_out) a.raw_out[w] = p;
             if (a.log2_out) a.log2_out[w] = log2_ref(p);
         }
     } else {
         double p;
         int w;
-        const bool slow = pick_argmax<KP>(WT, row, W, a.k, a.fast_ok, lane, p, w);
+        const bool slow = pick_argmax<KP>(WT, row, W, a.k, a.fast_ok, lane, p, w, &a.s, masked_n);
         if (lane == 0) {
             a.score_out[0] = log2_ref(p);
             a.score_out[1] = p;
@@ -534,7 +563,7 @@ __global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int3
     const TeamSmem S = carve_smem(smem_raw, 1);
     if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
     __syncwarp();
-    site_counts<KP, 1>(s, sites, -1, k, SHIFT_NONE, S.total, S.lut, lane);
+    site_counts<KP, 1>(s, sites, -1, k, SHIFT_NONE, S.total, S.lut, S.fix, lane);
     for (int e = lane; e < k * 4; e += 32) counts_out[e] = S.total[e];
 }
 

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
     int sweeps_in_phase = 0;
     while (phase != MPH_DONE) {
         if (phase != MPH_INIT && (phase == MPH_STOCH || sweeps_in_phase == 0)) {
-            site_counts<KP, 1>(a.s, sites, -1, k, SHIFT_NONE, S.total, S.lut, lane);
+            site_counts<KP, 1>(a.s, sites, -1, k, SHIFT_NONE, S.total, S.lut, S.fix, lane);
             if (m.data_bg) {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
             const int len_n = __ldg(a.s.len + n);
             const int W = len_n - k + 1;
             if (phase == MPH_INIT) { // getPWMOfRandomStarts[WithBPV] |> createMotifIndex prob [position] (fs:876-877, fs:993-994)
-                random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane);
+                random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
                 double p;
                 int w;
                 if (!m.data_bg) {
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(32) roulette_kernel(const RouletteArgs r) {
     if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
     __syncwarp();
     if (lane == 0) ring.fill(1);
-    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, lane);
+    site_counts<KP, 1>(a.s, a.sites, a.heldout, a.k, SHIFT_NONE, S.total, S.lut, S.fix, lane);
     const uint32_t *row = ring.wait(0);
     build_tables<KP>(WT, S.total, false, 0, a.k, a.wtab, lane);
     const int W = __ldg(a.s.len + a.heldout) - a.k + 1;

@@ -274,9 +274,9 @@ def test_pinned_fetch_returns_the_same_results():
 
 def test_errors_cross_the_boundary_as_status_codes():
     with pytest.raises(_abi.GibbsSymbolError):
-        GibbsEngine([b"ACGTNACGT", b"ACGTACGT"])
+        GibbsEngine([b"ACGT[ACGT", b"ACGTACGT"])    # '[' = 91: outside the 49-slot tables (fs:17-20)
     with pytest.raises(_abi.GibbsSymbolError):
-        GibbsEngine([b"ACGT-ACGT", b"acgtacgt"])
+        GibbsEngine([b"ACGT-ACGT", b"acgtacgt"])    # lower case never reaches the tables (the parser upper-cases)
     with GibbsEngine([b"ACGTACGT", b"ACG"]) as eng:
         with pytest.raises(_abi.GibbsShortSequenceError):
             eng.run(make_params(4, 1e-4, 5, [0.25] * 4), 1)
