@@ -199,13 +199,13 @@ int32_t set_smem(K kernel, int bytes) {
 // shortens every chain's critical path (measured faster than one warp per chain both when all chains
 // are resident at once -- C2 -- and when they run in several waves); one warp is kept for sets with
 // fewer than 4 sequences or rows too long for four sets of staging buffers.
-template <int KPV, int TV>
+template <int KPV, int TV, bool MASKED = false>
 int32_t launch_team(gibbs_handle *h, const ChainArgs &a, int grid) {
     const int smem = team_smem_bytes(a.s.row_words, TV);
     if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for %d warps per chain", TV);
-    int32_t rc = set_smem(chain_kernel<KPV, TV>, smem);
+    int32_t rc = set_smem(chain_kernel<KPV, TV, MASKED>, smem);
     if (rc) return rc;
-    chain_kernel<KPV, TV><<<grid, 32 * TV, smem, h->stream>>>(a);
+    chain_kernel<KPV, TV, MASKED><<<grid, 32 * TV, smem, h->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     return GIBBS_OK;
 }
@@ -218,7 +218,8 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
     // chain kernel's own INIT sweep already fills the GPU (measured 6.6 vs 7.5 ms on C2); with few chains or
     // many sequences the grid-wide kernel is the only way to use all SMs (C4, 8 chains: 17.2 s -> 0.61 s).
     const bool init_wide = init_env ? init_env[0] != '0' : (a.n_chains < 4 * h->sm_count || a.s.n >= 4096);
-    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide) {
+    const bool masked = a.s.mask != nullptr; // symbols outside A,C,G,T: one launch of the MASKED instantiation (1 or 4 warps)
+    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide && !masked) {
         const int smem = init_smem_bytes(a.s.row_words);
         if (smem <= 200 * 1024) {
             int32_t rc = set_smem(init_kernel<KPV>, smem);
@@ -242,7 +243,9 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
     struct Stage { int team, pause_below; };
     Stage stages[3];
     int n_stages = 0;
-    if (h->team_warps != 0) {
+    if (masked) {
+        stages[n_stages++] = {team_smem_bytes(a.s.row_words, 4) <= 200 * 1024 ? 4 : 1, 0};
+    } else if (h->team_warps != 0) {
         stages[n_stages++] = {h->team_warps, 0};
     } else {
         int first = a.n_chains > 2 * sms ? 4 : a.n_chains > sms ? 8 : 16; // wider teams only while warp slots are idle
@@ -280,6 +283,11 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
         b.pending_out_n = st + 1 < n_stages ? h->ctl.p + st + 1 : nullptr;
         const int grid = st == 0 ? a.n_chains : stages[st - 1].pause_below; // at most that many chains were paused
         int32_t rc;
+        if (masked) {
+            rc = stages[st].team == 4 ? launch_team<KPV, 4, true>(h, b, grid) : launch_team<KPV, 1, true>(h, b, grid);
+            if (rc) return rc;
+            continue;
+        }
         switch (stages[st].team) {
         case 16: rc = launch_team<KPV, 16>(h, b, grid); break;
         case 8: rc = launch_team<KPV, 8>(h, b, grid); break;

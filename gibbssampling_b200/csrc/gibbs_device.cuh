@@ -427,9 +427,9 @@ __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *
 // Leave-one-out count c = counts - own, then W(c, b) and its fixed-point log2 are gathered from the
 // precomputed table (normalizePPM fs:255-261 + createPositionWeightMatrix fs:282-287 evaluated once
 // per distinct count instead of once per window).
-template <int KP>
-__device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
-                                             const WEnt *__restrict__ wtab, int lane, uint64_t own_mask = 0) {
+template <int KP, bool MASKED>
+__device__ __forceinline__ void build_tables_impl(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
+                                                  const WEnt *__restrict__ wtab, int lane, uint64_t own_mask) {
 #pragma unroll
     for (int e = lane; e < 8 * KP; e += 32) {
         const int j = e >> 2, b = e & 3;
@@ -437,7 +437,7 @@ __device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t 
         int32_t lg = 0;
         if (j < k) {
             int c = counts[e];
-            if (has_own && (int)((own >> (2 * j)) & 3u) == b && !((own_mask >> (2 * j)) & 1u)) c -= 1; // (a masked own base was never counted)
+            if (has_own && (int)((own >> (2 * j)) & 3u) == b && !(MASKED && ((own_mask >> (2 * j)) & 1u))) c -= 1; // (a masked own base was never counted)
             const int4 raw = __ldg(reinterpret_cast<const int4 *>(wtab + (size_t)c * 4 + b));
             w = __hiloint2double(raw.y, raw.x);
             lg = raw.z;
@@ -452,6 +452,18 @@ __device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t 
         W.ptab[idx] = W.lgcol[(2 * p) * 4 + (nib & 3)] + W.lgcol[(2 * p + 1) * 4 + (nib >> 2)];
     }
     __syncwarp();
+}
+
+template <int KP>
+__device__ __forceinline__ void build_tables(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
+                                             const WEnt *__restrict__ wtab, int lane) {
+    build_tables_impl<KP, false>(W, counts, has_own, own, k, wtab, lane, 0);
+}
+// the held-out sequence's own site covers symbols outside A,C,G,T (own_mask: 0b11 at those columns); rare, out of line
+template <int KP>
+__device__ __noinline__ void build_tables_masked(const WarpTables &W, const int32_t *counts, uint64_t own, int k,
+                                                 const WEnt *__restrict__ wtab, int lane, uint64_t own_mask) {
+    build_tables_impl<KP, true>(W, counts, true, own, k, wtab, lane, own_mask);
 }
 
 // ------------------------------------------------------------------------------------------------

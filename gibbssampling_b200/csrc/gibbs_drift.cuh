@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(32) drift_kernel(const DriftArgs d) {
             uint64_t own = 0;
             const int32_t *counts;
             if (phase == PH_INIT) {
-                random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, false>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
                 counts = WT.counts;
             } else {
                 site_n = __ldcg(sites + n);

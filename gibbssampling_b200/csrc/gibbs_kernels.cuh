@@ -104,15 +104,20 @@ __global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, 
 #ifndef GIBBS_P0_NB_INIT_LARGE
 #define GIBBS_P0_NB_INIT_LARGE 2
 #endif
+#ifndef GIBBS_T4_MIN_BLOCKS
+#define GIBBS_T4_MIN_BLOCKS 7 // 72 registers per thread; measured against 6 (80) and 8 (64)
+#endif
 #ifndef GIBBS_INIT_MIN_BLOCKS
 #define GIBBS_INIT_MIN_BLOCKS 2
 #endif
-template <int KP, int NB>
-__device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
-                                                  int32_t *counts, const uint32_t *lut, int lane, int32_t *fix) {
+// MASKED = the set holds symbols outside A,C,G,T: a separate instantiation, so that the ACGT loop stays free of calls
+// and keeps its loads batched (with the check inline the random starts of C2 cost 60 % more instructions).
+template <int KP, int NB, bool MASKED>
+__device__ __forceinline__ void random_loo_counts_impl(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
+                                                       int32_t *counts, const uint32_t *lut, int lane, int32_t *fix) {
     const int N = a.s.n, k = a.k;
     for (int e = lane; e < MAX_COLS * 4; e += 32) counts[e] = 0;
-    if (a.s.mask != nullptr) fix[lane] = 0; // fix[] = the warp's lgcol, free until build_tables
+    if (MASKED) fix[lane] = 0; // fix[] = the warp's lgcol, free until build_tables
     __syncwarp();
     if (N < 2) return;
     const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
@@ -159,7 +164,7 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
                         pos = min(max(pos, 0), range - 1);   // memory safety for u outside [0,1)
                     }
                     kmer[q * 4 + x] = kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos);
-                    if (ok && row_masked(a.s, i)) hist_fix(a.s.mask, a.s.row_words, i, pos, k, fix);
+                    if (MASKED && ok && __ldg(a.s.rowflag + i) != 0) hist_fix(a.s.mask, a.s.row_words, i, pos, k, fix);
                 }
             }
 #pragma unroll
@@ -173,7 +178,7 @@ __device__ __forceinline__ void random_loo_counts(const ChainArgs &a, uint64_t c
         h.template flush_add<false>(counts, k, lane);
     }
     __syncwarp();
-    if (a.s.mask != nullptr) {
+    if (MASKED) {
         if (lane < k) counts[lane * 4] -= fix[lane];
         __syncwarp();
     }
@@ -239,11 +244,11 @@ __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_k
         const uint32_t *row = rows + (v & 1u) * row_words;
         const int chain = (int)(item / N), n = (int)(item % N);
         const int Wn = __ldg(a.s.len + n) - k + 1;
-        random_loo_counts<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE)>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lut, lane, WT.lgcol);
+        random_loo_counts_impl<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE), false>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lut, lane, WT.lgcol);
         build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
         double p;
         int w;
-        const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w, &a.s, row_masked(a.s, n) ? n : -1);
+        const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w); // (sets with masked symbols never get here)
         if (lane == 0) {
             a.sites[(size_t)chain * N + n] = w;
             a.hv[(size_t)chain * N + n] = p;
@@ -275,8 +280,10 @@ __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_k
 //     update MOVES a site (that changes the counts); later warps of the round are discarded and redone
 //     in the next round, which starts right after the mover. The committed sequence of site updates is
 //     therefore exactly the reference's sequential sweep.
-template <int KP, int T>
-__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3 : 1)) chain_kernel(const ChainArgs a) {
+// MASKED = the set holds symbols outside A,C,G,T (a.s.mask != null): a separate instantiation (4 warps only), because
+// the 4-warp kernel sits at its register limit and even never-taken branches cost the ACGT path 2-3 %.
+template <int KP, int T, bool MASKED = false>
+__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T4_MIN_BLOCKS : T == 8 ? 3 : 1)) chain_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
@@ -353,24 +360,29 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3
             const bool active = n < N && warp < width;
             int flag = 0, site_n = 0, w = 0, Wn = 0, masked_n = -1;
             double p = 0.0;
-            uint64_t own = 0, neu = 0, own_mk = 0;
+            uint64_t own = 0, neu = 0;
             if (active) {
                 const uint32_t *row = ring.wait(vbase + (uint32_t)n);
                 const int o = ((n >> 5) & 1) * 32 + (n & 31);
                 const int len_n = S.blk_len[o];
                 Wn = len_n - k + 1;
                 double hv_n = 0.0;
-                masked_n = row_masked(a.s, n) ? n : -1; // the held-out sequence holds symbols outside A,C,G,T
+                if (MASKED) masked_n = __ldg(a.s.rowflag + n) != 0 ? n : -1; // the held-out sequence holds symbols outside A,C,G,T
                 if (phase == PH_INIT) {
-                    random_loo_counts<KP, GIBBS_P0_NB_CHAIN>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                    random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
                     build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                 } else {
                     site_n = S.blk_site[o];
                     hv_n = S.blk_hv[o];
                     own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
-                    build_tables<KP>(WT, S.total, true, own, k, a.wtab, lane);
+                    if (MASKED && masked_n >= 0) // rare: the own site may cover symbols outside A,C,G,T
+                        build_tables_masked<KP>(WT, S.total, own, k, a.wtab, lane,
+                                                mask_kmer(a.s.mask, a.s.row_words, n, shifted_site(site_n, len_n, k, mode), k));
+                    else
+                        build_tables<KP>(WT, S.total, true, own, k, a.wtab, lane);
                 }
-                const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w, &a.s, row_masked(a.s, n) ? n : -1);
+                const bool slow = MASKED ? pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w, &a.s, masked_n)
+                                         : pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
                 bool accept = true, moved = false;
                 if (phase != PH_INIT) {
                     accept = score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0); // fs:402
@@ -407,7 +419,9 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? 7 : T == 8 ? 3
             n0 += committed;
             if (phase == PH_GREEDY) {
                 if (first_mover < T) { // in-place sweep: later n see the new site (fs:388): -old k-mer, +new k-mer
-                    if (warp == first_mover && masked_n >= 0) { // rare: masked bases were never counted
+                    if (MASKED && warp == first_mover && masked_n >= 0) { // rare: masked bases were never counted
+                        const int len_n = S.blk_len[((n >> 5) & 1) * 32 + (n & 31)];
+                        const uint64_t own_mk = mask_kmer(a.s.mask, a.s.row_words, n, shifted_site(site_n, len_n, k, mode), k);
                         const uint64_t neu_mk = mask_kmer(a.s.mask, a.s.row_words, n, w, k);
                         if (lane < k) {
                             const int bo = (int)((own >> (2 * lane)) & 3u), bn = (int)((neu >> (2 * lane)) & 3u);
