@@ -9,6 +9,7 @@
 #include "gibbs_motif.cuh"
 #include "gibbs_drift.cuh"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -913,6 +914,15 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         memcpy(d.gcnt, h->gcnt, sizeof d.gcnt);
         d.alpha_pc = (double)p->alphabet_size * p->pseudocount; // float alphabet.Length * pseudoCount, fs:117
         d.pc = p->pseudocount;
+        {   // Ranking pass allowed? Every odds ratio ppm / pcv lies in [pc / den, den / pc] with den <= all bases of the
+            // set + one more sequence + |A| pc (or N - 1 + |A| pc): no float64 product of k of them may leave the
+            // normal range (|log2| < 1000), and pc > 0 keeps every logarithm finite.
+            const double bases = (double)h->gcnt[0] + h->gcnt[1] + h->gcnt[2] + h->gcnt[3] + (double)h->max_len;
+            const double den = (bases > (double)h->n ? bases : (double)h->n) + d.alpha_pc;
+            d.fast_ok = (p->pseudocount > 0.0 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
+            if (getenv("GIBBS_B200_DRIFT_EXACT")) d.fast_ok = 0; // measurement / test switch: every window in float64
+            a.fast_ok = d.fast_ok;
+        }
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_drift(h, d);
         if (rc) return rc;

@@ -43,7 +43,7 @@ def test_data_background_restarts_match_oracle(case):
         assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"
         np.testing.assert_allclose(res.scores[c], score, rtol=RTOL)
         total += st.site_updates
-    assert res.stats["site_updates"] == total and res.stats["fast_path"] == 0
+    assert res.stats["site_updates"] == total and res.stats["fast_path"] == (1 if pc > 0 else 0)
 
 
 def test_script_call_and_phase_functions(golden):
@@ -74,3 +74,39 @@ def test_script_call_and_phase_functions(golden):
     got = SiteSampler.getBestPWMSsWithStartPositions(k, pc, DNA, seqs, start)
     assert [p for _, p in got] == kat["sites"]
     np.testing.assert_allclose([s for s, _ in got], [v for v, _ in kat["best_drifting"]], rtol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(60, 200, None, 8), (200, 500, 300, 12), (40, 120, None, 20), (30, 64, 40, 32)],
+                         ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
+def test_ranking_pass_equals_the_all_windows_float64_scan(shape, monkeypatch):
+    """The float32 ranking pass + exact re-scoring of the candidates must return what the scan of every window in
+    float64 returns (GIBBS_B200_DRIFT_EXACT=1 forces the latter): same sites, bit-identical scores, at sizes the CPU
+    oracle cannot reach in seconds. The small cases above pin both against the oracle."""
+    n, L, Lmin, k = shape
+    ps = planted_motif_set(n, L, k, seed=77, min_length=Lmin)
+    seqs = ps.sequences()
+    params = make_params(k, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA)
+    with GibbsEngine(seqs) as eng:
+        fast = eng.run(params, 6, chain_id_base=3, seed=9, want_counts=False)
+        monkeypatch.setenv("GIBBS_B200_DRIFT_EXACT", "1")
+        exact = eng.run(params, 6, chain_id_base=3, seed=9, want_counts=False)
+    assert fast.stats["fast_path"] == 1 and exact.stats["fast_path"] == 0
+    assert exact.stats["exact_rescans"] == exact.stats["site_updates"]
+    assert fast.stats["exact_rescans"] < 0.05 * fast.stats["site_updates"]
+    assert fast.sites.tolist() == exact.sites.tolist()
+    assert fast.scores.tobytes() == exact.scores.tobytes()
+    assert fast.sums.tobytes() == exact.sums.tobytes()
+
+
+def test_zero_pseudocount_takes_the_exact_scan():
+    ps = planted_motif_set(8, 60, 6, seed=5)
+    seqs = ps.sequences()
+    S = O.sources(seqs)
+    params = make_params(6, 0.0, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA)
+    with GibbsEngine(seqs) as eng:
+        res = eng.run(params, 3, seed=4, want_counts=False)
+    assert res.stats["fast_path"] == 0
+    for c in range(3):
+        rng, keep = O.make_rng(seed=4, chain=c)
+        score, pos, _ = O.site_step("do_site_sampling", S, 6, 0.0, rng=rng)
+        assert res.sites[c].tolist() == pos.tolist()
