@@ -55,7 +55,7 @@ def _split_motif_state(motifMem) -> tuple[np.ndarray, np.ndarray]:
 
 def _run(phase_mask: int, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, *, start=None,
          n_chains: int = 1, seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
-         max_sweeps: int = 0):
+         max_sweeps: int = 0, ppM=None):
     """pcv given -> the PCV family (fixed background); pcv None -> the data-derived family (fs:885-1038)."""
     _check_m(motifAmount)
     if pcv is None:
@@ -71,7 +71,13 @@ def _run(phase_mask: int, motifAmount, motifLength, pseudoCount, cutOff, alphabe
             scores, sites = _split_motif_state(start)
             eng.set_start_state(np.tile(sites, (n_chains, 1)), np.tile(scores, (n_chains, 1)))
         u = None if uniforms is None else np.asarray(uniforms, dtype=np.float64).reshape(n_chains, -1)
-        return eng.run(params, n_chains, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        if ppM is not None:
+            eng.set_start_ppm(ppM, motifLength)
+        try:
+            return eng.run(params, n_chains, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        finally:
+            if ppM is not None:
+                eng.set_start_ppm(None)
     finally:
         if own:
             eng.close()
@@ -192,18 +198,21 @@ def getMotifsWithBestInformationContents(numberOfRepetitions, motifAmount, motif
     return replay_motif_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
 
 
-def _not_built(name: str, where: str):
-    raise _abi.GibbsUnsupportedError(
-        _abi.GIBBS_ERR_UNSUPPORTED,
-        f"{name} ({where}) starts from a caller-supplied PositionProbabilityMatrix, which never crosses this "
-        "boundary (the PPM lives on the GPU); not built")
+def doMotifSamplingWithPPM(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, **kw) -> list:
+    """fs:1028-1032: SiteSampler.getMotifsWithBestPWMSOfPPM as the start, then the data-derived sweeps."""
+    if ppM is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "ppM is null (ArgumentNullException)")
+    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, ppM=ppM, **kw)
+    return _to_motif_array(res.scores[0], res.sites[0])
 
 
-def doMotifSamplingWithPPM(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, **kw):
-    """fs:1028-1032 -- not built."""
-    _not_built("doMotifSamplingWithPPM", "fs:1028")
-
-
-def getBestPWMSsOfPPM(numberOfRepetitions, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, **kw):
-    """fs:1001-1026 -- not built."""
-    _not_built("getBestPWMSsOfPPM", "fs:1001")
+def getBestPWMSsOfPPM(numberOfRepetitions, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, *,
+                      seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
+                      max_sweeps: int = 0) -> list:
+    """fs:1001-1026: the restart loop over doMotifSamplingWithPPM-shaped restarts."""
+    if ppM is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "ppM is null (ArgumentNullException)")
+    n_restarts = max(int(numberOfRepetitions) + 1, 1)
+    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
+               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps, ppM=ppM)
+    return replay_motif_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)

@@ -65,15 +65,21 @@ def _params(phase_mask: int, motifLength: int, pseudoCount: float, alphabet, pcv
 
 def _run_phases(phase_mask: int, motifLength: int, pseudoCount: float, alphabet, sources, pcv, *, start=None,
                 seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
-                max_sweeps: int = 0) -> SiteArray:
+                max_sweeps: int = 0, ppM=None) -> SiteArray:
     params = _params(phase_mask, motifLength, pseudoCount, alphabet, pcv, max_sweeps)
     eng, own = _engine_for(sources, engine)
     try:
         if start is not None:
             scores, sites = _split_state(start)
             eng.set_start_state(sites, scores)
+        if ppM is not None:
+            eng.set_start_ppm(ppM, motifLength)
         u = None if uniforms is None else np.asarray(uniforms, dtype=np.float64).reshape(1, -1)
-        res = eng.run(params, 1, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        try:
+            res = eng.run(params, 1, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        finally:
+            if ppM is not None:
+                eng.set_start_ppm(None)
         return _to_site_array(res.scores[0], res.sites[0])
     finally:
         if own:
@@ -178,7 +184,7 @@ def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, re
 
 
 def _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, pcv, *, seed: int = 0, chain: int = 0,
-                  uniforms=None, engine: Optional[GibbsEngine] = None, max_sweeps: int = 0) -> SiteArray:
+                  uniforms=None, engine: Optional[GibbsEngine] = None, max_sweeps: int = 0, ppM=None) -> SiteArray:
     params = _params(0, motifLength, pseudoCount, alphabet, pcv, max_sweeps)
     eng, own = _engine_for(sources, engine)
     try:
@@ -186,7 +192,13 @@ def _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sourc
         u = None
         if uniforms is not None:
             u = np.asarray(uniforms, dtype=np.float64).reshape(n_restarts, -1)  # restart r consumes row r
-        res = eng.run(params, n_restarts, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        if ppM is not None:
+            eng.set_start_ppm(ppM, motifLength)
+        try:
+            res = eng.run(params, n_restarts, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+        finally:
+            if ppM is not None:
+                eng.set_start_ppm(None)
         return replay_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
     finally:
         if own:
@@ -233,18 +245,27 @@ def getMotifsWithBestInformationContent(numberOfRepetitions, motifLength, pseudo
     return _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, None, **kw)
 
 
-def _unsupported(name: str, where: str):
-    raise _abi.GibbsUnsupportedError(
-        _abi.GIBBS_ERR_UNSUPPORTED,
-        f"{name} ({where}) starts from a caller-supplied PositionProbabilityMatrix, which never crosses this "
-        "boundary (the PPM lives on the GPU); not built")
+# ---- start from a caller-supplied PositionProbabilityMatrix (fs:644-689, fs:703) --------------------------------
+def getMotifsWithBestPWMSOfPPM(motifLength, pseudoCount, alphabet, sources, positionProbabilityMatrix, **kw) -> SiteArray:
+    """fs:644-661: every sequence is scanned with the GIVEN PPM; the random sites of the other sequences only shape
+    the drifting background. positionProbabilityMatrix: [49][k] like the reference's matrix, or [k][4] (A,C,G,T)."""
+    if positionProbabilityMatrix is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "positionProbabilityMatrix is null (ArgumentNullException)")
+    return _run_phases(_abi.PHASE_INIT, motifLength, pseudoCount, alphabet, sources, None, ppM=positionProbabilityMatrix, **kw)
 
 
-def doSiteSamplingWithPPM(motifLength, pseudoCount, alphabet, sources, ppM, **kw):
-    """fs:703-707 -- not built."""
-    _unsupported("doSiteSamplingWithPPM", "fs:703")
+def doSiteSamplingWithPPM(motifLength, pseudoCount, alphabet, sources, ppM, **kw) -> SiteArray:
+    """fs:703-707."""
+    if ppM is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "ppM is null (ArgumentNullException)")
+    mask = _abi.PHASE_INIT | _abi.PHASE_GREEDY | _abi.PHASE_LEFT | _abi.PHASE_RIGHT
+    return _run_phases(mask, motifLength, pseudoCount, alphabet, sources, None, ppM=ppM, **kw)
 
 
-def getBestInformationContentOfPPM(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, ppM, **kw):
-    """fs:664-689 -- not built."""
-    _unsupported("getBestInformationContentOfPPM", "fs:664")
+def getBestInformationContentOfPPM(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources,
+                                   positionProbabilityMatrix, **kw) -> SiteArray:
+    """fs:664-689: the restart loop over doSiteSamplingWithPPM-shaped restarts."""
+    if positionProbabilityMatrix is None:
+        raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "positionProbabilityMatrix is null (ArgumentNullException)")
+    return _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sources, None,
+                         ppM=positionProbabilityMatrix, **kw)

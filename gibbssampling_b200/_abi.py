@@ -34,7 +34,7 @@ EXPORTS = [
     "gibbs_abi_version", "gibbs_last_error", "gibbs_device_count", "gibbs_create", "gibbs_upload",
     "gibbs_destroy", "gibbs_set_stream", "gibbs_num_sequences", "gibbs_set_team_warps", "gibbs_synchronize",
     "gibbs_loo_counts", "gibbs_window_scores", "gibbs_pick_argmax", "gibbs_pick_roulette",
-    "gibbs_set_start_state", "gibbs_run_device", "gibbs_fetch", "gibbs_run", "gibbs_device_results",
+    "gibbs_set_start_ppm", "gibbs_set_start_state", "gibbs_run_device", "gibbs_fetch", "gibbs_run", "gibbs_device_results",
     "gibbs_host_alloc", "gibbs_host_free", "gibbs_measure_smem_bandwidth",
 ]
 

@@ -109,6 +109,8 @@ struct gibbs_handle {
     int32_t run_sampler = 0;
     // data-derived background (doSiteSampling): normalizePPM values per count, base counts per sequence
     DevBuf<double> pvals, gbuf;
+    DevBuf<double> start_ppm;  // gibbs_set_start_ppm: [k][4]
+    int32_t start_ppm_k = 0;   // 0 = none set
     DevBuf<int32_t> basecnt;
     bool drift_valid = false;
     double drift_pc = 0;
@@ -643,7 +645,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->stats.release(); h->best.release();
     h->bg_g.release(); h->bg_sum.release(); h->bg_max.release(); h->bg_max_i.release();
     h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
-    h->pvals.release(); h->basecnt.release(); h->gbuf.release();
+    h->pvals.release(); h->basecnt.release(); h->gbuf.release(); h->start_ppm.release();
     h->ctl.release(); h->resume.release(); h->pending.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -874,6 +876,14 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     a.stats = h->stats.p;
     a.cutoff = p->cutoff;
     memcpy(a.bg, p->bg, sizeof a.bg);
+    a.ppm_given = nullptr;
+    if (h->start_ppm_k != 0) {
+        if (p->background != GIBBS_BG_DATA)
+            return fail(GIBBS_ERR_ARG, "a start PPM is set (gibbs_set_start_ppm) but the run uses a fixed background: the reference "
+                                       "has the ...OfPPM / ...WithPPM functions in the data-derived family only (fs:644, fs:1028)");
+        if (h->start_ppm_k != p->k) return fail(GIBBS_ERR_ARG, "the start PPM has %d columns, the run k = %d", h->start_ppm_k, p->k);
+        a.ppm_given = h->start_ppm.p;
+    }
     if (p->sampler == GIBBS_MOTIF_SAMPLER) {
         if (p->background == GIBBS_BG_FIXED) {
             rc = ensure_bgtab(h, p, &launches);
@@ -944,6 +954,22 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     h->run_fast = a.fast_ok;
     h->run_launches = launches;
     h->run_done = true;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_set_start_ppm(gibbs_handle *h, const double *ppm, int32_t k) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    if (!ppm) {
+        h->start_ppm_k = 0;
+        return GIBBS_OK;
+    }
+    if (k < 1 || k > GIBBS_MAX_K) return fail(GIBBS_ERR_ARG, "motif width k=%d outside 1..%d", k, GIBBS_MAX_K);
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    CUDA_TRY(h->start_ppm.reserve((size_t)GIBBS_MAX_K * 4));
+    CUDA_TRY(cudaMemcpyAsync(h->start_ppm.p, ppm, (size_t)k * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream)); // the caller's buffer is free on return
+    h->start_ppm_k = k;
     return GIBBS_OK;
 }
 

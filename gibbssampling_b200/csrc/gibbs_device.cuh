@@ -71,6 +71,10 @@ struct ChainArgs {
     unsigned long long *stats;
     double cutoff;
     double bg[4];
+    // getMotifsWithBestPWMSOfPPM (fs:644-661): the random starts are scored against this caller-supplied PPM
+    // ([k][4], rows A,C,G,T of the reference's 49 x k matrix) instead of the PPM of the random sites; the random sites
+    // then only shape the background. Null = the usual random starts. Data-derived background only.
+    const double *ppm_given;
     // pause / resume at sweep boundaries: once few chains are still running they are continued by a
     // second launch with wider teams (see launch_chain_kp)
     int32_t *active;          // chains not finished yet

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(32) drift_kernel(const DriftArgs d) {
             for (int e = lane; e < 4 * k; e += 32) {
                 int c = counts[e];
                 if (phase != PH_INIT && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3)) c -= 1;
-                WT.wcol[e] = __ldg(d.pvals + c);
+                WT.wcol[e] = (phase == PH_INIT && a.ppm_given) ? __ldg(a.ppm_given + e) : __ldg(d.pvals + c); // fs:661 / fs:573-575
                 WT.lgcol[e] = c;
             }
             __syncwarp();
@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(32) drift_kernel(const DriftArgs d) {
             double p;
             int w;
             bool ranked = false;
-            if (d.fast_ok) { // (WT.counts was consumed above: its space holds the float32 log table)
+            if (d.fast_ok && !(phase == PH_INIT && a.ppm_given)) { // (a supplied PPM may hold zeros or denormals: exact scan)
+                // WT.counts was consumed above: its space holds the float32 log table
                 drift_pair_table<KP>(WT.wcol, reinterpret_cast<float *>(WT.counts), reinterpret_cast<float *>(WT.ptab), k, lane);
                 ranked = scan_drifting_fast<KP>(row, W, k, WT.wcol, reinterpret_cast<const float *>(WT.ptab), f0, cn, d.pc,
                                                 d.alpha_pc, lane, p, w);

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                 } else { // SiteSampler.getPWMOfRandomStarts: drifting background (fs:589-611)
                     for (int e = lane; e < 4 * k; e += 32) {
                         const int c = WT.counts[e];
-                        WT.wcol[e] = __ldg(m.pvals + c);
+                        WT.wcol[e] = a.ppm_given ? __ldg(a.ppm_given + e) : __ldg(m.pvals + c); // fs:1029 / fs:877
                         WT.lgcol[e] = c;
                     }
                     __syncwarp();

@@ -216,6 +216,21 @@ class GibbsEngine:
                                                   C.c_int32(_abi.GIBBS_RNG_PHILOX), None, C.c_int64(0)))
         self._last = (int(n_chains), int(params.k))
 
+    def set_start_ppm(self, ppm, k: Optional[int] = None) -> None:
+        """`positionProbabilityMatrix` of the ...OfPPM / ...WithPPM functions (fs:644): the random starts of the
+        following data-derived runs are scored against it. ppm = [k][4] (A,C,G,T per column) or the reference's
+        [49][k] matrix (rows = symbol - 42); None clears it."""
+        if ppm is None:
+            _abi.check(self._lib.gibbs_set_start_ppm(self._h, None, C.c_int32(0)))
+            return
+        a = np.asarray(ppm, dtype=np.float64)
+        if a.ndim == 2 and a.shape[0] == 49 and (k is None or a.shape[1] == k):
+            a = a[[ord(c) - 42 for c in "ACGT"], :].T
+        if a.ndim != 2 or a.shape[1] != 4 or (k is not None and a.shape[0] != k):
+            raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "ppm must be [k][4] (A,C,G,T) or [49][k]")
+        a = np.ascontiguousarray(a)
+        _abi.check(self._lib.gibbs_set_start_ppm(self._h, _ptr(a, C.c_double), C.c_int32(a.shape[0])))
+
     def set_start_state(self, sites, scores) -> None:
         """startPositions : (float*int)[] of the sweep functions (fs:381 ...), per chain."""
         s = np.ascontiguousarray(sites, dtype=np.int32)

@@ -161,6 +161,16 @@ int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldo
  * stochastic sweep (fs:851). Results stay on the device until gibbs_fetch.
  */
 /*
+ * Replaces: the `positionProbabilityMatrix` argument of getMotifsWithBestPWMSOfPPM (fs:644-661) and of its callers
+ * doSiteSamplingWithPPM (fs:703), getBestInformationContentOfPPM (fs:664), doMotifSamplingWithPPM (fs:1028),
+ * getBestPWMSsOfPPM (fs:1002). ppm = double [k][4]: rows A,C,G,T of the reference's 49 x k matrix, entry j*4+b.
+ * While set, the random starts (GIBBS_PHASE_INIT) of runs with GIBBS_BG_DATA and params.k == k are scored against
+ * this PPM instead of the PPM of the random sites; the random sites still shape the background (fs:651-659) and
+ * consume the same N(N-1) uniforms. ppm = NULL clears it. Runs with GIBBS_BG_FIXED reject a set PPM (the reference
+ * has no such function).
+ */
+int32_t gibbs_set_start_ppm(gibbs_handle *h, const double *ppm_or_null, int32_t k);
+/*
  * Start state for pipelines whose phase_mask lacks GIBBS_PHASE_INIT: the `startPositions :
  * (float*int)[]` / `motifMem : MotifIndex[]` argument of the sweep functions (fs:381, fs:350, fs:318,
  * fs:788, fs:828). sites int32 [n_chains][n_seqs] (-1 = Positions []), scores double

@@ -131,8 +131,10 @@ def test_select_best_is_strict_max_with_lowest_chain_id():
 
 
 def test_unbuilt_reference_entry_points_say_so():
-    with pytest.raises(_abi.GibbsUnsupportedError):
+    with pytest.raises(_abi.GibbsArgumentError):      # a null PPM is the reference's ArgumentNullException
         SiteSampler.doSiteSamplingWithPPM(6, 1e-4, DNA, ["ACGTACGT"], None)
+    with pytest.raises(_abi.GibbsArgumentError):
+        MotifSampler.doMotifSamplingWithPPM(1, 6, 1e-4, 0.0, DNA, ["ACGTACGT"], None)
     with pytest.raises(_abi.GibbsUnsupportedError):
         SiteSampler.doSiteSampling(6, 1e-4, list("AT"), ["ACGTACGT"])
     with pytest.raises(_abi.GibbsUnsupportedError):
