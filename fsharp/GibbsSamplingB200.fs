@@ -56,6 +56,12 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int gibbs_set_start_state(IntPtr handle, int nChains, int[] sites, float[] scores)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_set_start_ppm(IntPtr handle, float[] ppmOrNull, int k)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_host_alloc(unativeint bytes, IntPtr& ptr)   // optional: page-locked result buffers
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int gibbs_host_free(IntPtr ptr)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int gibbs_pick_argmax(IntPtr handle, int[] sites, int heldout, GibbsParams& p, float& score, int& site)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int gibbs_run(IntPtr handle, GibbsParams& p, int nChains, int64 chainIdBase, uint64 seed, int rngMode,
@@ -82,16 +88,26 @@ module Native =
         sources |> Array.iteri (fun i s -> s |> Array.iteri (fun j b -> buf.[int offsets.[i] + j] <- byte (BioItem.symbol b)))
         buf, offsets
 
-    let makeParams (k:int) (pc:float) (alphabet:#IBioItem[]) (pcv:CompositeVector.ProbabilityCompositeVector) phaseMask =
-        let sym c = pcv.Array.[int c - 42]
+    /// pcv = Some _ : the WithBPV family (fixed background); None : the data-derived family (fs:462, fs:697)
+    let makeParams (k:int) (pc:float) (alphabet:#IBioItem[]) (pcv:CompositeVector.ProbabilityCompositeVector option) phaseMask =
         let mutable p = GibbsParams()
         p.k <- k; p.alphabetSize <- alphabet.Length; p.pseudocount <- pc
-        p.bgA <- sym 'A'; p.bgC <- sym 'C'; p.bgG <- sym 'G'; p.bgT <- sym 'T'
-        p.sampler <- 0; p.phaseShifts <- 1; p.maxSweeps <- 0; p.phaseMask <- phaseMask; p.background <- 0
+        match pcv with
+        | Some v ->
+            let sym c = v.Array.[int c - 42]
+            p.bgA <- sym 'A'; p.bgC <- sym 'C'; p.bgG <- sym 'G'; p.bgT <- sym 'T'; p.background <- 0
+        | None ->
+            p.bgA <- 0.25; p.bgC <- 0.25; p.bgG <- 0.25; p.bgT <- 0.25; p.background <- 1
+        p.sampler <- 0; p.phaseShifts <- 1; p.maxSweeps <- 0; p.phaseMask <- phaseMask
         p
 
+    /// rows A,C,G,T of a 49 x k PositionProbabilityMatrix as [k][4] (gibbs_set_start_ppm)
+    let flattenPPM (k:int) (ppM:PositionMatrix.PositionProbabilityMatrix) =
+        Array.init (k * 4) (fun e -> ppM.Matrix.[int "ACGT".[e % 4] - 42, e / 4])
+
     /// n restarts as n chains of one launch; returns (scores, sites, sums) per restart
-    let runChains (phaseMask:int) (nChains:int) (seed:uint64) k pc alphabet sources pcv (start:((float*int)[]) option) =
+    let runChainsWith (ppM:PositionMatrix.PositionProbabilityMatrix option) (phaseMask:int) (nChains:int) (seed:uint64) k pc alphabet sources
+                      (pcv:CompositeVector.ProbabilityCompositeVector option) (start:((float*int)[]) option) =
         let buf, offsets = flatten sources
         let mutable h = IntPtr.Zero
         check (gibbs_create(buf, offsets, sources.Length, 0, &h))
@@ -103,6 +119,9 @@ module Native =
                 let scores = Array.init (nChains * n) (fun i -> fst st.[i % n])
                 check (gibbs_set_start_state(h, nChains, sites, scores))
             | None -> ()
+            match ppM with
+            | Some m -> check (gibbs_set_start_ppm(h, flattenPPM k m, k))   // fs:644: positionProbabilityMatrix
+            | None -> ()
             let mutable p = makeParams k pc alphabet pcv phaseMask
             let sites, scores, sums = Array.zeroCreate (nChains * n), Array.zeroCreate (nChains * n), Array.zeroCreate nChains
             let mutable best = 0
@@ -111,6 +130,9 @@ module Native =
             Array.init nChains (fun c -> Array.init n (fun i -> scores.[c * n + i], sites.[c * n + i])), sums
         finally
             gibbs_destroy h |> ignore
+
+    let runChains phaseMask nChains seed k pc alphabet sources pcv start =
+        runChainsWith None phaseMask nChains seed k pc alphabet sources (Some pcv) start
 
 open CompositeVector
 
@@ -150,3 +172,14 @@ module SiteSampler =
                     next <- next + 1
                     loop (n + 1) pwms bestPWMS
         loop 0 [||] [|0., 0|]
+
+    // ---- data-derived background (fs:462-640, fs:697): background = 1, no pcv ---------------------------------
+    /// fs:697-701
+    let doSiteSampling motifLength pseudoCount alphabet sources =
+        (Native.runChainsWith None 15 1 (seedOf None) motifLength pseudoCount alphabet sources None None |> fst).[0]
+    /// fs:703-707
+    let doSiteSamplingWithPPM motifLength pseudoCount alphabet sources (ppM:PositionMatrix.PositionProbabilityMatrix) =
+        (Native.runChainsWith (Some ppM) 15 1 (seedOf None) motifLength pseudoCount alphabet sources None None |> fst).[0]
+    /// fs:644-661
+    let getMotifsWithBestPWMSOfPPM motifLength pseudoCount alphabet sources (ppM:PositionMatrix.PositionProbabilityMatrix) =
+        (Native.runChainsWith (Some ppM) 1 1 (seedOf None) motifLength pseudoCount alphabet sources None None |> fst).[0]
