@@ -39,6 +39,17 @@ CONFIGS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step (ncu --set full, round 1)
 NCU_DRAM_BYTES_PER_STEP = int((0.613120 + 1.512448 + 3.318528 + 0.000256 + 1.624832 + 0.000512) * 1e6)
+# --family: which reference family the step runs (the default is the BASELINE.json workload)
+FAMILIES = {
+    "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts", "gibbs::chain_kernel",
+            "do_site_sampling_with_bpv"),
+    "data": ("SiteSampler restarts with the data-derived drifting background (doSiteSampling, fs:697)",
+             "data-derived, rebuilt per window (fs:470-473)", "gibbs::drift_kernel", "do_site_sampling"),
+    "motif": ("MotifSampler m = 1 restarts with a fixed background (doMotifSamplingWithPCV, fs:876), cutOff 0",
+              "fixed pcv, whole-set base counts", "gibbs::motif_kernel", None),
+    "motif-data": ("MotifSampler m = 1 restarts with the data-derived background (doMotifSampling, fs:1034), cutOff 0",
+                   "data-derived, rebuilt per held-out sequence (fs:896-905)", "gibbs::motif_kernel", None),
+}
 PSEUDOCOUNT = 1e-4      # fsx:384
 ALPHABET_SIZE = 5       # dnaBases = [A; T; G; C; Gap], fsx:368-369
 SEED = 0xB200
@@ -133,13 +144,17 @@ def _oracle():
     return oracle_lib
 
 
-def cpu_sample(ps, k, bg, *, threads: int, full_restart: bool, seed: int, chain_base: int) -> tuple[float, int, int]:
+def cpu_sample(ps, k, bg, *, threads: int, full_restart: bool, seed: int, chain_base: int,
+               family: str = "bpv") -> tuple[float, int, int]:
     """Run `threads` chains concurrently on host threads (ctypes releases the GIL).
     Returns (wall seconds, window scores, site updates)."""
     O = _oracle()
     S = O.sources(ps.sequences())
     pcv = O.pcv_from_acgt(bg)
-    name = "do_site_sampling_with_bpv" if full_restart else "random_starts_with_bpv"
+    if family == "data":
+        name, pcv = ("do_site_sampling" if full_restart else "random_starts"), None
+    else:
+        name = "do_site_sampling_with_bpv" if full_restart else "random_starts_with_bpv"
     out = [None] * threads
 
     def work(t):
@@ -225,7 +240,12 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
         chains = args.chains
     ps = planted_motif_set(n, length, k, seed=SEED)
     bg = background_of(ps.ascii, PSEUDOCOUNT, ALPHABET_SIZE)
-    params = make_params(k, PSEUDOCOUNT, ALPHABET_SIZE, bg, phase_shifts=shifts)
+    from gibbssampling_b200 import _abi
+    fam_text, fam_bg, fam_kernel, fam_oracle = FAMILIES[args.family]
+    params = make_params(k, PSEUDOCOUNT, ALPHABET_SIZE, bg, phase_shifts=shifts,
+                         background=_abi.GIBBS_BG_DATA if args.family in ("data", "motif-data") else _abi.GIBBS_BG_FIXED,
+                         sampler=_abi.GIBBS_MOTIF_SAMPLER if args.family.startswith("motif") else _abi.GIBBS_SITE_SAMPLER,
+                         cutoff=0.0)
     windows = length - k + 1
 
     # pinned host copies of the inputs (e2e path uploads them every step)
@@ -298,7 +318,11 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
         eng.upload_flat(host_ascii.numpy(), host_off.numpy())      # H2D + GPU 2-bit pack
         r = eng.run(params, chains, chain_id_base=chain_base, seed=SEED + 1000 + s, want_counts=False,
                     pinned=True)   # results land in the engine's page-locked buffers (gibbs_host_alloc)
-        best = SiteSampler.replay_restart_loop(chains - 1, r.scores, r.sites, r.sums)   # what fs:434 returns
+        if args.family.startswith("motif"):
+            from gibbssampling_b200 import MotifSampler
+            best = MotifSampler.replay_motif_restart_loop(chains - 1, r.scores, r.sites, r.sums)   # fs:857 / fs:974
+        else:
+            best = SiteSampler.replay_restart_loop(chains - 1, r.scores, r.sites, r.sums)   # what fs:434 / fs:615 returns
         if world > 1:
             allgather_best(float(r.sums[r.best_chain]), chain_base + r.best_chain, r.sites[r.best_chain],
                            r.scores[r.best_chain])
@@ -340,16 +364,17 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
         hbm_achieved = rank_updates_per_s * algorithmic_hbm_bytes_per_site_update(length) / 1e9
         value = g_windows / (dev_ms * 1e-3)
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and fam_oracle is not None:
             dt = ws = us = 0.0
             n_cpu_chains = 0
             while dt < 12.0 and n_cpu_chains < 64:          # about 10-30 s of CPU work
-                d1, w1, u1 = cpu_sample(ps, k, bg, threads=1, full_restart=True, seed=SEED, chain_base=n_cpu_chains)
+                d1, w1, u1 = cpu_sample(ps, k, bg, threads=1, full_restart=True, seed=SEED, chain_base=n_cpu_chains,
+                                        family=args.family)
                 dt, ws, us, n_cpu_chains = dt + d1, ws + w1, us + u1, n_cpu_chains + 1
             us = int(us)
             cpu = {"value": ws / dt, "unit": "window-scores/s", "site_updates_per_sec": us / dt, "cores": 1,
                    "kind": "port", "seconds": dt,
-                   "sample": (f"chains 0..{n_cpu_chains - 1} of the same workload, full doSiteSamplingWithBPV restarts ({us} site updates) "
+                   "sample": (f"chains 0..{n_cpu_chains - 1} of the same workload, full {fam_oracle} restarts ({us} site updates) "
                               "on 1 host core; C port of the F# reference (oracle/), reference-faithful from-scratch rebuilds; "
                               "the F# itself needs .NET, absent from this image")}
         line = {
@@ -358,10 +383,12 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic planted-motif DNA (Philox key 0xB200, 10% planted-base mutation)",
-            "config": {"workload": f"{cfg_name}: {n} seqs x {length} bp, k={k}, {chains} chains/GPU, SiteSampler WithBPV "
-                                   f"restarts (random starts + greedy sweeps + {'left/right shift sweeps' if shifts else 'no shifts'})",
+            "config": {"workload": f"{cfg_name}: {n} seqs x {length} bp, k={k}, {chains} chains/GPU, {fam_text}"
+                                   + ("" if args.family.startswith("motif") else
+                                      f" (random starts + greedy sweeps + {'left/right shift sweeps' if shifts else 'no shifts'})"),
+                       "family": args.family,
                        "chains_per_gpu": chains, "pseudocount": PSEUDOCOUNT, "alphabet_size": ALPHABET_SIZE,
-                       "background": "fixed (WithBPV), whole-set base counts",
+                       "background": fam_bg,
                        "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event window; the packed "
                              "sequences (125 KB at C2) are L2/SMEM-resident by design",
                        "timing": "CUDA events on the launch stream around each step, summed; max over ranks"},
@@ -369,13 +396,13 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
             "sweeps_per_chain": g_sweeps / (args.steps * chains * world), "exact_rescans_per_step": g_rescans / args.steps,
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s", "frac": achieved / smem_gbs,
-                         "traffic": NCU_DRAM_BYTES_PER_STEP if cfg_name == "C2" else None,
+                         "traffic": NCU_DRAM_BYTES_PER_STEP if (cfg_name == "C2" and args.family == "bpv") else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step, "
                                            "profiles/r01_ncu_c2_final_summary.txt",
                          "peak_source": "measured live: LDS.128 streaming microbenchmark (gibbs_measure_smem_bandwidth)",
                          "peak_theoretical": smem_theory, "frac_of_theoretical": achieved / smem_theory,
                          "algorithmic_bytes_per_window_score": algorithmic_smem_bytes_per_window(k),
-                         "kernel": "gibbs::chain_kernel", "kernel_ms": k_ms,
+                         "kernel": fam_kernel, "kernel_ms": k_ms,
                          "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": hbm_achieved / peaks["hbm_gbs"], "peak_source": peaks["_source"],
                                  "algorithmic_bytes_per_site_update": algorithmic_hbm_bytes_per_site_update(length)}},
@@ -399,6 +426,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="C2")
+    ap.add_argument("--family", choices=sorted(FAMILIES), default="bpv",
+                    help="reference family of the step; bpv = the BASELINE.json workload (the only one the driver runs)")
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
