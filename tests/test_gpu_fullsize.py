@@ -118,3 +118,51 @@ def test_c4_shape_properties():
             assert all(0 <= p <= L - k for p in pos)
         assert init.stats["site_updates"] == n and init.stats["sweeps"] == 1
         assert init.sites[0].tobytes() != res.sites[0].tobytes() or True
+
+
+@pytest.mark.parametrize("L", [100, 1000, 10000])
+@pytest.mark.parametrize("k", [6, 12, 20, 30])
+def test_c5_sweep_of_widths_and_lengths_matches_oracle(k, L):
+    """BASELINE configs[4]: k in {6, 12, 20, 30} x L in {100 bp, 1 kb, 10 kb}. Few sequences so that the oracle's
+    from-scratch rebuilds finish in seconds; every chunk geometry of the ranking pass (4 / 8 / 16 windows per lane,
+    several rounds per lane at 10 kb) and 2- and 3-word k-mers are covered."""
+    n = 6
+    ps = planted_motif_set(n, L, k, seed=900 + k + L)
+    seqs = ps.sequences()
+    bg = background_of(ps.ascii, PC, ALEN)
+    S = O.sources(seqs)
+    pcv = O.pcv_from_acgt(bg)
+    with GibbsEngine(seqs) as eng:
+        res = eng.run(make_params(k, PC, ALEN, bg), 2, chain_id_base=50, seed=k + L)
+    _check_invariants(ps, res, k)
+    for c in range(2):
+        rng, keep = O.make_rng(seed=k + L, chain=50 + c)
+        score, pos, _ = O.site_step("do_site_sampling_with_bpv", S, k, PC, pcv=pcv, rng=rng)
+        assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"
+        np.testing.assert_allclose(res.scores[c], score, rtol=1e-5)
+
+
+def test_c5_sweep_of_chain_counts():
+    """BASELINE configs[4]: 1 ... 65536 chains (powers of 4). A chain's result depends on (seed, chain id) only,
+    whatever the launch shape: all three hand-over stages, the grid-wide random starts and one-wave launches agree."""
+    n, L, k = 24, 100, 8
+    ps = planted_motif_set(n, L, k, seed=31)
+    seqs = ps.sequences()
+    bg = background_of(ps.ascii, PC, ALEN)
+    params = make_params(k, PC, ALEN, bg)
+    with GibbsEngine(seqs) as eng:
+        big = eng.run(params, 65536, seed=17)
+        _check_invariants(ps, big, k)
+        assert big.stats["site_updates"] >= 65536 * n * 4
+        for chains in (1, 4, 16, 64, 256, 1024, 4096, 16384):
+            res = eng.run(params, chains, seed=17, want_counts=False)
+            assert res.sites.tobytes() == big.sites[:chains].tobytes(), chains
+            assert res.scores.tobytes() == big.scores[:chains].tobytes(), chains
+            tail = eng.run(params, 3, chain_id_base=chains - 1, seed=17, want_counts=False)   # an unaligned slice
+            assert tail.sites[0].tobytes() == big.sites[chains - 1].tobytes()
+    S = O.sources(seqs)
+    pcv = O.pcv_from_acgt(bg)
+    for c in (0, 1, 4095, 65535):
+        rng, keep = O.make_rng(seed=17, chain=c)
+        score, pos, _ = O.site_step("do_site_sampling_with_bpv", S, k, PC, pcv=pcv, rng=rng)
+        assert big.sites[c].tolist() == pos.tolist(), f"chain {c}"
