@@ -8,16 +8,18 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgibbs_b200.so")
-SOURCES = [os.path.join(CSRC, "gibbs_api.cu")]
+SOURCES = [os.path.join(CSRC, "gibbs_api.cu"), os.path.join(CSRC, "gibbs_drift_launch.cu")]
 DEPS = SOURCES + [
     os.path.join(CSRC, "gibbs_device.cuh"),
     os.path.join(CSRC, "gibbs_kernels.cuh"),
     os.path.join(CSRC, "gibbs_motif.cuh"),
     os.path.join(CSRC, "gibbs_drift.cuh"),
+    os.path.join(CSRC, "gibbs_drift_dev.cuh"),
     os.path.join(ROOT, "include", "gibbs_b200.h"),
 ]
 
 NVCC_FLAGS = [
+    "--threads", "0",         # the translation units in parallel
     "--split-compile", "0",   # parallel ptxas over the template instantiations
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",

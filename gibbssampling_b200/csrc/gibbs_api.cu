@@ -17,6 +17,10 @@
 #include <new>
 #include <vector>
 
+namespace gibbs { // gibbs_drift_launch.cu
+cudaError_t launch_drift_team(int team, const ChainArgs &a, int grid, int smem, cudaStream_t stream);
+}
+
 using namespace gibbs;
 
 namespace {
@@ -214,7 +218,7 @@ int32_t launch_team(gibbs_handle *h, const ChainArgs &a, int grid) {
 }
 
 template <int KPV>
-int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
+int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
     h->run_extra_launches = 0;
     const char *init_env = getenv("GIBBS_B200_INIT_KERNEL"); // measurement switch: "0" keeps the random starts in the chain kernel
     // Random starts are N independent site updates of N-1 draws each. With many chains of few sequences the
@@ -222,7 +226,7 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
     // many sequences the grid-wide kernel is the only way to use all SMs (C4, 8 chains: 17.2 s -> 0.61 s).
     const bool init_wide = init_env ? init_env[0] != '0' : (a.n_chains < 4 * h->sm_count || a.s.n >= 4096);
     const bool masked = a.s.mask != nullptr; // symbols outside A,C,G,T: one launch of the MASKED instantiation (1 or 4 warps)
-    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide && !masked) {
+    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide && !masked && !drift) {
         const int smem = init_smem_bytes(a.s.row_words);
         if (smem <= 200 * 1024) {
             int32_t rc = set_smem(init_kernel<KPV>, smem);
@@ -248,6 +252,20 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
     int n_stages = 0;
     if (masked) {
         stages[n_stages++] = {team_smem_bytes(a.s.row_words, 4) <= 200 * 1024 ? 4 : 1, 0};
+    } else if (drift) { // data-derived background: 4 warps per chain (4 chains per SM), the last 2 per SM continue with 8
+        const int forced = h->team_warps == 16 ? 8 : h->team_warps;
+        if (forced != 0) {
+            stages[n_stages++] = {forced, 0};
+        } else {
+            int first = a.n_chains > 2 * sms ? 4 : 8;
+            if (first == 8 && !fits(8)) first = 4;
+            if (first == 4 && !fits(4)) first = 1;
+            stages[n_stages++] = {first, 0};
+            if (first == 4 && fits(8)) {
+                stages[n_stages - 1].pause_below = 2 * sms;
+                stages[n_stages++] = {8, 0};
+            }
+        }
     } else if (h->team_warps != 0) {
         stages[n_stages++] = {h->team_warps, 0};
     } else {
@@ -291,6 +309,13 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
             if (rc) return rc;
             continue;
         }
+        if (drift) { // instantiated in gibbs_drift_launch.cu
+            const int smem = team_smem_bytes(b.s.row_words, stages[st].team);
+            if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for %d warps per chain", stages[st].team);
+            CUDA_TRY(launch_drift_team(stages[st].team, b, grid, smem, h->stream));
+            if (st > 0) h->run_extra_launches += 1;
+            continue;
+        }
         switch (stages[st].team) {
         case 16: rc = launch_team<KPV, 16>(h, b, grid); break;
         case 8: rc = launch_team<KPV, 8>(h, b, grid); break;
@@ -303,10 +328,10 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a) {
     return GIBBS_OK;
 }
 
-int32_t launch_chain(gibbs_handle *h, const ChainArgs &a) {
+int32_t launch_chain(gibbs_handle *h, const ChainArgs &a, bool drift = false) {
     const int kp = (a.k + 1) / 2;
     switch (kp) {
-#define X(KPV) case KPV: return launch_chain_kp<KPV>(h, a);
+#define X(KPV) case KPV: return launch_chain_kp<KPV>(h, a, drift);
         KP_CASES(X)
 #undef X
     default: return fail(GIBBS_ERR_ARG, "unsupported k");
@@ -934,9 +959,21 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             a.fast_ok = d.fast_ok;
         }
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        rc = launch_drift(h, d);
-        if (rc) return rc;
-        h->run_team = 1;
+        if (getenv("GIBBS_B200_DRIFT_KERNEL")) { // measurement switch: the single-warp kernel this path started as
+            rc = launch_drift(h, d);
+            if (rc) return rc;
+            h->run_team = 1;
+        } else { // teams of warps, speculative rounds and the hand-over of chain_kernel, with the drifting-background scan
+            a.pvals = d.pvals;
+            a.basecnt = d.basecnt;
+            memcpy(a.gcnt, d.gcnt, sizeof a.gcnt);
+            a.alpha_pc = d.alpha_pc;
+            a.pc = d.pc;
+            a.drift_fast_ok = d.fast_ok;
+            rc = launch_chain(h, a, true);
+            if (rc) return rc;
+            launches += h->run_extra_launches;
+        }
     } else {
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_chain(h, a);

@@ -75,6 +75,13 @@ struct ChainArgs {
     // ([k][4], rows A,C,G,T of the reference's 49 x k matrix) instead of the PPM of the random sites; the random sites
     // then only shape the background. Null = the usual random starts. Data-derived background only.
     const double *ppm_given;
+    // data-derived background (chain_kernel<.., DRIFT = true>, fs:462-640): normalizePPM value of a count
+    // (c + pc) / ((N-1) + |A| pc) (fs:260), base counts per sequence and of the whole set, |A| pc (fs:117)
+    const double *pvals;      // [n]
+    const int32_t *basecnt;   // [n][4]
+    int32_t gcnt[4];
+    double alpha_pc, pc;
+    int32_t drift_fast_ok;    // the float32 ranking pass may be used
     // pause / resume at sweep boundaries: once few chains are still running they are continued by a
     // second launch with wider teams (see launch_chain_kp)
     int32_t *active;          // chains not finished yet
@@ -300,7 +307,7 @@ __device__ __forceinline__ int shifted_site(int pos, int len, int k, int mode) {
 __device__ __forceinline__ bool row_masked(const DeviceSeqs &s, int i) { return s.mask != nullptr && __ldg(s.rowflag + i) != 0; }
 
 // 2 bits per column of the k-mer at `pos` of sequence i: 0b11 where the base is not A,C,G,T
-__device__ __noinline__ uint64_t mask_kmer(const uint32_t *__restrict__ mask, int row_words, int i, int pos, int k) {
+static __device__ __noinline__ uint64_t mask_kmer(const uint32_t *__restrict__ mask, int row_words, int i, int pos, int k) {
     const uint32_t *p = mask + (size_t)i * row_words + (pos >> 4);
     const int sh = (pos & 15) * 2;
     const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
@@ -310,7 +317,7 @@ __device__ __noinline__ uint64_t mask_kmer(const uint32_t *__restrict__ mask, in
 
 // The histogram counted every masked base of this k-mer as code 0 (A): note the columns in fix[] so the
 // caller can take them out again. The reference counts such a base in its own (dead) row, fs:211-215.
-__device__ __noinline__ void hist_fix(const uint32_t *__restrict__ mask, int row_words, int i, int pos, int k, int32_t *fix) {
+static __device__ __noinline__ void hist_fix(const uint32_t *__restrict__ mask, int row_words, int i, int pos, int k, int32_t *fix) {
     uint64_t m = mask_kmer(mask, row_words, i, pos, k);
     while (m) {
         const int j = (__ffsll((long long)m) - 1) >> 1;

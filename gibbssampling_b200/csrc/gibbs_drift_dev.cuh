@@ -1,0 +1,280 @@
+// gibbssampling_b200/csrc/gibbs_drift_dev.cuh -- device routines of the data-derived (drifting) background
+// (getBestPWMSs fs:462-479): the all-windows float64 scan and the float32 ranking pass with exact re-scoring.
+// Used by chain_kernel<.., DRIFT = true> (SiteSampler), by the single-warp drift_kernel and by motif_kernel.
+#pragma once
+#include "gibbs_device.cuh"
+
+namespace gibbs {
+
+__device__ __forceinline__ int base_at(const uint32_t *row, int pos) { return (row[pos >> 4] >> ((pos & 15) * 2)) & 3; }
+
+// getBestPWMSs (fs:462-479) for the staged row. ppm = smem [k][4] float64 PPM of the leave-one-out counts.
+// f0[b] = fused background counts of the others; cn[b] = base counts of this sequence.
+__device__ __forceinline__ void scan_drifting(const uint32_t *row, int W, int k, const double *ppm, const int *f0,
+                                              const int *cn, double pc, double alpha_pc, int lane, double &hv_out,
+                                              int &w_out) {
+    const int B = (W + 31) >> 5;
+    const int w_begin = min(W, lane * B), w_end = min(W, w_begin + B);
+    // pass A: occurrences summed over this lane's windows (sliding counts, 4 byte fields: k <= 32)
+    int blocksum[4] = {0, 0, 0, 0};
+    if (w_begin < w_end) {
+        uint32_t occ = 0;
+        for (int j = 0; j < k; ++j) occ += 1u << (8 * base_at(row, w_begin + j));
+        for (int w = w_begin; w < w_end; ++w) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) blocksum[b] += (int)((occ >> (8 * b)) & 255u);
+            if (w + 1 < w_end) {
+                occ -= 1u << (8 * base_at(row, w));
+                occ += 1u << (8 * base_at(row, w + k));
+            }
+        }
+    }
+    // exclusive prefix over lanes
+    int before[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int v = blocksum[b];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += t;
+        }
+        before[b] = v - blocksum[b];
+    }
+    // pass B: every window exactly
+    double hv = 0.0;
+    int hw = 0;
+    if (w_begin < w_end) {
+        int run[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) run[b] = before[b];
+        uint32_t oc = 0;
+        for (int j = 0; j < k; ++j) oc += 1u << (8 * base_at(row, w_begin + j));
+        for (int w = w_begin; w < w_end; ++w) {
+            int F[4], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                run[b] += (int)((oc >> (8 * b)) & 255u);
+                F[b] = f0[b] + (w + 1) * cn[b] - run[b];
+                sum += F[b];
+            }
+            const double den = __dadd_rn((double)sum, alpha_pc);                       // fs:117
+            double pcv[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) pcv[b] = __ddiv_rn(__dadd_rn((double)F[b], pc), den); // fs:119
+            double v = 1.0;
+            for (int j = 0; j < k; ++j) {
+                const int b = base_at(row, w + j);
+                const double q = b == 0 ? pcv[0] : b == 1 ? pcv[1] : b == 2 ? pcv[2] : pcv[3];
+                v = __dmul_rn(v, __ddiv_rn(ppm[j * 4 + b], q));                           // fs:286, fs:292
+            }
+            if (v > hv) {
+                hv = v;
+                hw = w;
+            }
+            if (w + 1 < w_end) {
+                oc -= 1u << (8 * base_at(row, w));
+                oc += 1u << (8 * base_at(row, w + k));
+            }
+        }
+    }
+    warp_argmax(hv, hw);
+    hv_out = hv;
+    w_out = hw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ranking pass for the drifting background
+// ------------------------------------------------------------------------------------------------
+// log2 score(w) = sum_j log2 ppm[j][b_j] - sum_b occ_w[b] log2(F_w[b] + pc) + k log2(den_w): the first sum comes from
+// a float32 pair table (two bases per lookup), the rest from 5 MUFU.LG2 per window. The float32 value is within
+// ~1.2e-3 of the true log2 score (k <= 32: table entries and MUFU.LG2 are good to 2 ulp of values < 32, sums stay below
+// 1024 where a float32 ulp is 6.1e-5), so the float64 argmax lies among the windows within DRIFT_MARGIN of the float32
+// maximum. Those windows (at most one per lane, else the exact scan runs) are re-scored exactly as scan_drifting does.
+constexpr float DRIFT_MARGIN = 0.03125f;
+
+// float32 log2 of the PPM in pair-table form: pt[p*16 + nib] = lg[2p][nib & 3] + lg[2p+1][nib >> 2]
+template <int KP>
+__device__ __forceinline__ void drift_pair_table(const double *ppm, float *lg, float *pt, int k, int lane) {
+    for (int e = lane; e < 8 * KP; e += 32) lg[e] = (e < 4 * k) ? __log2f((float)ppm[e]) : 0.0f;
+    __syncwarp();
+    for (int idx = lane; idx < 16 * KP; idx += 32) {
+        const int p = idx >> 4, nib = idx & 15;
+        pt[idx] = lg[(2 * p) * 4 + (nib & 3)] + lg[(2 * p + 1) * 4 + (nib >> 2)];
+    }
+    __syncwarp();
+}
+
+// one window exactly, the body of scan_drifting's pass B (fs:471-474, fs:290-293)
+__device__ __forceinline__ double drift_exact_window(const uint32_t *row, int w, int k, const double *ppm, const int *f0,
+                                                     const int *cn, const int *run, double pc, double alpha_pc) {
+    int F[4], sum = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        F[b] = f0[b] + (w + 1) * cn[b] - run[b];
+        sum += F[b];
+    }
+    const double den = __dadd_rn((double)sum, alpha_pc);
+    double pcv[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) pcv[b] = __ddiv_rn(__dadd_rn((double)F[b], pc), den);
+    double v = 1.0;
+    for (int j = 0; j < k; ++j) {
+        const int b = base_at(row, w + j);
+        const double q = b == 0 ? pcv[0] : b == 1 ? pcv[1] : b == 2 ? pcv[2] : pcv[3];
+        v = __dmul_rn(v, __ddiv_rn(ppm[j * 4 + b], q));
+    }
+    return v;
+}
+
+// Returns false when the exact scan has to run instead (a lane with two windows inside the margin).
+template <int KP>
+__device__ __forceinline__ bool scan_drifting_fast(const uint32_t *row, int W, int k, const double *ppm, const float *pt,
+                                                   const int *f0, const int *cn, double pc, double alpha_pc, int lane,
+                                                   double &hv_out, int &w_out) {
+    const int B = (W + 31) >> 5;
+    const int w_begin = min(W, lane * B), w_end = min(W, w_begin + B);
+    int blocksum[4] = {0, 0, 0, 0};
+    if (w_begin < w_end) { // occurrences summed over this lane's windows (as scan_drifting's pass A)
+        uint32_t occ = 0;
+        for (int j = 0; j < k; ++j) occ += 1u << (8 * base_at(row, w_begin + j));
+        for (int w = w_begin; w < w_end; ++w) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) blocksum[b] += (int)((occ >> (8 * b)) & 255u);
+            if (w + 1 < w_end) {
+                occ -= 1u << (8 * base_at(row, w));
+                occ += 1u << (8 * base_at(row, w + k));
+            }
+        }
+    }
+    int run[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int v = blocksum[b];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += t;
+        }
+        run[b] = v - blocksum[b];
+    }
+    const float ninf = __int_as_float(0xff800000);
+    float M1 = ninf, M2 = ninf;
+    int w1 = 0, run1[4] = {0, 0, 0, 0};
+    if (w_begin < w_end) {
+        const float pcf = (float)pc, apcf = (float)alpha_pc, kf = (float)k;
+        uint32_t oc = 0;
+        for (int j = 0; j < k; ++j) oc += 1u << (8 * base_at(row, w_begin + j));
+        for (int w = w_begin; w < w_end; ++w) {
+            float bg = 0.0f;
+            int sum = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int ob = (int)((oc >> (8 * b)) & 255u);
+                run[b] += ob;
+                const int F = f0[b] + (w + 1) * cn[b] - run[b];
+                sum += F;
+                bg = fmaf((float)ob, __log2f((float)F + pcf), bg);
+            }
+            bg = fmaf(-kf, __log2f((float)sum + apcf), bg);
+            const uint64_t kmer = kmer_shared<KP>(row, w);
+            float mot = 0.0f;
+#pragma unroll
+            for (int p = 0; p < KP; ++p) mot += pt[p * 16 + ((uint32_t)(kmer >> (4 * p)) & 15u)];
+            const float a = mot - bg;
+            if (a > M1) {
+                M2 = M1;
+                M1 = a;
+                w1 = w;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) run1[b] = run[b];
+            } else if (a > M2) {
+                M2 = a;
+            }
+            if (w + 1 < w_end) {
+                oc -= 1u << (8 * base_at(row, w));
+                oc += 1u << (8 * base_at(row, w + k));
+            }
+        }
+    }
+    float M = M1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) M = fmaxf(M, __shfl_xor_sync(FULL, M, o));
+    const float thr = M - DRIFT_MARGIN;
+    if (__ballot_sync(FULL, M2 >= thr)) return false;
+    // Candidates (normally one) are re-scored by the whole warp with the reference's own operations: lanes 0-3 divide
+    // out the four background probabilities, lane j divides column j's ratio, and the product is taken left to right
+    // (fs:290-293) with one shuffle + multiply per column -- 2 dependent divisions instead of k + 4.
+    unsigned cand = __ballot_sync(FULL, M1 >= thr);
+    double hv = 0.0;
+    int hw = INT32_MAX;
+    while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int wc = __shfl_sync(FULL, w1, src);
+        int F[4], sum = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            F[b] = f0[b] + (wc + 1) * cn[b] - __shfl_sync(FULL, run1[b], src);
+            sum += F[b];
+        }
+        const double den = __dadd_rn((double)sum, alpha_pc);                       // fs:117
+        const int fb = lane == 0 ? F[0] : lane == 1 ? F[1] : lane == 2 ? F[2] : F[3];
+        const double q_lane = __ddiv_rn(__dadd_rn((double)fb, pc), den);             // fs:119, lanes 0-3 hold pcv[A,C,G,T]
+        const int b = lane < k ? base_at(row, wc + lane) : 0;
+        const double q = __shfl_sync(FULL, q_lane, b);
+        const double ratio = lane < k ? __ddiv_rn(ppm[lane * 4 + b], q) : 1.0;       // fs:286
+        double v = 1.0;
+        for (int j = 0; j < k; ++j) v = __dmul_rn(v, __shfl_sync(FULL, ratio, j));   // fs:292
+        if (better(v, wc, hv, hw)) { // largest product, lowest window on ties = the first strict maximum of fs:476
+            hv = v;
+            hw = wc;
+        }
+    }
+    hv_out = hv;
+    w_out = hw;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one site update with the drifting background, the pieces chain_kernel<.., DRIFT = true> calls
+// ------------------------------------------------------------------------------------------------
+// PPM of the leave-one-out counts (createPPMOf + normalizePPM, fs:573-575) into W.wcol, the counts themselves into
+// W.lgcol; f0 = fused createFCVWithout of the other sequences (fs:565-568: their bases outside their sites),
+// cn = base counts of the held-out sequence; the float32 pair table when the ranking pass is allowed.
+// counts = W.counts (random starts) or the all-sites total; use_given = the caller-supplied PPM of fs:644-661.
+template <int KP>
+__device__ __forceinline__ void drift_tables(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
+                                             const ChainArgs &a, bool use_given, bool fast, int n, int lane, int (&f0)[4],
+                                             int (&cn)[4]) {
+    for (int e = lane; e < 4 * k; e += 32) {
+        int c = counts[e];
+        if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3)) c -= 1;
+        W.wcol[e] = use_given ? __ldg(a.ppm_given + e) : __ldg(a.pvals + c);
+        W.lgcol[e] = c;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int s = 0;
+        for (int j = lane; j < k; j += 32) s += W.lgcol[j * 4 + b];
+        cn[b] = __ldg(a.basecnt + n * 4 + b);
+        f0[b] = (a.gcnt[b] - cn[b]) - __reduce_add_sync(FULL, s);
+    }
+    // (W.counts was consumed above: its space holds the float32 log table)
+    if (fast) drift_pair_table<KP>(W.wcol, reinterpret_cast<float *>(W.counts), reinterpret_cast<float *>(W.ptab), k, lane);
+}
+
+// getBestPWMSs (fs:462-479) for the staged row; returns true when every window was scored in float64
+template <int KP>
+__device__ __forceinline__ bool drift_pick(const WarpTables &W, const uint32_t *row, int Wn, int k, const ChainArgs &a, bool fast,
+                                           const int (&f0)[4], const int (&cn)[4], int lane, double &p, int &w) {
+    bool ranked = false;
+    if (fast)
+        ranked = scan_drifting_fast<KP>(row, Wn, k, W.wcol, reinterpret_cast<const float *>(W.ptab), f0, cn, a.pc, a.alpha_pc,
+                                        lane, p, w);
+    if (!ranked) scan_drifting(row, Wn, k, W.wcol, f0, cn, a.pc, a.alpha_pc, lane, p, w);
+    return !ranked;
+}
+
+} // namespace gibbs

@@ -1,6 +1,7 @@
 // gibbssampling_b200/csrc/gibbs_kernels.cuh -- __global__ kernels (sm_100a only).
 #pragma once
 #include "gibbs_device.cuh"
+#include "gibbs_drift_dev.cuh"
 
 namespace gibbs {
 
@@ -20,7 +21,7 @@ __device__ __forceinline__ int next_phase(int from, int mask) {
 // flags[0] = 1 + a byte outside '*'..'Z' (the reference's 49-slot tables cannot index it: IndexOutOfRange, fs:17-20)
 // flags[1] = number of symbols inside that range but outside A,C,G,T (mask plane 0b11, code 0)
 // flags[2] = 1 if one of them is Gap '-' (a member of the script's alphabet, fsx:368-369)
-__global__ void pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off, int n, int row_words,
+static __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off, int n, int row_words,
                             uint32_t *__restrict__ packed, uint32_t *__restrict__ mask, int32_t *__restrict__ rowflag,
                             int32_t *__restrict__ len_out, int *flags) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,7 +63,7 @@ __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__
 
 // W(c, b) = ((c + pc) / den) / q[b]   (normalizePPM fs:260, createPositionWeightMatrix fs:286)
 // plus its fixed-point log2. range[0] = min lg, range[1] = max lg, range[2] = any non-normal W.
-__global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, double q2, double q3, WEnt *wtab,
+static __global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, double q2, double q3, WEnt *wtab,
                             int *range) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * 4) return;
@@ -199,7 +200,7 @@ __host__ __device__ inline int init_smem_bytes(int row_words) {
 }
 
 template <int KP>
-__global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_kernel(const ChainArgs a) {
+static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.s.n, k = a.k, row_words = a.s.row_words;
@@ -282,8 +283,11 @@ __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_k
 //     therefore exactly the reference's sequential sweep.
 // MASKED = the set holds symbols outside A,C,G,T (a.s.mask != null): a separate instantiation (4 warps only), because
 // the 4-warp kernel sits at its register limit and even never-taken branches cost the ACGT path 2-3 %.
-template <int KP, int T, bool MASKED = false>
-__global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T4_MIN_BLOCKS : T == 8 ? 3 : 1)) chain_kernel(const ChainArgs a) {
+// DRIFT = the data-derived background of doSiteSampling (fs:697): same sweeps, rounds and hand-over; the site update
+// builds the PPM instead of the odds table and scans with the per-window background (gibbs_drift_dev.cuh). Same launch
+// bounds (measured on C2: 7 CTAs of 4 warps at 72 registers 166 ms, 6 at 80 178 ms, 4 at 118 registers 185-193 ms).
+template <int KP, int T, bool MASKED = false, bool DRIFT = false>
+static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T4_MIN_BLOCKS : T == 8 ? 3 : 1)) chain_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
@@ -368,21 +372,38 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T4_MIN_B
                 Wn = len_n - k + 1;
                 double hv_n = 0.0;
                 if (MASKED) masked_n = __ldg(a.s.rowflag + n) != 0 ? n : -1; // the held-out sequence holds symbols outside A,C,G,T
-                if (phase == PH_INIT) {
-                    random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
-                    build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+                bool slow;
+                if constexpr (DRIFT) {
+                    int f0[4], cn[4];
+                    const bool given = phase == PH_INIT && a.ppm_given != nullptr;
+                    const bool fast = a.drift_fast_ok && !given; // (a supplied PPM may hold zeros or denormals: exact scan)
+                    if (phase == PH_INIT) {
+                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, false>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                        drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
+                    } else {
+                        site_n = S.blk_site[o];
+                        hv_n = S.blk_hv[o];
+                        own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
+                        drift_tables<KP>(WT, S.total, true, own, k, a, false, fast, n, lane, f0, cn);
+                    }
+                    slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w);
                 } else {
-                    site_n = S.blk_site[o];
-                    hv_n = S.blk_hv[o];
-                    own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
-                    if (MASKED && masked_n >= 0) // rare: the own site may cover symbols outside A,C,G,T
-                        build_tables_masked<KP>(WT, S.total, own, k, a.wtab, lane,
-                                                mask_kmer(a.s.mask, a.s.row_words, n, shifted_site(site_n, len_n, k, mode), k));
-                    else
-                        build_tables<KP>(WT, S.total, true, own, k, a.wtab, lane);
+                    if (phase == PH_INIT) {
+                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                        build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+                    } else {
+                        site_n = S.blk_site[o];
+                        hv_n = S.blk_hv[o];
+                        own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
+                        if (MASKED && masked_n >= 0) // rare: the own site may cover symbols outside A,C,G,T
+                            build_tables_masked<KP>(WT, S.total, own, k, a.wtab, lane,
+                                                    mask_kmer(a.s.mask, a.s.row_words, n, shifted_site(site_n, len_n, k, mode), k));
+                        else
+                            build_tables<KP>(WT, S.total, true, own, k, a.wtab, lane);
+                    }
+                    slow = MASKED ? pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w, &a.s, masked_n)
+                                  : pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
                 }
-                const bool slow = MASKED ? pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w, &a.s, masked_n)
-                                         : pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
                 bool accept = true, moved = false;
                 if (phase != PH_INIT) {
                     accept = score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0); // fs:402
@@ -522,7 +543,7 @@ struct PrimArgs {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
+static __global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
@@ -534,7 +555,7 @@ __global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
 
 // mode 0: every window in float64 (raw product and log2); mode 1: argmax pick
 template <int KP>
-__global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
+static __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
@@ -571,7 +592,7 @@ __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
 
 // counts of all N sites of one chain (PWM counts reported with the best chain)
 template <int KP>
-__global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int32_t *sites, int k, int32_t *counts_out) {
+static __global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int32_t *sites, int k, int32_t *counts_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
@@ -582,7 +603,7 @@ __global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int3
 }
 
 // first chain with the largest sum (strict >), the restart selection of fs:450 / fs:156-170
-__global__ void best_chain_kernel(const double *sums, int n_chains, int *best_out) {
+static __global__ void best_chain_kernel(const double *sums, int n_chains, int *best_out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int best = 0;
         double bs = sums[0];
@@ -599,7 +620,7 @@ __global__ void best_chain_kernel(const double *sums, int n_chains, int *best_ou
 // shared-memory streaming microbenchmark: the measured denominator of the smem roofline
 // ------------------------------------------------------------------------------------------------
 // 1024 threads x LDS.128, conflict-free, 8 loads per round: bytes = grid * 1024 * 16 * 8 * iters
-__global__ void __launch_bounds__(1024) smem_stream_kernel(int iters, unsigned int *sink) {
+static __global__ void __launch_bounds__(1024) smem_stream_kernel(int iters, unsigned int *sink) {
     __shared__ uint4 buf[2048];
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = make_uint4(i, i * 3, i * 5, i * 7);
     __syncthreads();
