@@ -17,8 +17,18 @@
 #include <new>
 #include <vector>
 
-namespace gibbs { // gibbs_drift_launch.cu
-cudaError_t launch_drift_team(int team, const ChainArgs &a, int grid, int smem, cudaStream_t stream);
+namespace gibbs { // gibbs_chain_tu.cu, one translation unit per group of chain_kernel instantiations (_build.py)
+#define GIBBS_CHAIN_TU(name) cudaError_t name(const ChainArgs &a, int grid, int smem, cudaStream_t stream)
+GIBBS_CHAIN_TU(launch_chain_t1);
+GIBBS_CHAIN_TU(launch_chain_t4);
+GIBBS_CHAIN_TU(launch_chain_t8);
+GIBBS_CHAIN_TU(launch_chain_t16);
+GIBBS_CHAIN_TU(launch_chain_masked_t1);
+GIBBS_CHAIN_TU(launch_chain_masked_t4);
+GIBBS_CHAIN_TU(launch_chain_drift_t1);
+GIBBS_CHAIN_TU(launch_chain_drift_t4);
+GIBBS_CHAIN_TU(launch_chain_drift_t8);
+#undef GIBBS_CHAIN_TU
 }
 
 using namespace gibbs;
@@ -206,14 +216,20 @@ int32_t set_smem(K kernel, int bytes) {
 // shortens every chain's critical path (measured faster than one warp per chain both when all chains
 // are resident at once -- C2 -- and when they run in several waves); one warp is kept for sets with
 // fewer than 4 sequences or rows too long for four sets of staging buffers.
-template <int KPV, int TV, bool MASKED = false>
-int32_t launch_team(gibbs_handle *h, const ChainArgs &a, int grid) {
-    const int smem = team_smem_bytes(a.s.row_words, TV);
-    if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for %d warps per chain", TV);
-    int32_t rc = set_smem(chain_kernel<KPV, TV, MASKED>, smem);
-    if (rc) return rc;
-    chain_kernel<KPV, TV, MASKED><<<grid, 32 * TV, smem, h->stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
+// one stage of a run: the chain_kernel group for (warps per chain, masked symbols, drifting background)
+int32_t launch_team(gibbs_handle *h, int team, bool masked, bool drift, const ChainArgs &a, int grid) {
+    const int smem = team_smem_bytes(a.s.row_words, team);
+    if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for %d warps per chain", team);
+    cudaError_t e = cudaErrorInvalidValue;
+    if (masked) e = team == 4 ? launch_chain_masked_t4(a, grid, smem, h->stream) : launch_chain_masked_t1(a, grid, smem, h->stream);
+    else if (drift)
+        e = team == 8 ? launch_chain_drift_t8(a, grid, smem, h->stream)
+            : team == 4 ? launch_chain_drift_t4(a, grid, smem, h->stream) : launch_chain_drift_t1(a, grid, smem, h->stream);
+    else
+        e = team == 16 ? launch_chain_t16(a, grid, smem, h->stream)
+            : team == 8 ? launch_chain_t8(a, grid, smem, h->stream)
+            : team == 4 ? launch_chain_t4(a, grid, smem, h->stream) : launch_chain_t1(a, grid, smem, h->stream);
+    CUDA_TRY(e);
     return GIBBS_OK;
 }
 
@@ -303,25 +319,7 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
         b.pending_out = st + 1 < n_stages ? h->pending.p + (size_t)st * a.n_chains : nullptr;
         b.pending_out_n = st + 1 < n_stages ? h->ctl.p + st + 1 : nullptr;
         const int grid = st == 0 ? a.n_chains : stages[st - 1].pause_below; // at most that many chains were paused
-        int32_t rc;
-        if (masked) {
-            rc = stages[st].team == 4 ? launch_team<KPV, 4, true>(h, b, grid) : launch_team<KPV, 1, true>(h, b, grid);
-            if (rc) return rc;
-            continue;
-        }
-        if (drift) { // instantiated in gibbs_drift_launch.cu
-            const int smem = team_smem_bytes(b.s.row_words, stages[st].team);
-            if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for %d warps per chain", stages[st].team);
-            CUDA_TRY(launch_drift_team(stages[st].team, b, grid, smem, h->stream));
-            if (st > 0) h->run_extra_launches += 1;
-            continue;
-        }
-        switch (stages[st].team) {
-        case 16: rc = launch_team<KPV, 16>(h, b, grid); break;
-        case 8: rc = launch_team<KPV, 8>(h, b, grid); break;
-        case 4: rc = launch_team<KPV, 4>(h, b, grid); break;
-        default: rc = launch_team<KPV, 1>(h, b, grid); break;
-        }
+        int32_t rc = launch_team(h, stages[st].team, masked, drift, b, grid);
         if (rc) return rc;
         if (st > 0) h->run_extra_launches += 1;
     }
@@ -440,25 +438,6 @@ int32_t ensure_drift(gibbs_handle *h, const gibbs_params *p, int *launches) {
     h->drift_pc = p->pseudocount;
     h->drift_alen = p->alphabet_size;
     h->drift_valid = true;
-    return GIBBS_OK;
-}
-
-int32_t launch_drift(gibbs_handle *h, const DriftArgs &d) {
-    const int kp = (d.c.k + 1) / 2;
-    const int smem = team_smem_bytes(d.c.s.row_words, 1);
-    switch (kp) {
-#define X(KPV)                                                                          \
-    case KPV: {                                                                         \
-        int32_t rc = set_smem(drift_kernel<KPV>, smem);                                 \
-        if (rc) return rc;                                                              \
-        drift_kernel<KPV><<<d.c.n_chains, 32, smem, h->stream>>>(d);                    \
-        break;                                                                          \
-    }
-        KP_CASES(X)
-#undef X
-    default: return fail(GIBBS_ERR_ARG, "unsupported k");
-    }
-    CUDA_TRY(cudaGetLastError());
     return GIBBS_OK;
 }
 
@@ -942,38 +921,25 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         if (rc) return rc;
         h->run_team = 1;
     } else if (p->background == GIBBS_BG_DATA) {
-        DriftArgs d{};
-        d.c = a;
-        d.pvals = h->pvals.p;
-        d.basecnt = h->basecnt.p;
-        memcpy(d.gcnt, h->gcnt, sizeof d.gcnt);
-        d.alpha_pc = (double)p->alphabet_size * p->pseudocount; // float alphabet.Length * pseudoCount, fs:117
-        d.pc = p->pseudocount;
+        // teams of warps, speculative rounds and the hand-over of chain_kernel, with the drifting-background scan
+        a.pvals = h->pvals.p;
+        a.basecnt = h->basecnt.p;
+        memcpy(a.gcnt, h->gcnt, sizeof a.gcnt);
+        a.alpha_pc = (double)p->alphabet_size * p->pseudocount; // float alphabet.Length * pseudoCount, fs:117
+        a.pc = p->pseudocount;
         {   // Ranking pass allowed? Every odds ratio ppm / pcv lies in [pc / den, den / pc] with den <= all bases of the
             // set + one more sequence + |A| pc (or N - 1 + |A| pc): no float64 product of k of them may leave the
             // normal range (|log2| < 1000), and pc > 0 keeps every logarithm finite.
             const double bases = (double)h->gcnt[0] + h->gcnt[1] + h->gcnt[2] + h->gcnt[3] + (double)h->max_len;
-            const double den = (bases > (double)h->n ? bases : (double)h->n) + d.alpha_pc;
-            d.fast_ok = (p->pseudocount > 0.0 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
-            if (getenv("GIBBS_B200_DRIFT_EXACT")) d.fast_ok = 0; // measurement / test switch: every window in float64
-            a.fast_ok = d.fast_ok;
+            const double den = (bases > (double)h->n ? bases : (double)h->n) + a.alpha_pc;
+            a.drift_fast_ok = (p->pseudocount > 0.0 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
+            if (getenv("GIBBS_B200_DRIFT_EXACT")) a.drift_fast_ok = 0; // measurement / test switch: every window in float64
+            a.fast_ok = a.drift_fast_ok;
         }
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        if (getenv("GIBBS_B200_DRIFT_KERNEL")) { // measurement switch: the single-warp kernel this path started as
-            rc = launch_drift(h, d);
-            if (rc) return rc;
-            h->run_team = 1;
-        } else { // teams of warps, speculative rounds and the hand-over of chain_kernel, with the drifting-background scan
-            a.pvals = d.pvals;
-            a.basecnt = d.basecnt;
-            memcpy(a.gcnt, d.gcnt, sizeof a.gcnt);
-            a.alpha_pc = d.alpha_pc;
-            a.pc = d.pc;
-            a.drift_fast_ok = d.fast_ok;
-            rc = launch_chain(h, a, true);
-            if (rc) return rc;
-            launches += h->run_extra_launches;
-        }
+        rc = launch_chain(h, a, true);
+        if (rc) return rc;
+        launches += h->run_extra_launches;
     } else {
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_chain(h, a);

@@ -1,6 +1,6 @@
 // gibbssampling_b200/csrc/gibbs_drift_dev.cuh -- device routines of the data-derived (drifting) background
 // (getBestPWMSs fs:462-479): the all-windows float64 scan and the float32 ranking pass with exact re-scoring.
-// Used by chain_kernel<.., DRIFT = true> (SiteSampler), by the single-warp drift_kernel and by motif_kernel.
+// Used by chain_kernel<.., DRIFT = true> (SiteSampler, gibbs_drift_launch.cu) and by motif_kernel (random starts).
 #pragma once
 #include "gibbs_device.cuh"
 

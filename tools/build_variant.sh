@@ -1,4 +1,9 @@
 #!/bin/bash
-# usage: build_variant.sh <name> <-D flags...>   -> variants/lib_<name>.so
+# usage: build_variant.sh <name> <-D flags...>   -> variants/lib_<name>.so (select it with GIBBS_B200_LIB=...)
 name=$1; shift
-nvcc --split-compile 0 -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared -cudart static "$@" -o variants/lib_$name.so gibbssampling_b200/csrc/gibbs_api.cu gibbssampling_b200/csrc/gibbs_drift_launch.cu
+mkdir -p variants
+python - "$name" "$@" <<'PY'
+import sys
+from gibbssampling_b200 import _build
+print(_build.build(out=f"variants/lib_{sys.argv[1]}.so", extra_flags=sys.argv[2:]))
+PY
