@@ -929,10 +929,10 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         a.pc = p->pseudocount;
         {   // Ranking pass allowed? Every odds ratio ppm / pcv lies in [pc / den, den / pc] with den <= all bases of the
             // set + one more sequence + |A| pc (or N - 1 + |A| pc): no float64 product of k of them may leave the
-            // normal range (|log2| < 1000), and pc > 0 keeps every logarithm finite.
+            // normal range (|log2| < 1000), and pc >= 1e-30 keeps every float32 logarithm argument normal and finite.
             const double bases = (double)h->gcnt[0] + h->gcnt[1] + h->gcnt[2] + h->gcnt[3] + (double)h->max_len;
             const double den = (bases > (double)h->n ? bases : (double)h->n) + a.alpha_pc;
-            a.drift_fast_ok = (p->pseudocount > 0.0 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
+            a.drift_fast_ok = (p->pseudocount >= 1e-30 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
             if (getenv("GIBBS_B200_DRIFT_EXACT")) a.drift_fast_ok = 0; // measurement / test switch: every window in float64
             a.fast_ok = a.drift_fast_ok;
         }

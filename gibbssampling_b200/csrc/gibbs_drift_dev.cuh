@@ -93,6 +93,14 @@ __device__ __forceinline__ void scan_drifting(const uint32_t *row, int W, int k,
 // maximum. Those windows (at most one per lane, else the exact scan runs) are re-scored exactly as scan_drifting does.
 constexpr float DRIFT_MARGIN = 0.03125f;
 
+// MUFU.LG2 alone: the arguments of the ranking pass are normal floats (counts + pc with pc >= 1e-30, checked on the
+// host), so the denormal rescaling that __log2f wraps around the instruction is dead weight (4 of 5 instructions)
+__device__ __forceinline__ float lg2_normal(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // float32 log2 of the PPM in pair-table form: pt[p*16 + nib] = lg[2p][nib & 3] + lg[2p+1][nib >> 2]
 template <int KP>
 __device__ __forceinline__ void drift_pair_table(const double *ppm, float *lg, float *pt, int k, int lane) {
@@ -174,9 +182,9 @@ __device__ __forceinline__ bool scan_drifting_fast(const uint32_t *row, int W, i
                 run[b] += ob;
                 const int F = f0[b] + (w + 1) * cn[b] - run[b];
                 sum += F;
-                bg = fmaf((float)ob, __log2f((float)F + pcf), bg);
+                bg = fmaf((float)ob, lg2_normal((float)F + pcf), bg);
             }
-            bg = fmaf(-kf, __log2f((float)sum + apcf), bg);
+            bg = fmaf(-kf, lg2_normal((float)sum + apcf), bg);
             const uint64_t kmer = kmer_shared<KP>(row, w);
             float mot = 0.0f;
 #pragma unroll
@@ -191,9 +199,9 @@ __device__ __forceinline__ bool scan_drifting_fast(const uint32_t *row, int W, i
             } else if (a > M2) {
                 M2 = a;
             }
-            if (w + 1 < w_end) {
-                oc -= 1u << (8 * base_at(row, w));
-                oc += 1u << (8 * base_at(row, w + k));
+            if (w + 1 < w_end) { // slide: base w leaves, base w + k enters (both inside the 64 bits just fetched when k < 32)
+                oc -= 1u << (8 * ((uint32_t)kmer & 3u));
+                oc += 1u << (8 * (k < 32 ? (int)((uint32_t)(kmer >> (2 * k)) & 3u) : base_at(row, w + k)));
             }
         }
     }

@@ -6,11 +6,12 @@ def regions(path):
     out = []; name = None
     for i, l in enumerate(open(path).read().splitlines(), 1):
         m = re.match(r'(?:template.*>\s*)?(?:__device__|__global__|static|inline|struct)\b.*?\b(\w+)\s*(\(|\{|$)', l)
+        if l.startswith('static '): l = l[7:]
         if l.startswith('__device__') or l.startswith('__global__') or l.startswith('struct ') or l.startswith('template'):
             m2 = re.search(r'(\w+)\s*\(', l) or re.search(r'struct\s+(\w+)', l)
             if m2 and not l.startswith('template'): out.append((i, m2.group(1)))
     return out
-reg = {'gibbs_device.cuh': regions('gibbssampling_b200/csrc/gibbs_device.cuh'), 'gibbs_kernels.cuh': regions('gibbssampling_b200/csrc/gibbs_kernels.cuh')}
+reg = {f: regions('gibbssampling_b200/csrc/' + f) for f in ('gibbs_device.cuh', 'gibbs_kernels.cuh', 'gibbs_drift_dev.cuh')}
 def region_of(f, l):
     if f not in reg: return f
     name = '?'
