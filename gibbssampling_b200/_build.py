@@ -34,6 +34,8 @@ CHAIN_GROUPS = [
     ("launch_chain_drift_t1", 1, 0, 1),
     ("launch_chain_masked_t4", 4, 1, 0),
     ("launch_chain_masked_t1", 1, 1, 0),
+    ("launch_chain_masked_drift_t4", 4, 1, 1),
+    ("launch_chain_masked_drift_t1", 1, 1, 1),
 ]
 
 COMMON_FLAGS = [

@@ -25,6 +25,8 @@ GIBBS_CHAIN_TU(launch_chain_t8);
 GIBBS_CHAIN_TU(launch_chain_t16);
 GIBBS_CHAIN_TU(launch_chain_masked_t1);
 GIBBS_CHAIN_TU(launch_chain_masked_t4);
+GIBBS_CHAIN_TU(launch_chain_masked_drift_t1);
+GIBBS_CHAIN_TU(launch_chain_masked_drift_t4);
 GIBBS_CHAIN_TU(launch_chain_drift_t1);
 GIBBS_CHAIN_TU(launch_chain_drift_t4);
 GIBBS_CHAIN_TU(launch_chain_drift_t8);
@@ -125,7 +127,7 @@ struct gibbs_handle {
     DevBuf<double> pvals, gbuf;
     DevBuf<double> start_ppm;  // gibbs_set_start_ppm: [k][4]
     int32_t start_ppm_k = 0;   // 0 = none set
-    DevBuf<int32_t> basecnt;
+    DevBuf<int32_t> basecnt, maskcnt;
     bool drift_valid = false;
     double drift_pc = 0;
     int32_t drift_alen = 0;
@@ -221,7 +223,9 @@ int32_t launch_team(gibbs_handle *h, int team, bool masked, bool drift, const Ch
     const int smem = team_smem_bytes(a.s.row_words, team);
     if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for %d warps per chain", team);
     cudaError_t e = cudaErrorInvalidValue;
-    if (masked) e = team == 4 ? launch_chain_masked_t4(a, grid, smem, h->stream) : launch_chain_masked_t1(a, grid, smem, h->stream);
+    if (masked && drift)
+        e = team == 4 ? launch_chain_masked_drift_t4(a, grid, smem, h->stream) : launch_chain_masked_drift_t1(a, grid, smem, h->stream);
+    else if (masked) e = team == 4 ? launch_chain_masked_t4(a, grid, smem, h->stream) : launch_chain_masked_t1(a, grid, smem, h->stream);
     else if (drift)
         e = team == 8 ? launch_chain_drift_t8(a, grid, smem, h->stream)
             : team == 4 ? launch_chain_drift_t4(a, grid, smem, h->stream) : launch_chain_drift_t1(a, grid, smem, h->stream);
@@ -422,7 +426,8 @@ int32_t ensure_drift(gibbs_handle *h, const gibbs_params *p, int *launches) {
     const double den = (double)(h->n - 1) + ((double)p->alphabet_size * p->pseudocount); // fs:257
     pvals_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->n, p->pseudocount, den, h->pvals.p);
     CUDA_TRY(cudaGetLastError());
-    basecount_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(dev_seqs(h), h->basecnt.p);
+    CUDA_TRY(h->maskcnt.reserve((size_t)h->n));
+    basecount_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(dev_seqs(h), h->basecnt.p, h->maskcnt.p);
     CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 2;
     std::vector<int32_t> bc((size_t)h->n * 4);
@@ -649,7 +654,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->stats.release(); h->best.release();
     h->bg_g.release(); h->bg_sum.release(); h->bg_max.release(); h->bg_max_i.release();
     h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
-    h->pvals.release(); h->basecnt.release(); h->gbuf.release(); h->start_ppm.release();
+    h->pvals.release(); h->basecnt.release(); h->maskcnt.release(); h->gbuf.release(); h->start_ppm.release();
     h->ctl.release(); h->resume.release(); h->pending.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -822,9 +827,9 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     if (p->sampler != GIBBS_SITE_SAMPLER && p->sampler != GIBBS_MOTIF_SAMPLER) return fail(GIBBS_ERR_ARG, "unknown sampler %d", p->sampler);
     if (rng_mode != GIBBS_RNG_PHILOX && rng_mode != GIBBS_RNG_INJECTED) return fail(GIBBS_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (rng_mode == GIBBS_RNG_INJECTED && (!uniforms || uniforms_per_chain < 0)) return fail(GIBBS_ERR_ARG, "injected uniforms missing");
-    if (h->n_masked > 0 && (p->sampler != GIBBS_SITE_SAMPLER || p->background != GIBBS_BG_FIXED))
-        return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler with a fixed background only "
-                                           "(MotifSampler / data-derived backgrounds need ACGT-only sequences)");
+    if (h->n_masked > 0 && p->sampler != GIBBS_SITE_SAMPLER)
+        return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler only (the MotifSampler needs "
+                                           "ACGT-only sequences)");
     rc = set_device(h);
     if (rc) return rc;
     h->run_done = false;
@@ -924,6 +929,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         // teams of warps, speculative rounds and the hand-over of chain_kernel, with the drifting-background scan
         a.pvals = h->pvals.p;
         a.basecnt = h->basecnt.p;
+        a.maskcnt = h->n_masked > 0 ? h->maskcnt.p : nullptr;
         memcpy(a.gcnt, h->gcnt, sizeof a.gcnt);
         a.alpha_pc = (double)p->alphabet_size * p->pseudocount; // float alphabet.Length * pseudoCount, fs:117
         a.pc = p->pseudocount;

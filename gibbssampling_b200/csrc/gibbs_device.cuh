@@ -79,6 +79,7 @@ struct ChainArgs {
     // (c + pc) / ((N-1) + |A| pc) (fs:260), base counts per sequence and of the whole set, |A| pc (fs:117)
     const double *pvals;      // [n]
     const int32_t *basecnt;   // [n][4]
+    const int32_t *maskcnt;   // [n] symbols outside A,C,G,T per sequence (null when the set has none)
     int32_t gcnt[4];
     double alpha_pc, pc;
     int32_t drift_fast_ok;    // the float32 ranking pass may be used

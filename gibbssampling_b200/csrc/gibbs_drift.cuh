@@ -17,18 +17,24 @@
 namespace gibbs {
 
 
-// one thread per sequence: A,C,G,T counts
-__global__ void basecount_kernel(DeviceSeqs s, int32_t *basecnt) {
+// one thread per sequence: A,C,G,T counts, and the number of symbols outside A,C,G,T (maskcnt may be null)
+__global__ void basecount_kernel(DeviceSeqs s, int32_t *basecnt, int32_t *maskcnt) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= s.n) return;
     const uint32_t *row = s.packed + (size_t)n * s.row_words;
+    const uint32_t *mrow = s.mask ? s.mask + (size_t)n * s.row_words : nullptr;
     const int L = s.len[n];
-    int c[4] = {0, 0, 0, 0};
+    int c[4] = {0, 0, 0, 0}, m = 0;
     for (int b = 0; b < L; ++b) {
         const int code = (row[b >> 4] >> ((b & 15) * 2)) & 3;
+        if (mrow && ((mrow[b >> 4] >> ((b & 15) * 2)) & 1)) {
+            ++m;
+            continue;
+        }
         c[0] += code == 0; c[1] += code == 1; c[2] += code == 2; c[3] += code == 3;
     }
     for (int b = 0; b < 4; ++b) basecnt[n * 4 + b] = c[b];
+    if (maskcnt) maskcnt[n] = m;
 }
 
 __global__ void pvals_kernel(int n, double pc, double den, double *pvals) {

@@ -245,6 +245,96 @@ __device__ __forceinline__ bool scan_drifting_fast(const uint32_t *row, int W, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// the all-windows scan for a held-out sequence with symbols outside A,C,G,T (rare path, out of line)
+// ------------------------------------------------------------------------------------------------
+// Such a symbol is not in `alphabet`: its PWM row is 0, so a window that holds it scores 0 (fs:283-287). The drifting
+// background still sees it: increaseInPlaceFCVOf adds EVERY symbol of the held-out sequence (fs:79-81, fs:471) and
+// substractSegmentCountsFrom takes the window's symbols out again (fs:84-88), so the dead rows hold
+// (w + 1) M_n - sum_{m <= w} occM_m (M_n = such symbols in the sequence, occM_m = in window m) and add to the
+// denominator of createNormalizedPCVOfFCV, which sums all 49 slots (fs:116). The other sequences' dead rows were
+// dropped by fuseFrequencyVectors (fs:67-69).
+__device__ __forceinline__ int mask_at(const uint32_t *__restrict__ mrow, int pos) { return (__ldg(mrow + (pos >> 4)) >> ((pos & 15) * 2)) & 1; }
+
+static __device__ __noinline__ void scan_drifting_masked(const uint32_t *row, const uint32_t *__restrict__ mrow, int W, int k, const double *ppm,
+                                                  const int *f0, const int *cn, int Mn, double pc, double alpha_pc, int lane,
+                                                  double &hv_out, int &w_out) {
+    const int B = (W + 31) >> 5;
+    const int w_begin = min(W, lane * B), w_end = min(W, w_begin + B);
+    // byte-packed occurrences of A,C,G,T in the window (masked bases excluded) + the masked count
+    auto add = [&](uint32_t &occ, int &om, int pos, int sign) {
+        if (mask_at(mrow, pos)) om += sign;
+        else occ += (uint32_t)sign << (8 * base_at(row, pos));
+    };
+    int blocksum[5] = {0, 0, 0, 0, 0};
+    if (w_begin < w_end) {
+        uint32_t occ = 0;
+        int om = 0;
+        for (int j = 0; j < k; ++j) add(occ, om, w_begin + j, 1);
+        for (int w = w_begin; w < w_end; ++w) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) blocksum[b] += (int)((occ >> (8 * b)) & 255u);
+            blocksum[4] += om;
+            if (w + 1 < w_end) {
+                add(occ, om, w, -1);
+                add(occ, om, w + k, 1);
+            }
+        }
+    }
+    int run[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        int v = blocksum[b];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += t;
+        }
+        run[b] = v - blocksum[b];
+    }
+    double hv = 0.0;
+    int hw = 0;
+    if (w_begin < w_end) {
+        uint32_t oc = 0;
+        int om = 0;
+        for (int j = 0; j < k; ++j) add(oc, om, w_begin + j, 1);
+        for (int w = w_begin; w < w_end; ++w) {
+            int F[4], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                run[b] += (int)((oc >> (8 * b)) & 255u);
+                F[b] = f0[b] + (w + 1) * cn[b] - run[b];
+                sum += F[b];
+            }
+            run[4] += om;
+            sum += (w + 1) * Mn - run[4];                                         // the dead rows (fs:116 sums every slot)
+            if (om == 0) {                                                          // else the window scores 0
+                const double den = __dadd_rn((double)sum, alpha_pc);
+                double pcv[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) pcv[b] = __ddiv_rn(__dadd_rn((double)F[b], pc), den);
+                double v = 1.0;
+                for (int j = 0; j < k; ++j) {
+                    const int b = base_at(row, w + j);
+                    const double q = b == 0 ? pcv[0] : b == 1 ? pcv[1] : b == 2 ? pcv[2] : pcv[3];
+                    v = __dmul_rn(v, __ddiv_rn(ppm[j * 4 + b], q));
+                }
+                if (v > hv) {
+                    hv = v;
+                    hw = w;
+                }
+            }
+            if (w + 1 < w_end) {
+                add(oc, om, w, -1);
+                add(oc, om, w + k, 1);
+            }
+        }
+    }
+    warp_argmax(hv, hw);
+    hv_out = hv;
+    w_out = hw;
+}
+
+// ------------------------------------------------------------------------------------------------
 // one site update with the drifting background, the pieces chain_kernel<.., DRIFT = true> calls
 // ------------------------------------------------------------------------------------------------
 // PPM of the leave-one-out counts (createPPMOf + normalizePPM, fs:573-575) into W.wcol, the counts themselves into
@@ -254,10 +344,10 @@ __device__ __forceinline__ bool scan_drifting_fast(const uint32_t *row, int W, i
 template <int KP>
 __device__ __forceinline__ void drift_tables(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
                                              const ChainArgs &a, bool use_given, bool fast, int n, int lane, int (&f0)[4],
-                                             int (&cn)[4]) {
+                                             int (&cn)[4], uint64_t own_mask = 0) {
     for (int e = lane; e < 4 * k; e += 32) {
         int c = counts[e];
-        if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3)) c -= 1;
+        if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3) && !((own_mask >> (2 * (e >> 2))) & 1u)) c -= 1; // (a masked own base was never counted)
         W.wcol[e] = use_given ? __ldg(a.ppm_given + e) : __ldg(a.pvals + c);
         W.lgcol[e] = c;
     }
@@ -273,10 +363,16 @@ __device__ __forceinline__ void drift_tables(const WarpTables &W, const int32_t 
     if (fast) drift_pair_table<KP>(W.wcol, reinterpret_cast<float *>(W.counts), reinterpret_cast<float *>(W.ptab), k, lane);
 }
 
-// getBestPWMSs (fs:462-479) for the staged row; returns true when every window was scored in float64
+// getBestPWMSs (fs:462-479) for the staged row; returns true when every window was scored in float64.
+// masked_n >= 0: the held-out sequence holds symbols outside A,C,G,T (a.s.mask != null)
 template <int KP>
 __device__ __forceinline__ bool drift_pick(const WarpTables &W, const uint32_t *row, int Wn, int k, const ChainArgs &a, bool fast,
-                                           const int (&f0)[4], const int (&cn)[4], int lane, double &p, int &w) {
+                                           const int (&f0)[4], const int (&cn)[4], int lane, double &p, int &w, int masked_n = -1) {
+    if (masked_n >= 0) {
+        scan_drifting_masked(row, a.s.mask + (size_t)masked_n * a.s.row_words, Wn, k, W.wcol, f0, cn, __ldg(a.maskcnt + masked_n), a.pc,
+                             a.alpha_pc, lane, p, w);
+        return true;
+    }
     bool ranked = false;
     if (fast)
         ranked = scan_drifting_fast<KP>(row, Wn, k, W.wcol, reinterpret_cast<const float *>(W.ptab), f0, cn, a.pc, a.alpha_pc,

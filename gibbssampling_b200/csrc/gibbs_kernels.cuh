@@ -378,15 +378,17 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
                     const bool given = phase == PH_INIT && a.ppm_given != nullptr;
                     const bool fast = a.drift_fast_ok && !given; // (a supplied PPM may hold zeros or denormals: exact scan)
                     if (phase == PH_INIT) {
-                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, false>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
                         drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
                     } else {
                         site_n = S.blk_site[o];
                         hv_n = S.blk_hv[o];
                         own = kmer_shared<KP>(row, shifted_site(site_n, len_n, k, mode));
-                        drift_tables<KP>(WT, S.total, true, own, k, a, false, fast, n, lane, f0, cn);
+                        uint64_t own_mk = 0; // rare: the own site may cover symbols outside A,C,G,T
+                        if (MASKED && masked_n >= 0) own_mk = mask_kmer(a.s.mask, a.s.row_words, n, shifted_site(site_n, len_n, k, mode), k);
+                        drift_tables<KP>(WT, S.total, true, own, k, a, false, fast, n, lane, f0, cn, own_mk);
                     }
-                    slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w);
+                    slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w, MASKED ? masked_n : -1);
                 } else {
                     if (phase == PH_INIT) {
                         random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);

@@ -138,8 +138,8 @@ def test_symbol_errors_and_unsupported_combinations():
             eng.run(make_params(4, 1e-4, 5, BG), 1)
         ok = eng.run(make_params(4, 1e-4, 4, BG), 2, seed=5)      # alphabet of 4: Gap scores 0 like N
         assert ok.sites.shape == (2, 2)
-        with pytest.raises(_abi.GibbsUnsupportedError):
-            eng.run(make_params(4, 1e-4, 4, BG, background=_abi.GIBBS_BG_DATA), 1)
+        data = eng.run(make_params(4, 1e-4, 4, BG, background=_abi.GIBBS_BG_DATA), 2, seed=5)   # built (see below)
+        assert data.sites.shape == (2, 2)
         with pytest.raises(_abi.GibbsUnsupportedError):
             eng.run(make_params(4, 1e-4, 4, BG, sampler=_abi.GIBBS_MOTIF_SAMPLER, cutoff=0.0), 1)
     with GibbsEngine([b"ACGTACGT", b"ACGTACGT"]) as eng:          # no masked symbol: everything stays available
@@ -166,3 +166,37 @@ def test_row_without_a_valid_window(team):
         ok = np.isfinite(score)
         np.testing.assert_allclose(res.scores[c][ok], score[ok], rtol=LOG2_RTOL)
         assert res.sums[c] == -np.inf
+
+
+DATA_CASES = [  # (seed, n, lo, hi, k, other symbols, fraction, alphabet_size)
+    (11, 6, 30, 60, 6, "NRY*", 0.05, 5),
+    (12, 9, 40, 90, 12, "N", 0.02, 5),
+    (13, 5, 25, 40, 7, "N-W", 0.10, 4),      # Gap outside a 4-symbol alphabet: a dead row like N
+    (14, 8, 200, 300, 16, "NB", 0.01, 5),
+    (15, 4, 12, 20, 3, "N", 0.30, 5),        # heavy masking
+]
+
+
+@pytest.mark.parametrize("case", DATA_CASES, ids=lambda c: f"s{c[0]}_n{c[1]}_k{c[4]}")
+def test_data_derived_background_with_masked_symbols(case):
+    """doSiteSampling (fs:697) on sequences with symbols outside the alphabet: zero-score windows, uncounted site
+    bases, and the dead rows that the held-out sequence adds to the background denominator (fs:471, fs:116)."""
+    seed, n, lo, hi, k, sym, frac, alen = case
+    seqs = _seqs(seed, n, lo, hi, sym, frac)
+    S = O.sources(seqs)
+    alphabet = _alphabet(alen)
+    params = make_params(k, 1e-4, alen, BG, background=_abi.GIBBS_BG_DATA)
+    with GibbsEngine(seqs) as eng:
+        res = eng.run(params, 4, chain_id_base=60, seed=5 + seed, want_counts=False)
+        u = np.random.default_rng(seed).random((1, draws_per_chain(n)))
+        inj = eng.run(params, 1, uniforms=u, want_counts=False)
+    for c in range(4):
+        rng, keep = O.make_rng(seed=5 + seed, chain=60 + c)
+        score, pos, _ = O.site_step("do_site_sampling", S, k, 1e-4, rng=rng, alphabet=alphabet)
+        assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"
+        finite = np.isfinite(score)
+        assert np.array_equal(np.isfinite(res.scores[c]), finite)
+        np.testing.assert_allclose(res.scores[c][finite], score[finite], rtol=LOG2_RTOL)
+    rng, keep = O.make_rng(uniforms=u[0])
+    score, pos, _ = O.site_step("do_site_sampling", S, k, 1e-4, rng=rng, alphabet=alphabet)
+    assert inj.sites[0].tolist() == pos.tolist()
