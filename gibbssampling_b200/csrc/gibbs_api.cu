@@ -913,6 +913,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         m.cand_w = h->cand_w.p;
         m.error = h->err_flag.p;
         m.data_bg = p->background == GIBBS_BG_DATA ? 1 : 0;
+        m.greedy_fast_ok = a.fast_ok; // fixed background: the range check of the W table (ensure_wtab)
         if (m.data_bg) {
             m.pvals = h->pvals.p;
             m.basecnt = h->basecnt.p;
@@ -920,7 +921,19 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             m.alpha_pc = (double)p->alphabet_size * p->pseudocount;
             m.pc = p->pseudocount;
             m.gbuf = h->gbuf.p;
+            // every odds ratio lies in [pc / den, den / pc] (see the SiteSampler branch below): no product of k of them
+            // leaves the float64 normal range, the fixed-point keys stay far inside int32
+            const double bases = (double)h->gcnt[0] + h->gcnt[1] + h->gcnt[2] + h->gcnt[3] + (double)h->max_len;
+            const double den = (bases > (double)h->n ? bases : (double)h->n) + m.alpha_pc;
+            m.greedy_fast_ok = (p->pseudocount >= 1e-30 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
+            m.c.pvals = m.pvals; // the random starts use the SiteSampler's drifting-background routines (drift_tables / drift_pick)
+            m.c.basecnt = m.basecnt;
+            m.c.maskcnt = nullptr;
+            memcpy(m.c.gcnt, m.gcnt, sizeof m.gcnt);
+            m.c.alpha_pc = m.alpha_pc;
+            m.c.pc = m.pc;
         }
+        if (getenv("GIBBS_B200_MOTIF_EXACT")) m.greedy_fast_ok = 0; // measurement / test switch: every window in float64
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_motif(h, m);
         if (rc) return rc;

@@ -37,6 +37,7 @@ struct MotifArgs {
     int32_t gcnt[4];
     double alpha_pc, pc;
     double *gbuf;          // [chains][wstride] background window probabilities of the current held-out sequence
+    int32_t greedy_fast_ok; // greedy sweeps may rank windows in fixed point (no float64 under/overflow possible, pc > 0)
 };
 
 // one thread per sequence
@@ -143,6 +144,81 @@ __device__ __forceinline__ bool motif_roulette(const double *g, double gsum, int
     return false;
 }
 
+// ------------------------------------------------------------------------------------------------
+// greedy sweeps (fs:788-822, fs:885-929) without scoring every window in float64
+// ------------------------------------------------------------------------------------------------
+// The greedy update takes the head of `background entries ++ candidates` sorted by PWMS (stable): only the best
+// candidate matters, i.e. the FIRST window whose log2 score is the largest, if that exceeds the cut-off. The ranking
+// pass of the SiteSampler finds the first window with the largest float64 PRODUCT. The two agree unless another
+// window's product is so close to the maximum that both round to the same log2; every window that close lies in a
+// chunk the ranking pass re-scores anyway, so the check is a comparison there, and such a case (or anything else the
+// ranking pass cannot decide) falls back to the all-windows candidate list below.
+template <int KP, int CH>
+__device__ __forceinline__ bool pick_unique_argmax_ch(const WarpTables &T, const uint32_t *row, int W, int k, int lane,
+                                                      double &hv_out, int &w_out) {
+    using G = ScanGeom<KP, CH>;
+    int32_t M1, M2;
+    int S1;
+    scan_fast<KP, CH>(row, W, T.ptab, lane, M1, M2, S1);
+    const int32_t M = __reduce_max_sync(FULL, M1);
+    const int32_t thr = M - (((k + 1) << KEY_IDX_BITS) + 255);
+    if (__ballot_sync(FULL, M2 >= thr)) return false;
+    unsigned cand = __ballot_sync(FULL, M1 >= thr);
+    double p = 0.0, p2 = 0.0; // this lane's best and second-best re-scored window
+    int w = INT32_MAX;
+    while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int32_t key = __shfl_sync(FULL, M1, src);
+        const int seg = __shfl_sync(FULL, S1, src);
+        const int wi = chunk_base<CH>(seg * G::CPS + src + 32 * (255 - (key & 255)), W) + lane;
+        if (lane < CH && wi < W) {
+            const double pi = exact_window<KP>(row, wi, k, T.wcol);
+            if (better(pi, wi, p, w)) {
+                p2 = fmax(p2, p);
+                p = pi;
+                w = wi;
+            } else if (wi != w) {
+                p2 = fmax(p2, pi);
+            }
+        }
+    }
+    double pm = p;
+    int wm = w;
+    warp_argmax(pm, wm);
+    const double lim = pm * (1.0 - 1e-12); // log2 of anything below this differs from log2(pm) by > 1000 ulp
+    const bool close = (w != wm && p >= lim) || p2 >= lim; // (pm = 0: every lane reports close -> fall back)
+    if (__ballot_sync(FULL, close)) return false;
+    hv_out = pm;
+    w_out = wm;
+    return true;
+}
+
+template <int KP>
+__device__ __forceinline__ bool pick_unique_argmax(const WarpTables &T, const uint32_t *row, int W, int k, int lane, double &hv_out,
+                                                   int &w_out) {
+    if (W > 256) return pick_unique_argmax_ch<KP, 16>(T, row, W, k, lane, hv_out, w_out);
+    if (W > 128) return pick_unique_argmax_ch<KP, 8>(T, row, W, k, lane, hv_out, w_out);
+    return pick_unique_argmax_ch<KP, 4>(T, row, W, k, lane, hv_out, w_out);
+}
+
+// fixed-point log2 tables of an odds table built on the fly (data-derived background): what wtab_kernel precomputes
+// for the fixed background. T.wcol holds the float64 odds (dummy column of an odd k = 1.0).
+template <int KP>
+__device__ __forceinline__ void fixed_point_tables(const WarpTables &T, int lane) {
+    for (int e = lane; e < 8 * KP; e += 32) {
+        double units = rint(log2(T.wcol[e]) * (double)(1 << LG_FRAC_BITS));
+        units = fmin(fmax(units, -4000000.0), 4000000.0);
+        T.lgcol[e] = (int)units * (1 << KEY_IDX_BITS);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < 16 * KP; idx += 32) {
+        const int p = idx >> 4, nib = idx & 15;
+        T.ptab[idx] = T.lgcol[(2 * p) * 4 + (nib & 3)] + T.lgcol[(2 * p + 1) * 4 + (nib >> 2)];
+    }
+    __syncwarp();
+}
+
 template <int KP>
 __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -168,7 +244,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
     __syncwarp();
     if (lane == 0) ring.fill(4);
 
-    unsigned long long st_updates = 0, st_windows = 0;
+    unsigned long long st_updates = 0, st_windows = 0, st_slow = 0; // st_slow: updates that scored every window in float64
     int st_sweeps = 0, capped = 0;
     uint32_t v = 0;
 
@@ -200,22 +276,12 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                 if (!m.data_bg) {
                     build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                     pick_argmax<KP>(WT, row, W, k, a.fast_ok, lane, p, w);
-                } else { // SiteSampler.getPWMOfRandomStarts: drifting background (fs:589-611)
-                    for (int e = lane; e < 4 * k; e += 32) {
-                        const int c = WT.counts[e];
-                        WT.wcol[e] = a.ppm_given ? __ldg(a.ppm_given + e) : __ldg(m.pvals + c); // fs:1029 / fs:877
-                        WT.lgcol[e] = c;
-                    }
-                    __syncwarp();
+                } else { // SiteSampler.getPWMOfRandomStarts: drifting background (fs:589-611), ranked like the SiteSampler's
+                    const bool given = a.ppm_given != nullptr;           // fs:1029: scored against the caller's PPM
+                    const bool fast = m.greedy_fast_ok && !given;
                     int f0[4], cn[4];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        int s = 0;
-                        for (int j = lane; j < k; j += 32) s += WT.lgcol[j * 4 + b];
-                        cn[b] = __ldg(m.basecnt + n * 4 + b);
-                        f0[b] = (m.gcnt[b] - cn[b]) - __reduce_add_sync(FULL, s);
-                    }
-                    scan_drifting(row, W, k, WT.wcol, f0, cn, m.pc, m.alpha_pc, lane, p, w);
+                    drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
+                    drift_pick<KP>(WT, row, W, k, a, fast, f0, cn, lane, p, w);
                 }
                 if (lane == 0) {
                     sites[n] = w;
@@ -260,16 +326,20 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                         const double qb = b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3];
                         WT.wcol[e] = (e >> 2) < k ? __ddiv_rn(__ldg(m.pvals + WT.lgcol[e]), qb) : 1.0;
                     }
-                    // background-only probability of every window (fs:776), first maximum, and their sum in list order
+                    // background-only probability of every window (fs:776), first maximum, and their sum in list order:
+                    // the same left-to-right product as a window score, over a table whose every column is q
+                    // (kept in the pair-table space, which is rebuilt after this loop when the greedy ranking pass runs)
+                    double *qtab = reinterpret_cast<double *>(WT.ptab);
+                    for (int e = lane; e < 8 * KP; e += 32) {
+                        const int b = e & 3;
+                        qtab[e] = (e >> 2) < k ? (b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3]) : 1.0;
+                    }
+                    __syncwarp();
                     double bestg = 0.0;
                     for (int w0 = 0; w0 < W; w0 += 32) {
                         const int w = w0 + lane;
                         if (w < W) {
-                            double v = 1.0;
-                            for (int j = 0; j < k; ++j) {
-                                const int b = base_at(row, w + j);
-                                v = __dmul_rn(v, b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3]);
-                            }
+                            const double v = exact_window<KP>(row, w, k, qtab);
                             gbuf[w] = v;
                             bestg = fmax(bestg, v);
                         }
@@ -291,7 +361,19 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                 }
                 double best_l;
                 int best_w;
-                const int n_cand = motif_candidates<KP>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w);
+                int n_cand = -1;
+                if (phase == MPH_GREEDY && m.greedy_fast_ok) { // only the best candidate matters: rank, re-score, compare
+                    if (m.data_bg) fixed_point_tables<KP>(WT, lane);
+                    double pbest;
+                    if (pick_unique_argmax<KP>(WT, row, W, k, lane, pbest, best_w)) {
+                        best_l = log2_ref(pbest);
+                        n_cand = best_l > a.cutoff ? 1 : 0; // fs:735
+                    }
+                }
+                if (n_cand < 0) {
+                    n_cand = motif_candidates<KP>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w);
+                    st_slow += 1;
+                }
                 double new_pw;
                 int new_site;
                 bool take;
@@ -374,6 +456,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
         for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(pw + n));
         a.sums[chain] = sum;
         atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
+        atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
         atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
         atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
         atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
