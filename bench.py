@@ -38,7 +38,7 @@ CONFIGS = {
     "C4": (100000, 200, 20, 148, True),   # ChIP-seq-peak-sized set with phase-shift moves
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step (ncu --set full, round 1)
-NCU_DRAM_BYTES_PER_STEP = int((0.613120 + 1.512448 + 3.318528 + 0.000256 + 1.624832 + 0.000512) * 1e6)
+NCU_DRAM_BYTES_PER_STEP = int((0.316672 + 1.589760 + 3.313920 + 0.000000 + 1.631232 + 0.003328) * 1e6)
 # --family: which reference family the step runs (the default is the BASELINE.json workload)
 FAMILIES = {
     "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts", "gibbs::chain_kernel",
