@@ -110,3 +110,25 @@ def test_zero_pseudocount_takes_the_exact_scan():
         rng, keep = O.make_rng(seed=4, chain=c)
         score, pos, _ = O.site_step("do_site_sampling", S, 6, 0.0, rng=rng)
         assert res.sites[c].tolist() == pos.tolist()
+
+
+def test_hand_over_stages_do_not_change_a_chain():
+    """More than two chains per SM: stage 1 (4 warps) pauses the last chains and stage 2 (8 warps) continues them.
+    A chain's result depends on (seed, chain id) only, whatever the launch shape; spot-checked against the oracle."""
+    n, L, k = 24, 100, 8
+    ps = planted_motif_set(n, L, k, seed=41)
+    seqs = ps.sequences()
+    params = make_params(k, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA)
+    with GibbsEngine(seqs) as eng:
+        big = eng.run(params, 2000, seed=23, want_counts=False)
+        assert big.stats["kernel_launches"] >= 3                     # two chain-kernel stages + best chain
+        for chains, base in ((1, 0), (5, 1234), (300, 900), (64, 1936)):
+            res = eng.run(params, chains, chain_id_base=base, seed=23, want_counts=False)
+            assert res.sites.tobytes() == big.sites[base:base + chains].tobytes(), (chains, base)
+            assert res.scores.tobytes() == big.scores[base:base + chains].tobytes(), (chains, base)
+    S = O.sources(seqs)
+    for c in (0, 777, 1999):
+        rng, _ = O.make_rng(seed=23, chain=c)
+        score, pos, _ = O.site_step("do_site_sampling", S, k, 1e-4, rng=rng)
+        assert big.sites[c].tolist() == pos.tolist(), f"chain {c}"
+        np.testing.assert_allclose(big.scores[c], score, rtol=RTOL)
