@@ -13,8 +13,13 @@
  *   - every function returns a gibbs_status (0 = OK); the text of the last failure is available
  *     from gibbs_last_error(); nothing throws or aborts across the boundary
  *   - sequences: ONE contiguous buffer of upper-case ASCII symbols (BioItem.symbol, fs:17) plus
- *     int64 offsets[n_seqs + 1]. This build accepts A, C, G, T only; any other symbol is
- *     GIBBS_ERR_SYMBOL (the reference's 49-slot tables accept '*'..'Z', fs:20)
+ *     int64 offsets[n_seqs + 1]. Every symbol the reference's 49-slot tables index ('*'..'Z',
+ *     fs:17-20) is accepted, anything else is GIBBS_ERR_SYMBOL. A, C, G, T are the alphabet the
+ *     tables are built for; any other symbol is treated as NOT in `alphabet`: its PWM row is 0
+ *     (fs:283-287), a window that holds it scores 0, a site base that is one is not counted.
+ *     Gap '-' with alphabet_size >= 5 (the script's dnaBases, where Gap IS an alphabet member
+ *     with a PWM row of its own) and any such symbol under the MotifSampler are
+ *     GIBBS_ERR_UNSUPPORTED
  *   - base order of every 4-wide table: A, C, G, T
  *   - (float*int)[] results: parallel arrays double score[n] (log2, fs:303) and int32 site[n]
  *   - there is NO CPU fallback: every compute entry point launches CUDA kernels on the handle's
@@ -37,7 +42,7 @@ extern "C" {
 typedef enum gibbs_status {
     GIBBS_OK = 0,
     GIBBS_ERR_ARG = 1,         /* ArgumentNullException / ArgumentException (fs:24, fs:183)        */
-    GIBBS_ERR_SYMBOL = 2,      /* IndexOutOfRangeException analogue: symbol outside A,C,G,T (fs:17) */
+    GIBBS_ERR_SYMBOL = 2,      /* IndexOutOfRangeException: symbol outside '*'..'Z' (fs:17, fs:20)   */
     GIBBS_ERR_SHORT_SEQ = 3,   /* InvalidOperationException from Array.take when L < k (fs:152)     */
     GIBBS_ERR_CUDA = 4,        /* CUDA runtime / launch failure or no usable device                 */
     GIBBS_ERR_NCCL = 5,        /* reserved: collectives run in the host layer (torch.distributed)   */
