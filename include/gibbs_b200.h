@@ -90,12 +90,12 @@ typedef struct gibbs_run_stats {
     int64_t site_updates;  /* scans of one held-out sequence, all chains                        */
     int64_t window_scores; /* windows scored inside those scans                                 */
     int64_t sweeps;        /* passes n = 0..N-1, all chains                                     */
-    int64_t exact_rescans; /* site updates that fell back to the all-windows float64 path       */
+    int64_t exact_rescans; /* site updates that scored every window in float64 (no ranking pass) */
     int64_t capped_chains; /* chains stopped by max_sweeps                                      */
     int64_t speculative_discards; /* greedy-sweep site updates computed ahead and thrown away   */
     int32_t kernel_launches; /* CUDA kernels launched by the call                               */
     int32_t fast_path;     /* 1 = fixed-point filter + float64 verification was usable          */
-    int32_t team_warps;    /* warps that ran each chain (1 or 4)                                */
+    int32_t team_warps;    /* warps per chain of the first launch (1, 4, 8 or 16)               */
     int32_t reserved;
     double kernel_ms;      /* device time of the chain kernel (CUDA events on the handle stream) */
 } gibbs_run_stats;
@@ -155,17 +155,6 @@ int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldo
 
 /* ---- chains / restarts ------------------------------------------------------------------------ */
 /*
- * Replaces: one restart pipeline per chain --
- *   sampler 0: getPWMOfRandomStartsWithBPV |> findBestMotifWithStartPosition
- *              |> getLeftShiftedBestPWMSsWithBPV |> getRightShiftedBestPWMSsWithBPV (fs:691-695)
- *   sampler 1: getPWMOfRandomStartsWithBPV |> findBestMotifPositionsWithStartPositionsByPCV
- *              |> findBestMotifPositionsWithStartPositionByPCV, motifAmount = 1 (fs:876-879)
- * n_chains independent chains run concurrently (one warp each); chain c uses the uniform stream
- * (seed, chain_id_base + c) or uniforms[c * uniforms_per_chain ...]. Draw order inside a chain:
- * random init n ascending, i ascending skipping n (fs:595-598), then one draw per n for the
- * stochastic sweep (fs:851). Results stay on the device until gibbs_fetch.
- */
-/*
  * Replaces: the `positionProbabilityMatrix` argument of getMotifsWithBestPWMSOfPPM (fs:644-661) and of its callers
  * doSiteSamplingWithPPM (fs:703), getBestInformationContentOfPPM (fs:664), doMotifSamplingWithPPM (fs:1028),
  * getBestPWMSsOfPPM (fs:1002). ppm = double [k][4]: rows A,C,G,T of the reference's 49 x k matrix, entry j*4+b.
@@ -183,6 +172,20 @@ int32_t gibbs_set_start_ppm(gibbs_handle *h, const double *ppm_or_null, int32_t 
  */
 int32_t gibbs_set_start_state(gibbs_handle *h, int32_t n_chains, const int32_t *sites,
                               const double *scores);
+/*
+ * Replaces: one restart pipeline per chain --
+ *   sampler 0, background 0: getPWMOfRandomStartsWithBPV |> findBestMotifWithStartPosition
+ *              |> getLeftShiftedBestPWMSsWithBPV |> getRightShiftedBestPWMSsWithBPV (doSiteSamplingWithBPV, fs:691-695)
+ *   sampler 0, background 1: the same pipeline over getBestPWMSs with the drifting background
+ *              (doSiteSampling, fs:697-701; doSiteSamplingWithPPM, fs:703-707, after gibbs_set_start_ppm)
+ *   sampler 1, background 0: getPWMOfRandomStartsWithBPV |> findBestMotifPositionsWithStartPositionsByPCV
+ *              |> findBestMotifPositionsWithStartPositionByPCV, motifAmount = 1 (fs:876-879)
+ *   sampler 1, background 1: doMotifSampling (fs:1034-1038) / doMotifSamplingWithPPM (fs:1028-1032), motifAmount = 1
+ * n_chains independent chains (= restarts) run concurrently, a team of warps each; chain c uses the uniform stream
+ * (seed, chain_id_base + c) or uniforms[c * uniforms_per_chain ...], so its result does not depend on how many
+ * chains, launches or GPUs share the run. Draw order inside a chain: random init n ascending, i ascending skipping
+ * n (fs:595-598), then one draw per n for the stochastic sweep (fs:851). Results stay on the device until gibbs_fetch.
+ */
 int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chains,
                          int64_t chain_id_base, uint64_t seed, int32_t rng_mode,
                          const double *uniforms_or_null, int64_t uniforms_per_chain);
