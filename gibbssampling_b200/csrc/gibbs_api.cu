@@ -128,6 +128,8 @@ struct gibbs_handle {
     DevBuf<double> start_ppm;  // gibbs_set_start_ppm: [k][4]
     int32_t start_ppm_k = 0;   // 0 = none set
     DevBuf<int32_t> basecnt, maskcnt;
+    DevBuf<int32_t> ss;        // prefix tables [n][max_len + 2][4] of the ranking pass (null-sized when too large)
+    bool ss_valid = false;
     bool drift_valid = false;
     double drift_pc = 0;
     int32_t drift_alen = 0;
@@ -429,6 +431,20 @@ int32_t ensure_drift(gibbs_handle *h, const gibbs_params *p, int *launches) {
     CUDA_TRY(h->maskcnt.reserve((size_t)h->n));
     basecount_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(dev_seqs(h), h->basecnt.p, h->maskcnt.p);
     CUDA_TRY(cudaGetLastError());
+    // prefix tables of the ranking pass: int32 sums reach L^2 / 2, and 16 B per base are only worth keeping while they
+    // fit comfortably (C4: 320 MB); otherwise the ranking pass keeps its sliding counters
+    h->ss_valid = false;
+    const size_t ss_ints = (size_t)h->n * (size_t)(h->max_len + 2) * 4;
+    if (h->max_len <= 46000 && ss_ints * sizeof(int32_t) <= ((size_t)4 << 30)) {
+        if (h->ss.reserve(ss_ints) == cudaSuccess) {
+            prefix_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(dev_seqs(h), h->max_len + 2, reinterpret_cast<int4 *>(h->ss.p));
+            if (launches) *launches += 1;
+            h->ss_valid = true;
+        } else {
+            cudaGetLastError(); // not enough memory: fall back to the sliding counters
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 2;
     std::vector<int32_t> bc((size_t)h->n * 4);
     CUDA_TRY(cudaMemcpyAsync(bc.data(), h->basecnt.p, bc.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -654,7 +670,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->stats.release(); h->best.release();
     h->bg_g.release(); h->bg_sum.release(); h->bg_max.release(); h->bg_max_i.release();
     h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
-    h->pvals.release(); h->basecnt.release(); h->maskcnt.release(); h->gbuf.release(); h->start_ppm.release();
+    h->pvals.release(); h->basecnt.release(); h->maskcnt.release(); h->ss.release(); h->gbuf.release(); h->start_ppm.release();
     h->ctl.release(); h->resume.release(); h->pending.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -929,6 +945,8 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             m.c.pvals = m.pvals; // the random starts use the SiteSampler's drifting-background routines (drift_tables / drift_pick)
             m.c.basecnt = m.basecnt;
             m.c.maskcnt = nullptr;
+            m.c.ss = h->ss_valid ? h->ss.p : nullptr;
+            m.c.ss_stride = h->max_len + 2;
             memcpy(m.c.gcnt, m.gcnt, sizeof m.gcnt);
             m.c.alpha_pc = m.alpha_pc;
             m.c.pc = m.pc;
@@ -943,6 +961,8 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         a.pvals = h->pvals.p;
         a.basecnt = h->basecnt.p;
         a.maskcnt = h->n_masked > 0 ? h->maskcnt.p : nullptr;
+        a.ss = h->ss_valid ? h->ss.p : nullptr;
+        a.ss_stride = h->max_len + 2;
         memcpy(a.gcnt, h->gcnt, sizeof a.gcnt);
         a.alpha_pc = (double)p->alphabet_size * p->pseudocount; // float alphabet.Length * pseudoCount, fs:117
         a.pc = p->pseudocount;

@@ -83,6 +83,8 @@ struct ChainArgs {
     int32_t gcnt[4];
     double alpha_pc, pc;
     int32_t drift_fast_ok;    // the float32 ranking pass may be used
+    const int32_t *ss;        // [n][ss_stride][4] prefix tables of every sequence (prefix_kernel), or null
+    int32_t ss_stride;        // entries (int4) per sequence: max_len + 2
     // pause / resume at sweep boundaries: once few chains are still running they are continued by a
     // second launch with wider teams (see launch_chain_kp)
     int32_t *active;          // chains not finished yet

@@ -37,6 +37,29 @@ __global__ void basecount_kernel(DeviceSeqs s, int32_t *basecnt, int32_t *maskcn
     if (maskcnt) maskcnt[n] = m;
 }
 
+// ss[n][t] = sum_{u < t} P_n[u] with P_n[u] = base counts (A,C,G,T; other symbols skipped) of the first u bases of
+// sequence n, t = 0 .. len + 1: the prefix-of-prefix table of scan_drifting_tables. One thread per sequence (run once).
+__global__ void prefix_kernel(DeviceSeqs s, int stride, int4 *ss) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= s.n) return;
+    const uint32_t *row = s.packed + (size_t)n * s.row_words;
+    const uint32_t *mrow = s.mask ? s.mask + (size_t)n * s.row_words : nullptr;
+    int4 *out = ss + (size_t)n * stride;
+    const int L = s.len[n];
+    int4 P = make_int4(0, 0, 0, 0), S = make_int4(0, 0, 0, 0);
+    for (int t = 0; t <= L + 1 && t < stride; ++t) {
+        out[t] = S;                     // S = sum_{u < t} P[u]
+        S.x += P.x; S.y += P.y; S.z += P.z; S.w += P.w;
+        if (t < L) {                    // P becomes the counts of the first t + 1 bases
+            const int code = (row[t >> 4] >> ((t & 15) * 2)) & 3;
+            const bool masked = mrow && ((mrow[t >> 4] >> ((t & 15) * 2)) & 1);
+            if (!masked) {
+                P.x += code == 0; P.y += code == 1; P.z += code == 2; P.w += code == 3;
+            }
+        }
+    }
+}
+
 __global__ void pvals_kernel(int n, double pc, double den, double *pvals) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n) pvals[c] = __ddiv_rn(__dadd_rn((double)c, pc), den);

@@ -244,6 +244,87 @@ __device__ __forceinline__ bool scan_drifting_fast(const uint32_t *row, int W, i
     return true;
 }
 
+// The same ranking pass over per-sequence PREFIX TABLES: ss[t][b] = sum_{u < t} (number of base b among the first u
+// bases), a property of the sequence computed once (prefix_kernel). With P[t] = ss[t+1] - ss[t] the occurrences of a
+// window are P[w+k] - P[w] and the drifting sum over the windows before it is
+//   sum_{m <= w} occ_m = (ss[w+k+1] - ss[k]) - ss[w+1],
+// so no sliding counters, no pass over the lane's windows to seed them, no cross-lane prefix, and lanes take
+// interleaved windows (coalesced 16-byte table reads). Four loads and a dozen integer adds replace ~45 instructions
+// per window and eight live registers.
+template <int KP>
+__device__ __forceinline__ bool scan_drifting_tables(const uint32_t *row, const int4 *__restrict__ ss, int W, int k, const double *ppm,
+                                                     const float *pt, const int *f0, const int *cn, double pc, double alpha_pc,
+                                                     int lane, double &hv_out, int &w_out) {
+    const float ninf = __int_as_float(0xff800000);
+    const float pcf = (float)pc, apcf = (float)alpha_pc, kf = (float)k;
+    const int4 sk = __ldg(ss + k);
+    float M1 = ninf, M2 = ninf;
+    int w1 = 0;
+    for (int w = lane; w < W; w += 32) {
+        const int4 a0 = __ldg(ss + w), a1 = __ldg(ss + w + 1), b0 = __ldg(ss + w + k), b1 = __ldg(ss + w + k + 1);
+        const int occ[4] = {(b1.x - b0.x) - (a1.x - a0.x), (b1.y - b0.y) - (a1.y - a0.y), (b1.z - b0.z) - (a1.z - a0.z),
+                            (b1.w - b0.w) - (a1.w - a0.w)};
+        const int run[4] = {b1.x - sk.x - a1.x, b1.y - sk.y - a1.y, b1.z - sk.z - a1.z, b1.w - sk.w - a1.w};
+        float bg = 0.0f;
+        int sum = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int F = f0[b] + (w + 1) * cn[b] - run[b];
+            sum += F;
+            bg = fmaf((float)occ[b], lg2_normal((float)F + pcf), bg);
+        }
+        bg = fmaf(-kf, lg2_normal((float)sum + apcf), bg);
+        const uint64_t kmer = kmer_shared<KP>(row, w);
+        float mot = 0.0f;
+#pragma unroll
+        for (int p = 0; p < KP; ++p) mot += pt[p * 16 + ((uint32_t)(kmer >> (4 * p)) & 15u)];
+        const float a = mot - bg;
+        if (a > M1) {
+            M2 = M1;
+            M1 = a;
+            w1 = w;
+        } else if (a > M2) {
+            M2 = a;
+        }
+    }
+    float M = M1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) M = fmaxf(M, __shfl_xor_sync(FULL, M, o));
+    const float thr = M - DRIFT_MARGIN;
+    if (__ballot_sync(FULL, M2 >= thr)) return false;
+    unsigned cand = __ballot_sync(FULL, M1 >= thr);
+    double hv = 0.0;
+    int hw = INT32_MAX;
+    while (cand) { // cooperative re-scoring with the reference's own operations, as in scan_drifting_fast
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int wc = __shfl_sync(FULL, w1, src);
+        const int4 a1 = __ldg(ss + wc + 1), b1 = __ldg(ss + wc + k + 1);
+        const int run[4] = {b1.x - sk.x - a1.x, b1.y - sk.y - a1.y, b1.z - sk.z - a1.z, b1.w - sk.w - a1.w};
+        int F[4], sum = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            F[b] = f0[b] + (wc + 1) * cn[b] - run[b];
+            sum += F[b];
+        }
+        const double den = __dadd_rn((double)sum, alpha_pc);                       // fs:117
+        const int fb = lane == 0 ? F[0] : lane == 1 ? F[1] : lane == 2 ? F[2] : F[3];
+        const double q_lane = __ddiv_rn(__dadd_rn((double)fb, pc), den);             // fs:119, lanes 0-3 hold pcv[A,C,G,T]
+        const int b = lane < k ? base_at(row, wc + lane) : 0;
+        const double q = __shfl_sync(FULL, q_lane, b);
+        const double ratio = lane < k ? __ddiv_rn(ppm[lane * 4 + b], q) : 1.0;       // fs:286
+        double v = 1.0;
+        for (int j = 0; j < k; ++j) v = __dmul_rn(v, __shfl_sync(FULL, ratio, j));   // fs:292
+        if (better(v, wc, hv, hw)) {
+            hv = v;
+            hw = wc;
+        }
+    }
+    hv_out = hv;
+    w_out = hw;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the all-windows scan for a held-out sequence with symbols outside A,C,G,T (rare path, out of line)
 // ------------------------------------------------------------------------------------------------
@@ -364,17 +445,21 @@ __device__ __forceinline__ void drift_tables(const WarpTables &W, const int32_t 
 }
 
 // getBestPWMSs (fs:462-479) for the staged row; returns true when every window was scored in float64.
-// masked_n >= 0: the held-out sequence holds symbols outside A,C,G,T (a.s.mask != null)
+// masked_n >= 0: the held-out sequence holds symbols outside A,C,G,T (a.s.mask != null); seq = its index (prefix tables)
 template <int KP>
 __device__ __forceinline__ bool drift_pick(const WarpTables &W, const uint32_t *row, int Wn, int k, const ChainArgs &a, bool fast,
-                                           const int (&f0)[4], const int (&cn)[4], int lane, double &p, int &w, int masked_n = -1) {
+                                           const int (&f0)[4], const int (&cn)[4], int lane, double &p, int &w, int masked_n = -1,
+                                           int seq = -1) {
     if (masked_n >= 0) {
         scan_drifting_masked(row, a.s.mask + (size_t)masked_n * a.s.row_words, Wn, k, W.wcol, f0, cn, __ldg(a.maskcnt + masked_n), a.pc,
                              a.alpha_pc, lane, p, w);
         return true;
     }
     bool ranked = false;
-    if (fast)
+    if (fast && a.ss != nullptr && seq >= 0)
+        ranked = scan_drifting_tables<KP>(row, reinterpret_cast<const int4 *>(a.ss) + (size_t)seq * a.ss_stride, Wn, k, W.wcol,
+                                          reinterpret_cast<const float *>(W.ptab), f0, cn, a.pc, a.alpha_pc, lane, p, w);
+    else if (fast)
         ranked = scan_drifting_fast<KP>(row, Wn, k, W.wcol, reinterpret_cast<const float *>(W.ptab), f0, cn, a.pc, a.alpha_pc,
                                         lane, p, w);
     if (!ranked) scan_drifting(row, Wn, k, W.wcol, f0, cn, a.pc, a.alpha_pc, lane, p, w);

@@ -388,7 +388,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
                         if (MASKED && masked_n >= 0) own_mk = mask_kmer(a.s.mask, a.s.row_words, n, shifted_site(site_n, len_n, k, mode), k);
                         drift_tables<KP>(WT, S.total, true, own, k, a, false, fast, n, lane, f0, cn, own_mk);
                     }
-                    slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w, MASKED ? masked_n : -1);
+                    slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w, MASKED ? masked_n : -1, n);
                 } else {
                     if (phase == PH_INIT) {
                         random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);

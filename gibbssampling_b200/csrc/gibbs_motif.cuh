@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                     const bool fast = m.greedy_fast_ok && !given;
                     int f0[4], cn[4];
                     drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
-                    drift_pick<KP>(WT, row, W, k, a, fast, f0, cn, lane, p, w);
+                    drift_pick<KP>(WT, row, W, k, a, fast, f0, cn, lane, p, w, -1, n);
                 }
                 if (lane == 0) {
                     sites[n] = w;
