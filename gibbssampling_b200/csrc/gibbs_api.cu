@@ -248,15 +248,16 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
     // many sequences the grid-wide kernel is the only way to use all SMs (C4, 8 chains: 17.2 s -> 0.61 s).
     const bool init_wide = init_env ? init_env[0] != '0' : (a.n_chains < 4 * h->sm_count || a.s.n >= 4096);
     const bool masked = a.s.mask != nullptr; // symbols outside A,C,G,T: one launch of the MASKED instantiation (1 or 4 warps)
-    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide && !masked && !drift) {
+    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide && !masked) {
         const int smem = init_smem_bytes(a.s.row_words);
         if (smem <= 200 * 1024) {
-            int32_t rc = set_smem(init_kernel<KPV>, smem);
+            int32_t rc = drift ? set_smem(init_kernel<KPV, true>, smem) : set_smem(init_kernel<KPV, false>, smem);
             if (rc) return rc;
             const long long items = (long long)a.n_chains * a.s.n;
             long long grid = (items + INIT_WARPS - 1) / INIT_WARPS;
             if (grid > 4LL * h->sm_count) grid = 4LL * h->sm_count;
-            init_kernel<KPV><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
+            if (drift) init_kernel<KPV, true><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
+            else init_kernel<KPV, false><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
             CUDA_TRY(cudaGetLastError());
             a.phase_mask &= ~GIBBS_PHASE_INIT; // the chain kernel continues from the state just written
             h->run_extra_launches += 1;

@@ -199,7 +199,8 @@ __host__ __device__ inline int init_smem_bytes(int row_words) {
     return 64 + INIT_WARPS * 16 + INIT_WARPS * WARP_TABLE_BYTES + INIT_WARPS * 2 * row_words * 4;
 }
 
-template <int KP>
+// DRIFT = the data-derived background (getPWMOfRandomStarts fs:589-611, getMotifsWithBestPWMSOfPPM fs:644-661)
+template <int KP, bool DRIFT = false>
 static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -246,10 +247,19 @@ static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS)
         const int chain = (int)(item / N), n = (int)(item % N);
         const int Wn = __ldg(a.s.len + n) - k + 1;
         random_loo_counts_impl<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE), false>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lut, lane, WT.lgcol);
-        build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
         double p;
         int w;
-        const bool slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w); // (sets with masked symbols never get here)
+        bool slow;
+        if constexpr (DRIFT) {
+            int f0[4], cn[4];
+            const bool given = a.ppm_given != nullptr;
+            const bool fast = a.drift_fast_ok && !given;
+            drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
+            slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w, -1, n);
+        } else {
+            build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+            slow = pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w); // (sets with masked symbols never get here)
+        }
         if (lane == 0) {
             a.sites[(size_t)chain * N + n] = w;
             a.hv[(size_t)chain * N + n] = p;

@@ -132,3 +132,29 @@ def test_hand_over_stages_do_not_change_a_chain():
         score, pos, _ = O.site_step("do_site_sampling", S, k, 1e-4, rng=rng)
         assert big.sites[c].tolist() == pos.tolist(), f"chain {c}"
         np.testing.assert_allclose(big.scores[c], score, rtol=RTOL)
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+@pytest.mark.parametrize("shape", [(60, 64, 40, 9), (300, 90, None, 12)], ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
+def test_random_starts_same_on_both_kernels(shape, wide, monkeypatch):
+    """getPWMOfRandomStarts (fs:589-611) inside the chain kernel or as the grid-wide init kernel: both consume the
+    uniform stream as the oracle does."""
+    n, L, Lmin, k = shape
+    monkeypatch.setenv("GIBBS_B200_INIT_KERNEL", wide)
+    ps = planted_motif_set(n, L, k, seed=22, min_length=Lmin)
+    seqs = ps.sequences()
+    S = O.sources(seqs)
+    with GibbsEngine(seqs) as eng:
+        init = eng.run(make_params(k, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA, phase_mask=_abi.PHASE_INIT), 3,
+                       chain_id_base=5, seed=31, want_counts=False)
+        full = eng.run(make_params(k, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA), 3, chain_id_base=5, seed=31,
+                       want_counts=False)
+    assert init.stats["kernel_launches"] >= (2 if wide == "1" else 1)
+    for c in range(3):
+        rng, _ = O.make_rng(seed=31, chain=5 + c)
+        score, pos, _ = O.site_step("random_starts", S, k, 1e-4, rng=rng)
+        assert init.sites[c].tolist() == pos.tolist(), f"chain {c}"
+        np.testing.assert_allclose(init.scores[c], score, rtol=RTOL)
+        rng, _ = O.make_rng(seed=31, chain=5 + c)
+        score, pos, _ = O.site_step("do_site_sampling", S, k, 1e-4, rng=rng)
+        assert full.sites[c].tolist() == pos.tolist(), f"chain {c}"
