@@ -94,3 +94,23 @@ def test_motif_sampler_ppm_family_matches_oracle(case):
     got = MotifSampler.doMotifSamplingWithPPM(1, k, 1e-4, 0.0, DNA, seqs, ppm49, uniforms=u)
     assert [tuple(g.Positions) for g in got] == [tuple(p) for _, p in want]
     np.testing.assert_allclose([g.PWMS for g in got], [s for s, _ in want], rtol=RTOL)
+
+
+def test_script_flow_profile_from_gap_padded_consensus_then_site_sampling_with_ppm():
+    """fsx:505-512: a PPM built from aligned, gap-padded consensus sequences (dnaBases, Gap is a member) drives
+    doSiteSamplingWithPPM over gap-free genes. Only the A,C,G,T rows of the PPM can matter there."""
+    from gibbssampling_b200 import PositionMatrix as PM
+    from gibbssampling_b200.BioArray import ofNucleotideString
+    consensus = [ofNucleotideString(s) for s in ("-----cGTCcaGAA", "gGGAagCTCtgGAA", "tGAAgcTACagGAC", "cGAAggGCCgcGAC")]
+    k = len(consensus[0])
+    ppm49 = PM.getPositionProbabilityMatrix(len(consensus), DNA, 1e-4,
+                                           PM.fusePositionFrequencyMatrices(k, [PM.createPFMOf(s) for s in consensus]))
+    ps = planted_motif_set(7, 120, k, seed=77)
+    genes = ps.sequences()
+    S = O.sources(genes)
+    u = np.random.default_rng(8).random(draws_per_chain(7))
+    r, keep = O.make_rng(uniforms=u)
+    score, pos, _ = O.site_step("do_site_sampling_with_ppm", S, k, 1e-4, ppm=ppm49, rng=r)
+    got = SiteSampler.doSiteSamplingWithPPM(k, 1e-4, DNA, genes, ppm49, uniforms=u)
+    assert [p for _, p in got] == pos.tolist()
+    np.testing.assert_allclose([s for s, _ in got], score, rtol=RTOL)
