@@ -89,3 +89,46 @@ def createPCVOfSources(alphabet: Sequence, pseudoCount: float, sources: Sequence
     """The fixed background a user of the WithBPV family would build."""
     fused = fuseFrequencyVectors(alphabet, (createFCVOf(s) for s in sources))
     return createNormalizedPCVOfFCV(alphabet, pseudoCount, fused)
+
+
+# ---- the remaining functions of the reference module (fs:43-124), host side, for callers and for inspection ----
+def increaseInPlaceFCV(bioItem, frequencyCompositeVector: FrequencyCompositeVector) -> FrequencyCompositeVector:
+    """fs:43-46."""
+    frequencyCompositeVector[bioItem] = frequencyCompositeVector[bioItem] + 1
+    return frequencyCompositeVector
+
+
+def createFCVWithout(motifLength: int, position: int, resSource) -> FrequencyCompositeVector:
+    """fs:73-76: counts of a sequence outside the segment [position, position + motifLength)."""
+    s = _as_bytes(resSource)
+    return createFCVOf(s[:max(position, 0)] + s[position + motifLength:])
+
+
+def increaseInPlaceFCVOf(resSources, backGroundCounts: FrequencyCompositeVector) -> FrequencyCompositeVector:
+    """fs:79-81: adds every symbol of the sequence to the SAME vector (the in-place mutation behind quirk A.6-1)."""
+    backGroundCounts.Array += createFCVOf(resSources).Array
+    return backGroundCounts
+
+
+def substractSegmentCountsFrom(source, fcVector: FrequencyCompositeVector) -> FrequencyCompositeVector:
+    """fs:84-88: max(count - 1, 0) per symbol of the segment. The result WRAPS the argument's array (fs:85), so the
+    argument is mutated too -- the aliasing that makes the background drift from window to window."""
+    out = FrequencyCompositeVector.__new__(FrequencyCompositeVector)
+    out.Array = fcVector.Array
+    for sym in _as_bytes(source):
+        c = int(fcVector[sym])
+        out[sym] = c - 1 if c - 1 > 0 else 0
+    return out
+
+
+def createPCVOf(caArray: FrequencyCompositeVector) -> ProbabilityCompositeVector:
+    """fs:109-112: int -> float copy."""
+    return ProbabilityCompositeVector(caArray.Array.astype(np.float64))
+
+
+def calculateSegmentScoreBy(pcv: ProbabilityCompositeVector, bioItems) -> float:
+    """fs:123-124: ((1. * pcv[b0]) * pcv[b1]) * ..., the background-only probability of a window (fs:776)."""
+    value = 1.0
+    for sym in _as_bytes(bioItems):
+        value = value * float(pcv[sym])
+    return value

@@ -57,3 +57,38 @@ def test_profile_from_gap_padded_consensus_like_the_script():
     col0 = {ch: ppm[ord(ch) - 42, 0] for ch in "ACGT-"}
     den = 3 + 5 * 1e-4
     assert col0["-"] == (1 + 1e-4) / den and col0["G"] == (1 + 1e-4) / den and col0["T"] == (1 + 1e-4) / den and col0["A"] == 1e-4 / den
+
+
+def test_composite_vector_helpers_reproduce_the_drifting_background():
+    """createFCVWithout / increaseInPlaceFCVOf / substractSegmentCountsFrom / createNormalizedPCVOfFCV composed as
+    getBestPWMSs composes them (fs:470-474) give the oracle's drifting-background window scores."""
+    from gibbssampling_b200 import CompositeVector as CV
+    rng = np.random.default_rng(5)
+    n, L, k, pc = 5, 30, 6, 1e-4
+    seqs = ["".join(rng.choice(list("ACGT"), size=L)).encode() for _ in range(n)]
+    S = O.sources(seqs)
+    sites = rng.integers(0, L - k + 1, size=n).astype(np.int32)
+    h = 1
+    pfm = O.loo_pfm(S, sites, h, k)
+    ppm49 = np.asarray(O.ppm_of_pfm(pfm, n - 1, pc, b"ATGC-")).reshape(49, k)
+    fcv = CV.fuseFrequencyVectors(DNA, [CV.createFCVWithout(k, int(sites[i]), seqs[i]) for i in range(n) if i != h])
+    best = (0.0, 0)
+    for w in range(L - k + 1):                                            # fs:466-478
+        seg = seqs[h][w:w + k]
+        CV.increaseInPlaceFCVOf(seqs[h], fcv)
+        tmp = CV.substractSegmentCountsFrom(seg, fcv)
+        assert tmp.Array is fcv.Array                                      # the aliasing of fs:85
+        pcv = CV.createNormalizedPCVOfFCV(DNA, pc, tmp)
+        score = PM.calculateSegmentScoreBy(PM.createPositionWeightMatrix(DNA, pcv, ppm49), seg)
+        if score > best[0]:
+            best = (score, w)
+    raws = []
+    fcv2 = CV.fuseFrequencyVectors(DNA, [CV.createFCVWithout(k, int(sites[i]), seqs[i]) for i in range(n) if i != h])
+    for w in range(L - k + 1):
+        CV.increaseInPlaceFCVOf(seqs[h], fcv2)
+        pcv = CV.createNormalizedPCVOfFCV(DNA, pc, CV.substractSegmentCountsFrom(seqs[h][w:w + k], fcv2))
+        raws.append(PM.calculateSegmentScoreBy(PM.createPositionWeightMatrix(DNA, pcv, ppm49), seqs[h][w:w + k]))
+    want_score, want_pos, want_raw, _ = O.best_pwms(seqs[h], k, pc, O.loo_fcv(S, sites, h, k), ppm49)
+    assert raws == want_raw.tolist()                                        # bit for bit, window by window
+    assert best[1] == want_pos and np.log(best[0]) / np.log(2.0) == pytest.approx(want_score, rel=1e-12)
+    assert CV.calculateSegmentScoreBy(CV.ProbabilityCompositeVector.ofACGT(.1, .2, .3, .4), b"ACGTA") == ((((1.0 * .1) * .2) * .3) * .4) * .1
