@@ -952,7 +952,11 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             m.c.alpha_pc = m.alpha_pc;
             m.c.pc = m.pc;
         }
-        if (getenv("GIBBS_B200_MOTIF_EXACT")) m.greedy_fast_ok = 0; // measurement / test switch: every window in float64
+        m.roulette_scan_ok = 1;
+        if (getenv("GIBBS_B200_MOTIF_EXACT")) { // measurement / test switch: every window in float64, sequential roulette walk
+            m.greedy_fast_ok = 0;
+            m.roulette_scan_ok = 0;
+        }
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_motif(h, m);
         if (rc) return rc;

@@ -38,6 +38,7 @@ struct MotifArgs {
     double alpha_pc, pc;
     double *gbuf;          // [chains][wstride] background window probabilities of the current held-out sequence
     int32_t greedy_fast_ok; // greedy sweeps may rank windows in fixed point (no float64 under/overflow possible, pc > 0)
+    int32_t roulette_scan_ok; // stochastic sweep may locate the roulette bucket with a warp scan (0 = always walk)
 };
 
 // one thread per sequence
@@ -111,9 +112,9 @@ __device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint3
 // rouletteWheelSelection (fs:746-754) over [W background entries] ++ [candidates]: exact sequential
 // float64 semantics (sum from 0.0 in list order, weights PWMS/sum, inclusive bounds on both sides).
 // Returns false when the pick ran past the list (the reference throws, fs:753).
-__device__ __forceinline__ bool motif_roulette(const double *g, double gsum, int W, const double *cand_l,
-                                               const int32_t *cand_w, int n_cand, double pick, int lane, double &pwms_out,
-                                               int &site_out) {
+__device__ __noinline__ bool motif_roulette_exact(const double *g, double gsum, int W, const double *cand_l,
+                                                  const int32_t *cand_w, int n_cand, double pick, int lane, double &pwms_out,
+                                                  int &site_out) {
     double sum = gsum; // the background entries come first in the list; gsum was accumulated in that order
     for (int i = 0; i < n_cand; ++i) sum = __dadd_rn(sum, cand_l[i]);
     double acc = 0.0;
@@ -153,6 +154,79 @@ __device__ __forceinline__ bool motif_roulette(const double *g, double gsum, int
 // window's product is so close to the maximum that both round to the same log2; every window that close lies in a
 // chunk the ranking pass re-scores anyway, so the check is a comparison there, and such a case (or anything else the
 // ranking pass cannot decide) falls back to the all-windows candidate list below.
+// Inverse-CDF selection with a warp prefix sum, exact by construction. The reference walks the list and takes the
+// first item whose float64 running sum reaches the pick (fs:746-754); that running sum is order-dependent, so a
+// parallel scan cannot reproduce its bits -- but it can locate the bucket: scan and walk differ by at most
+// (items + 64) * 2^-52 of the total mass, so when the pick is farther than four times that from both edges of the
+// bucket the scan found, the walk must stop in the same bucket. Otherwise (probability ~1e-11 per pick), or when an
+// item is negative (a cut-off below 0 admits negative PWMS; the walk's condition is then not monotone), the exact
+// sequential walk runs. Lanes take contiguous blocks of the list, so lane order is list order.
+__device__ __forceinline__ bool motif_roulette(const double *g, double gsum, int W, const double *cand_l, const int32_t *cand_w,
+                                               int n_cand, double pick, int lane, double &pwms_out, int &site_out,
+                                               bool scan_ok = true) {
+    if (!scan_ok) return motif_roulette_exact(g, gsum, W, cand_l, cand_w, n_cand, pick, lane, pwms_out, site_out);
+    const int total = W + n_cand;
+    const int B = (total + 31) >> 5;
+    const int i0 = min(total, lane * B), i1 = min(total, i0 + B);
+    auto item = [&](int i) { return i < W ? g[i] : cand_l[i - W]; };
+    double part = 0.0;
+    bool negative = false;
+    for (int i = i0; i < i1; ++i) {
+        const double v = item(i);
+        negative |= !(v >= 0.0);
+        part += v;
+    }
+    double incl = part; // inclusive scan of the block sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const double sum = __shfl_sync(FULL, incl, 31);
+    bool decided = false;
+    if (!__ballot_sync(FULL, negative) && sum > 0.0 && sum < INFINITY) {
+        const double eps = 4.0 * (double)(total + 64) * 0x1p-52;
+        const double target = pick * sum;                    // pick <= prefix / sum  <=>  pick * sum <= prefix (up to eps)
+        const double before = incl - part;
+        const unsigned holds = __ballot_sync(FULL, i0 < i1 && target <= incl); // first lane whose block reaches the pick
+        if (holds) {
+            const int src = __ffs(holds) - 1;
+            int idx = -1;
+            double lo = 0.0, hi = 0.0;
+            if (lane == src) {
+                double acc = before;
+                for (int i = i0; i < i1; ++i) {
+                    const double nxt = acc + item(i);
+                    if (target <= nxt) {
+                        idx = i;
+                        lo = acc;
+                        hi = nxt;
+                        break;
+                    }
+                    acc = nxt;
+                }
+            }
+            idx = __shfl_sync(FULL, idx, src);
+            lo = __shfl_sync(FULL, lo, src);
+            hi = __shfl_sync(FULL, hi, src);
+            const double tol = eps * sum;
+            // clear of both edges: lo + tol < target < hi - tol (idx = 0 has no lower edge: the walk starts at 0 <= pick)
+            if (idx >= 0 && target < hi - tol && (idx == 0 || target > lo + tol)) {
+                if (idx < W) {
+                    pwms_out = g[idx];
+                    site_out = -1;
+                } else {
+                    pwms_out = cand_l[idx - W];
+                    site_out = cand_w[idx - W];
+                }
+                decided = true;
+            }
+        }
+    }
+    if (decided) return true;
+    return motif_roulette_exact(g, gsum, W, cand_l, cand_w, n_cand, pick, lane, pwms_out, site_out);
+}
+
 template <int KP, int CH>
 __device__ __forceinline__ bool pick_unique_argmax_ch(const WarpTables &T, const uint32_t *row, int W, int k, int lane,
                                                       double &hv_out, int &w_out) {
@@ -390,7 +464,8 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
                     } else {
                         u = ((int64_t)d < a.uniforms_per_chain) ? __ldg(a.uniforms + (size_t)chain * a.uniforms_per_chain + d) : 0.0;
                     }
-                    const bool ok = motif_roulette(g_n, gsum_n, W, cand_l, cand_w, n_cand, u, lane, new_pw, new_site);
+                    const bool ok = motif_roulette(g_n, gsum_n, W, cand_l, cand_w, n_cand, u, lane, new_pw, new_site,
+                                                   m.roulette_scan_ok != 0);
                     if (!ok) {
                         if (lane == 0) atomicExch(m.error, 1);
                         new_pw = pw_n;
