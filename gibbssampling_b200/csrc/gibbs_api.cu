@@ -795,8 +795,9 @@ int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldo
                             double *pwms_out, int32_t *site_out) {
     int32_t rc = check_params(h, p);
     if (rc) return rc;
+    if (p->background != GIBBS_BG_FIXED) return fail(GIBBS_ERR_UNSUPPORTED, "gibbs_pick_roulette takes a fixed background (WithPCV)");
     if (heldout < 0 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
-    if (h->n_masked > 0) return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler with a fixed background only");
+    if (h->n_masked > 0) return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler only");
     rc = set_device(h);
     if (rc) return rc;
     rc = stage_sites(h, sites, heldout, p->k);

@@ -292,6 +292,10 @@ def test_errors_cross_the_boundary_as_status_codes():
             eng.run(make_params(2, 1e-4, 5, [0.25] * 4, phase_mask=_abi.PHASE_GREEDY), 1)  # no start state
         ok = eng.run(make_params(3, 1e-4, 5, [0.25] * 4), 2, seed=1)
         assert ok.sites.shape == (2, 2)
+        with pytest.raises(_abi.GibbsUnsupportedError):   # the primitives are the WithBPV functions: fixed background only
+            eng.pick_argmax([0, 0], 0, make_params(3, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA))
+        with pytest.raises(_abi.GibbsUnsupportedError):
+            eng.window_scores([0, 0], 0, make_params(3, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA))
 
 
 def test_single_sequence_and_exact_length():
