@@ -183,3 +183,76 @@ module SiteSampler =
     /// fs:644-661
     let getMotifsWithBestPWMSOfPPM motifLength pseudoCount alphabet sources (ppM:PositionMatrix.PositionProbabilityMatrix) =
         (Native.runChainsWith (Some ppM) 1 1 (seedOf None) motifLength pseudoCount alphabet sources None None |> fst).[0]
+
+module MotifSampler =
+
+    /// fs:712-716 (kept as in the reference)
+    type MotifIndex = { PWMS : float; Positions : int list }
+    let createMotifIndex pwms pos = { PWMS = pwms; Positions = pos }
+
+    let private seedOf (seed:uint64 option) = defaultArg seed (uint64 DateTime.Now.Ticks)
+
+    /// sampler = 1 (include/gibbs_b200.h); motifAmount must be 1 (combinations of windows, fs:727-742, are not built)
+    let private run (phaseMask:int) (nChains:int) seed (motifAmount:int) k pc (cutOff:float) alphabet sources
+                    (pcv:ProbabilityCompositeVector option) (ppM:PositionMatrix.PositionProbabilityMatrix option) (start:MotifIndex[] option) =
+        if motifAmount <> 1 then raise (NotSupportedException "motifAmount >= 2 is not built (GIBBS_ERR_UNSUPPORTED)")
+        let buf, offsets = Native.flatten sources
+        let mutable h = IntPtr.Zero
+        Native.check (Native.gibbs_create(buf, offsets, sources.Length, 0, &h))
+        try
+            let n = sources.Length
+            match start with
+            | Some st ->   // Positions [] -> site -1 (fs:796: a sequence may have no site)
+                let sites  = Array.init (nChains * n) (fun i -> match st.[i % n].Positions with p :: _ -> p | [] -> -1)
+                let scores = Array.init (nChains * n) (fun i -> st.[i % n].PWMS)
+                Native.check (Native.gibbs_set_start_state(h, nChains, sites, scores))
+            | None -> ()
+            match ppM with
+            | Some m -> Native.check (Native.gibbs_set_start_ppm(h, Native.flattenPPM k m, k))
+            | None -> ()
+            let mutable p = Native.makeParams k pc alphabet pcv phaseMask
+            p.sampler <- 1; p.cutoff <- cutOff
+            let sites, scores, sums = Array.zeroCreate (nChains * n), Array.zeroCreate (nChains * n), Array.zeroCreate nChains
+            let mutable best = 0
+            let mutable stats = Native.GibbsRunStats()
+            Native.check (Native.gibbs_run(h, &p, nChains, 0L, seed, 0, null, 0L, sites, scores, sums, &best, null, &stats))
+            Array.init nChains (fun c ->
+                Array.init n (fun i -> createMotifIndex scores.[c * n + i] (if sites.[c * n + i] >= 0 then [sites.[c * n + i]] else [])))
+        finally
+            Native.gibbs_destroy h |> ignore
+
+    /// fs:828-853: the synchronous roulette sweep (GIBBS_PHASE_STOCHASTIC = 16)
+    let findBestMotifPositionsWithStartPositionsByPCV motifAmount motifLength pseudoCount cutOff alphabet sources (pcv:ProbabilityCompositeVector) (motifMem:MotifIndex[]) =
+        (run 16 1 (seedOf None) motifAmount motifLength pseudoCount cutOff alphabet sources (Some pcv) None (Some motifMem)).[0]
+    /// fs:788-822: greedy in-place sweeps (GIBBS_PHASE_MOTIF_GREEDY = 32)
+    let findBestMotifPositionsWithStartPositionByPCV motifAmount motifLength pseudoCount cutOff alphabet sources (pcv:ProbabilityCompositeVector) (motifMem:MotifIndex[]) =
+        (run 32 1 0UL motifAmount motifLength pseudoCount cutOff alphabet sources (Some pcv) None (Some motifMem)).[0]
+    /// fs:876-879
+    let doMotifSamplingWithPCV motifAmount motifLength pseudoCount cutOff alphabet sources (pcv:ProbabilityCompositeVector) =
+        (run 0 1 (seedOf None) motifAmount motifLength pseudoCount cutOff alphabet sources (Some pcv) None None).[0]
+    /// fs:1034-1038
+    let doMotifSampling motifAmount motifLength pseudoCount cutOff alphabet sources =
+        (run 0 1 (seedOf None) motifAmount motifLength pseudoCount cutOff alphabet sources None None None).[0]
+    /// fs:1028-1032
+    let doMotifSamplingWithPPM motifAmount motifLength pseudoCount cutOff alphabet sources (ppM:PositionMatrix.PositionProbabilityMatrix) =
+        (run 0 1 (seedOf None) motifAmount motifLength pseudoCount cutOff alphabet sources None (Some ppM) None).[0]
+
+    /// fs:856-881 / fs:973-998: the promote-or-restart loop replayed over numberOfRepetitions + 1 parallel restarts
+    let private restartLoop (numberOfRepetitions:int) (restarts:MotifIndex[][]) =
+        let mutable next = 0
+        let ic (x:MotifIndex[]) = x |> Array.map (fun item -> item.PWMS) |> Array.sum
+        let rec loop (n:int) (acc:MotifIndex[]) (bestPWMS:MotifIndex[]) =
+            if n > numberOfRepetitions then bestPWMS
+            elif acc = bestPWMS then bestPWMS
+            elif ic acc > ic bestPWMS then loop (n + 1) [||] (if Array.isEmpty acc then bestPWMS else acc)
+            else
+                let pwms = restarts.[next]
+                next <- next + 1
+                loop (n + 1) pwms bestPWMS
+        loop 0 [||] [|createMotifIndex 0. []|]
+    let findBestInormationContentContainingMotifsWithPCV numberOfRepetitions motifAmount motifLength pseudoCount cutOff alphabet sources (pcv:ProbabilityCompositeVector) =
+        run 0 (numberOfRepetitions + 1) (seedOf None) motifAmount motifLength pseudoCount cutOff alphabet sources (Some pcv) None None
+        |> restartLoop numberOfRepetitions
+    let getMotifsWithBestInformationContents numberOfRepetitions motifAmount motifLength pseudoCount cutOff alphabet sources =
+        run 0 (numberOfRepetitions + 1) (seedOf None) motifAmount motifLength pseudoCount cutOff alphabet sources None None None
+        |> restartLoop numberOfRepetitions
