@@ -44,7 +44,7 @@ FAMILIES = {
     "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts", "gibbs::chain_kernel",
             "do_site_sampling_with_bpv"),
     "data": ("SiteSampler restarts with the data-derived drifting background (doSiteSampling, fs:697)",
-             "data-derived, rebuilt per window (fs:470-473)", "gibbs::drift_kernel", "do_site_sampling"),
+             "data-derived, rebuilt per window (fs:470-473)", "gibbs::chain_kernel<KP, T, MASKED, DRIFT = true>", "do_site_sampling"),
     "motif": ("MotifSampler m = 1 restarts with a fixed background (doMotifSamplingWithPCV, fs:876), cutOff 0",
               "fixed pcv, whole-set base counts", "gibbs::motif_kernel", None),
     "motif-data": ("MotifSampler m = 1 restarts with the data-derived background (doMotifSampling, fs:1034), cutOff 0",

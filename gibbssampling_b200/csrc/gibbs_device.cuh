@@ -86,7 +86,7 @@ struct ChainArgs {
     const int32_t *ss;        // [n][ss_stride][4] prefix tables of every sequence (prefix_kernel), or null
     int32_t ss_stride;        // entries (int4) per sequence: max_len + 2
     // pause / resume at sweep boundaries: once few chains are still running they are continued by a
-    // second launch with wider teams (see launch_chain_kp)
+    // following launches with wider teams: 4 -> 8 -> 16 warps per chain (see launch_chain_kp)
     int32_t *active;          // chains not finished yet
     int32_t pause_below;      // pause when *active <= pause_below (0 = never)
     int32_t from_list;        // 1 = this launch continues the chains listed in pending_in

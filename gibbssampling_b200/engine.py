@@ -145,7 +145,7 @@ class GibbsEngine:
         _abi.check(self._lib.gibbs_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def set_team_warps(self, warps: int) -> None:
-        """Tuning knob: warps per chain (0 = automatic, 1 or 4)."""
+        """Tuning knob: warps per chain (0 = automatic with hand-over stages; 1, 4, 8 or 16 = one launch of that size)."""
         _abi.check(self._lib.gibbs_set_team_warps(self._h, C.c_int32(warps)))
 
     def synchronize(self) -> None:
