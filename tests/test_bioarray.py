@@ -24,3 +24,20 @@ def test_every_kept_symbol_indexes_the_49_slot_tables():
         symbolIndex(ord("a"))
     with pytest.raises(IndexError):
         symbolIndex(ord(" "))
+
+
+def test_parser_properties():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.text(alphabet=st.characters(min_codepoint=0, max_codepoint=255), max_size=80))
+    def check(s):
+        out = ofNucleotideString(s)
+        assert all(c in NUCLEOTIDE_SYMBOLS for c in out)                   # only nucleotide symbols survive
+        assert ofNucleotideString(out) == out                              # idempotent
+        assert ofNucleotideString(s.lower()) == ofNucleotideString(s.upper()) or any(ord(c) > 127 for c in s)
+        assert len(out) <= len(s)
+        keep = [c.upper() for c in s if c.upper().encode("latin-1", "ignore") and c.upper().encode("latin-1", "ignore") in [bytes([x]) for x in NUCLEOTIDE_SYMBOLS]]
+        assert out.decode() == "".join(keep)
+
+    check()

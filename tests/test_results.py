@@ -69,3 +69,23 @@ def test_profile_rejects_bad_shapes():
         Results.motifProfile(np.zeros((3, 5)), 4, 1e-4, 5, [0.25] * 4)
     with pytest.raises(ValueError):
         Results.motifProfile(np.zeros((3, 4)), 4, 1e-4, 5, [0.25] * 3)
+
+
+def test_count_by_positions_matches_a_naive_count():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.lists(st.integers(0, 3), min_size=2, max_size=2), min_size=0, max_size=30))
+    def check(vectors):
+        results = [[(0.5, p) for p in v] for v in vectors]
+        got = Results.countByPositions(results)
+        keys = [tuple(v) for v in vectors]
+        assert sum(c for _, c in got) == len(vectors)
+        assert {k: c for k, c in got} == {k: keys.count(k) for k in set(keys)}
+        counts = [c for _, c in got]
+        assert counts == sorted(counts, reverse=True)
+        for (k1, c1), (k2, c2) in zip(got, got[1:]):                       # stable: equal counts keep first-seen order
+            if c1 == c2:
+                assert keys.index(k1) < keys.index(k2)
+
+    check()
