@@ -39,6 +39,8 @@ CONFIGS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step (ncu --set full, round 1)
 NCU_DRAM_BYTES_PER_STEP = int((0.316672 + 1.589760 + 3.313920 + 0.000000 + 1.631232 + 0.003328) * 1e6)
+NCU_DRAM_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step, "
+                   "profiles/r01_ncu_c2_final_summary.txt")
 # --family: which reference family the step runs (the default is the BASELINE.json workload)
 FAMILIES = {
     "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts", "gibbs::chain_kernel",
@@ -65,6 +67,17 @@ def algorithmic_hbm_bytes_per_site_update(length: int) -> float:
     return float((length + 3) // 4 + 8)
 
 
+def workload_config(cfg_name: str, cfg, family: str, chains: int) -> dict:
+    """The `config` object: identical for the GPU arm and the reference arm (the driver compares them)."""
+    n, length, k, _, shifts = cfg
+    fam_text, fam_bg, _, _ = FAMILIES[family]
+    return {"workload": f"{cfg_name}: {n} seqs x {length} bp, k={k}, {chains} chains/GPU, {fam_text}"
+                        + ("" if family.startswith("motif") else
+                           f" (random starts + greedy sweeps + {'left/right shift sweeps' if shifts else 'no shifts'})"),
+            "family": family, "chains_per_gpu": chains, "pseudocount": PSEUDOCOUNT, "alphabet_size": ALPHABET_SIZE,
+            "background": fam_bg}
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
 
@@ -72,8 +85,10 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index = index
+    def __init__(self, indices):
+        """indices: the GPUs of this job. ONE sampler process for all of them (rank 0 runs it): every extra nvidia-smi
+        polling the driver at 10 Hz can stall kernel launches of every rank for a moment."""
+        self.index = ",".join(str(i) for i in indices)
         self.proc = None
         self.lines: list[str] = []
 
@@ -106,7 +121,8 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        lines = self.lines[max(first - 1, 0): (last + 2) if last is not None else None] or self.lines[-2:]
+        ng = self.index.count(",") + 1      # one line per GPU per sample
+        lines = self.lines[max(first - ng, 0): (last + 2 * ng) if last is not None else None] or self.lines[-2 * ng:]
         for line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -174,35 +190,46 @@ def cpu_sample(ps, k, bg, *, threads: int, full_restart: bool, seed: int, chain_
 
 def run_reference_arm(args, cfg_name, cfg) -> None:
     """`--impl reference`: the reference's CPU algorithm on the box's host cores. The F# cannot run here
-    (no .NET runtime in the image or on the GPU box), so this times the oracle port with all host threads."""
+    (no .NET runtime in the image or on the GPU box), so this times the oracle port -- its FAITHFUL mode: from-scratch
+    leave-one-out rebuilds and a PWM per window like GibbsSampling.fs -- with all host threads. Same work as the GPU
+    arm: whole restarts of the family's pipeline (random starts, greedy sweeps to convergence, left and right shift
+    sweeps) on the same synthetic set, chain ids taken from the same range; one step = one restart per host thread
+    (a bounded sample of the step's `chains` restarts)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from gibbssampling_b200.synthetic import background_of, planted_motif_set
 
     n, length, k, chains, shifts = cfg
+    if args.chains:
+        chains = args.chains
+    if args.family.startswith("motif"):
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU port times the SiteSampler families only"}), flush=True)
+        return
     ps = planted_motif_set(n, length, k, seed=SEED)
     bg = background_of(ps.ascii, PSEUDOCOUNT, ALPHABET_SIZE)
     cores = os.cpu_count() or 1
+    # C3 / C4 restarts take hours in the faithful mode: there a step is one random-start sweep per thread
+    full = n * n * length <= 2_000_000_000
     for w in range(args.warmup):
-        cpu_sample(ps, k, bg, threads=cores, full_restart=False, seed=SEED, chain_base=w * cores)
+        cpu_sample(ps, k, bg, threads=cores, full_restart=full, seed=SEED, chain_base=(w * cores) % max(chains, 1), family=args.family)
     tot_t = tot_w = tot_u = 0.0
     for s in range(args.steps):
-        dt, ws, us = cpu_sample(ps, k, bg, threads=cores, full_restart=False, seed=SEED,
-                                chain_base=(args.warmup + s) * cores)
+        dt, ws, us = cpu_sample(ps, k, bg, threads=cores, full_restart=full, seed=SEED,
+                                chain_base=((args.warmup + s) * cores) % max(chains, 1), family=args.family)
         tot_t += dt
         tot_w += ws
         tot_u += us
     value = tot_w / tot_t
-    sample = (f"per step: one getPWMOfRandomStartsWithBPV sweep (fs:412, {n} site updates, from-scratch PWM per "
-              f"site update and per window like the F#) per host thread, {cores} threads; oracle port (C, -O2)")
+    what = (f"whole {FAMILIES[args.family][3]} restarts" if full else "one random-start sweep (fs:412) of a restart (whole restarts take hours at this size)")
+    sample = (f"per step: {what}, one per host thread ({cores} threads, {int(tot_u / max(args.steps, 1))} site updates per step, "
+              f"from-scratch PWM per site update and per window like the F#); oracle port (C, -O2, faithful mode)")
     line = {
         "impl": "reference", "metric": "gibbs_window_scores_per_sec", "value": value, "unit": "window-scores/s",
         "site_updates_per_sec": tot_u / tot_t, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic planted-motif DNA (seed 0xB200)",
-        "config": {"workload": f"{cfg_name}: {n} seqs x {length} bp, k={k}, SiteSampler WithBPV restarts",
-                   "pseudocount": PSEUDOCOUNT, "alphabet_size": ALPHABET_SIZE},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic planted-motif DNA (Philox key 0xB200, 10% planted-base mutation)",
+        "config": workload_config(cfg_name, cfg, args.family, chains),
         "cpu_baseline": {"value": value, "unit": "window-scores/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "window-scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -218,7 +245,7 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
     import torch
     import torch.distributed as dist
 
-    from gibbssampling_b200 import SiteSampler
+    from gibbssampling_b200 import _abi
     from gibbssampling_b200.distributed import allgather_best
     from gibbssampling_b200.engine import GibbsEngine, make_params, measure_smem_bandwidth
     from gibbssampling_b200.synthetic import background_of, planted_motif_set
@@ -240,13 +267,15 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
         chains = args.chains
     ps = planted_motif_set(n, length, k, seed=SEED)
     bg = background_of(ps.ascii, PSEUDOCOUNT, ALPHABET_SIZE)
-    from gibbssampling_b200 import _abi
+
+    def params_of(family: str):
+        return make_params(k, PSEUDOCOUNT, ALPHABET_SIZE, bg, phase_shifts=shifts,
+                           background=_abi.GIBBS_BG_DATA if family in ("data", "motif-data") else _abi.GIBBS_BG_FIXED,
+                           sampler=_abi.GIBBS_MOTIF_SAMPLER if family.startswith("motif") else _abi.GIBBS_SITE_SAMPLER,
+                           cutoff=0.0)
+
     fam_text, fam_bg, fam_kernel, fam_oracle = FAMILIES[args.family]
-    params = make_params(k, PSEUDOCOUNT, ALPHABET_SIZE, bg, phase_shifts=shifts,
-                         background=_abi.GIBBS_BG_DATA if args.family in ("data", "motif-data") else _abi.GIBBS_BG_FIXED,
-                         sampler=_abi.GIBBS_MOTIF_SAMPLER if args.family.startswith("motif") else _abi.GIBBS_SITE_SAMPLER,
-                         cutoff=0.0)
-    windows = length - k + 1
+    params = params_of(args.family)
 
     # pinned host copies of the inputs (e2e path uploads them every step)
     host_ascii = torch.empty(ps.ascii.size, dtype=torch.uint8, pin_memory=True)
@@ -260,109 +289,130 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
     eng.set_stream(stream.cuda_stream)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")  # > 126 MB L2
     chain_base = rank * chains
+    reps = chains - 1                        # numberOfRepetitions of the restart loop the step's restarts feed (fs:434)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step(step: int):
-        """hot path with inputs resident in HBM; ends with the all_gather of each GPU's best result"""
-        eng.run_device(params, chains, chain_id_base=chain_base, seed=SEED + step)
-
-    def finish_step():
-        res = eng.fetch(want_sites=True, want_scores=True, want_counts=False)
-        b = res.best_chain
+    def finish_step(e):
+        """the restart loop (fs:435-459) on the device; only the winner's rows come back; N > 1: one all_gather"""
+        best = e.fetch_best(reps, pinned=True)
         if world > 1:
-            allgather_best(float(res.sums[b]), chain_base + b, res.sites[b], res.scores[b])
-        return res
+            allgather_best(best.total, chain_base + max(best.restart, 0), best.sites, best.scores)
+        return best
 
-    sampler = ClockSampler(local_rank)   # started early (nvidia-smi needs a moment); samples are cut to the timed region
-    sampler.start()
+    def timed_steps(e, prm, n_steps, seed0):
+        """n_steps device-resident steps, each inside its own CUDA-event window on the launch stream (L2 flushed
+        before the window opens). Returns (sum of windows in ms, per-step stats)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        stats = []
+        for s_ in range(n_steps):
+            flush.fill_(s_)                     # L2 flush between steps, outside the per-step event window
+            ev[s_][0].record(stream)
+            e.run_device(prm, chains, chain_id_base=chain_base, seed=seed0 + s_)
+            ev[s_][1].record(stream)
+            stats.append(finish_step(e).stats)  # sync + D2H of the winner (not inside the event window)
+        return [a_.elapsed_time(b_) for a_, b_ in ev], stats
+
+    sampler = None
+    if rank == 0:                            # ONE nvidia-smi for all GPUs of the job, started early (it needs a moment)
+        sampler = ClockSampler(range(world))
+        sampler.start()
     # ---- warm-up ----
     for w in range(args.warmup):
-        device_step(-1 - w)
-        finish_step()
+        eng.run_device(params, chains, chain_id_base=chain_base, seed=SEED - 1 - w)
+        finish_step(eng)
     barrier()
 
     # ---- timed: device-resident ----
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    tot_windows = tot_updates = tot_sweeps = tot_rescans = launches = 0
-    kernel_ms = []
     barrier()
-    clk_first = sampler.mark()
+    clk_first = sampler.mark() if sampler else 0
     t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.fill_(s)                      # L2 flush between steps, outside the per-step event window
-        ev[s][0].record(stream)
-        device_step(s)
-        ev[s][1].record(stream)
-        res = finish_step()                 # sync + D2H (not inside the event window)
-        st = res.stats
-        tot_windows += st["window_scores"]
-        tot_updates += st["site_updates"]
-        tot_sweeps += st["sweeps"]
-        tot_rescans += st["exact_rescans"]
-        launches += st["kernel_launches"]
-        kernel_ms.append(st["kernel_ms"])
+    win_ms, step_stats = timed_steps(eng, params, args.steps, SEED)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clk_last = sampler.mark()
+    clk_last = sampler.mark() if sampler else 0
+    dev_ms = sum(win_ms)
+    tot_windows = sum(st["window_scores"] for st in step_stats)
+    tot_updates = sum(st["site_updates"] for st in step_stats)
+    tot_sweeps = sum(st["sweeps"] for st in step_stats)
+    tot_rescans = sum(st["exact_rescans"] for st in step_stats)
+    launches = sum(st["kernel_launches"] for st in step_stats)
+    kernel_ms = [st["kernel_ms"] for st in step_stats]
 
     # ---- timed: end to end through the public API with host buffers ----
-    e2e_windows = 0
     h2d = int(ps.ascii.size + ps.offsets.size * 8)
-    d2h = int(chains * n * (4 + 8) + chains * 8 + 4)
-    def e2e_step(s: int):
+    d2h = int(n * (4 + 8) + 8 + 4 + 8 * 8)      # the winner's (float*int)[] + its sum, restart index, run counters
+
+    def e2e_step(s_: int):
         eng.upload_flat(host_ascii.numpy(), host_off.numpy())      # H2D + GPU 2-bit pack
-        r = eng.run(params, chains, chain_id_base=chain_base, seed=SEED + 1000 + s, want_counts=False,
-                    pinned=True)   # results land in the engine's page-locked buffers (gibbs_host_alloc)
-        if args.family.startswith("motif"):
-            from gibbssampling_b200 import MotifSampler
-            best = MotifSampler.replay_motif_restart_loop(chains - 1, r.scores, r.sites, r.sums)   # fs:857 / fs:974
-        else:
-            best = SiteSampler.replay_restart_loop(chains - 1, r.scores, r.sites, r.sums)   # what fs:434 / fs:615 returns
-        if world > 1:
-            allgather_best(float(r.sums[r.best_chain]), chain_base + r.best_chain, r.sites[r.best_chain],
-                           r.scores[r.best_chain])
-        return r, best
+        eng.run_device(params, chains, chain_id_base=chain_base, seed=SEED + 1000 + s_)
+        return finish_step(eng)                                     # what fs:434 / fs:615 / fs:856 returns
 
     for w in range(args.warmup):            # untimed: first use allocates the page-locked result buffers
         e2e_step(-1 - w)
     barrier()
+    e2e_windows = 0
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        r, best = e2e_step(s)
-        e2e_windows += r.stats["window_scores"]
-        launches_e2e = r.stats["kernel_launches"] + 1
+    for s_ in range(args.steps):
+        best = e2e_step(s_)
+        e2e_windows += best.stats["window_scores"]
+        launches_e2e = best.stats["kernel_launches"]
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop(clk_first, clk_last)
-    assert len(best) in (1, n)
+    clocks = sampler.stop(clk_first, clk_last) if sampler else None
+    assert len(best.sites) in (1, n)
 
-    # ---- reduce over ranks: totals summed, times max ----
+    # ---- reduce over ranks: totals summed, times max; per-rank figures kept for attribution ----
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    mine = [dev_ms / args.steps, k_ms, 1e3 * e2e_s / args.steps, statistics.median(win_ms), max(win_ms), min(win_ms)]
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s, t_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         c = torch.tensor([tot_windows, tot_updates, e2e_windows, tot_sweeps, tot_rescans], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s, t_wall = (float(x) for x in t.tolist())
+        per = torch.zeros(world, len(mine), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(per, torch.tensor(mine, dtype=torch.float64, device="cuda"))
+        per = per.tolist()
+        dev_ms_max, e2e_s, t_wall = (float(x) for x in t.tolist())
         g_windows, g_updates, g_e2e_windows, g_sweeps, g_rescans = (float(x) for x in c.tolist())
     else:
+        per = [mine]
+        dev_ms_max = dev_ms
         g_windows, g_updates, g_e2e_windows, g_sweeps, g_rescans = tot_windows, tot_updates, e2e_windows, tot_sweeps, tot_rescans
 
+    # ---- the other reference families on the same set (N = 1, default workload only): short runs, reported beside the headline ----
+    peaks = measured_peaks()
+    smem_gbs = None
+    families = None
     if rank == 0:
-        peaks = measured_peaks()
         smem_gbs, _ = measure_smem_bandwidth(local_rank, 20000)
+    if world == 1 and args.family == "bpv" and not args.no_families:
+        families = {}
+        for fam in ("data", "motif", "motif-data"):
+            prm = params_of(fam)
+            eng.run_device(prm, chains, chain_id_base=chain_base, seed=SEED - 7)     # warm-up (tables, allocations)
+            finish_step(eng)
+            ms, sts = timed_steps(eng, prm, 2, SEED + 50)
+            w_ = sum(st["window_scores"] for st in sts)
+            kms = sum(st["kernel_ms"] for st in sts) / len(sts)
+            rate = w_ / (sum(ms) * 1e-3)
+            families[fam] = {"what": FAMILIES[fam][0], "kernel": FAMILIES[fam][2], "value": rate, "unit": "window-scores/s",
+                             "ms_per_step": sum(ms) / len(ms), "kernel_ms": kms, "steps": len(ms),
+                             "frac": rate * algorithmic_smem_bytes_per_window(k) / 1e9 / smem_gbs,
+                             "site_updates_per_sec": sum(st["site_updates"] for st in sts) / (sum(ms) * 1e-3),
+                             "gpu_launches": sum(st["kernel_launches"] for st in sts)}
+
+    if rank == 0:
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         smem_theory = sm_count * 128.0 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9
-        k_ms = sum(kernel_ms) / len(kernel_ms)
         rank_windows_per_s = (tot_windows / args.steps) / (k_ms * 1e-3)
         rank_updates_per_s = (tot_updates / args.steps) / (k_ms * 1e-3)
         achieved = rank_windows_per_s * algorithmic_smem_bytes_per_window(k) / 1e9
         hbm_achieved = rank_updates_per_s * algorithmic_hbm_bytes_per_site_update(length) / 1e9
-        value = g_windows / (dev_ms * 1e-3)
+        value = g_windows / (dev_ms_max * 1e-3)
         cpu = None
         if world == 1 and not args.no_cpu and fam_oracle is not None:
             dt = ws = us = 0.0
@@ -377,28 +427,27 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
                    "sample": (f"chains 0..{n_cpu_chains - 1} of the same workload, full {fam_oracle} restarts ({us} site updates) "
                               "on 1 host core; C port of the F# reference (oracle/), reference-faithful from-scratch rebuilds; "
                               "the F# itself needs .NET, absent from this image")}
+        config = workload_config(cfg_name, cfg, args.family, chains)
         line = {
             "metric": "gibbs_window_scores_per_sec", "value": value, "unit": "window-scores/s",
-            "site_updates_per_sec": g_updates / (dev_ms * 1e-3),
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "site_updates_per_sec": g_updates / (dev_ms_max * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic planted-motif DNA (Philox key 0xB200, 10% planted-base mutation)",
-            "config": {"workload": f"{cfg_name}: {n} seqs x {length} bp, k={k}, {chains} chains/GPU, {fam_text}"
-                                   + ("" if args.family.startswith("motif") else
-                                      f" (random starts + greedy sweeps + {'left/right shift sweeps' if shifts else 'no shifts'})"),
-                       "family": args.family,
-                       "chains_per_gpu": chains, "pseudocount": PSEUDOCOUNT, "alphabet_size": ALPHABET_SIZE,
-                       "background": fam_bg,
-                       "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event window; the packed "
-                             "sequences (125 KB at C2) are L2/SMEM-resident by design",
-                       "timing": "CUDA events on the launch stream around each step, summed; max over ranks"},
+            "config": config,
+            "measurement": {"l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event window; the packed "
+                                  "sequences (144 KB at C2) are L2/SMEM-resident by design",
+                            "timing": "CUDA events on the launch stream around each step, summed; max over ranks",
+                            "init_path": {1: "chain kernel", 2: "grid-wide kernel, global gathers", 3: "grid-wide kernel, set in shared memory"}.get(step_stats[-1]["init_path"]),
+                            "clock_sampler": "one nvidia-smi process on rank 0 for all GPUs of the job"},
             "window_scores_per_step": g_windows / args.steps, "site_updates_per_step": g_updates / args.steps,
             "sweeps_per_chain": g_sweeps / (args.steps * chains * world), "exact_rescans_per_step": g_rescans / args.steps,
             "wall_s_timed_region": t_wall,
+            "per_rank": {"fields": ["event_window_ms_per_step", "kernel_ms_per_step", "e2e_ms_per_step", "window_ms_median",
+                                    "window_ms_max", "window_ms_min"], "ranks": per},
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s", "frac": achieved / smem_gbs,
                          "traffic": NCU_DRAM_BYTES_PER_STEP if (cfg_name == "C2" and args.family == "bpv") else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step, "
-                                           "profiles/r01_ncu_c2_final_summary.txt",
+                         "traffic_source": NCU_DRAM_SOURCE,
                          "peak_source": "measured live: LDS.128 streaming microbenchmark (gibbs_measure_smem_bandwidth)",
                          "peak_theoretical": smem_theory, "frac_of_theoretical": achieved / smem_theory,
                          "algorithmic_bytes_per_window_score": algorithmic_smem_bytes_per_window(k),
@@ -409,7 +458,9 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
             "cpu_baseline": cpu,
             "e2e": {"value": g_e2e_windows / e2e_s, "unit": "window-scores/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "gibbs_upload + gibbs_run (C ABI) + replay of the fs:434 restart loop"},
+                    "api": "gibbs_upload + gibbs_run_device + gibbs_fetch_best (C ABI): ASCII in, the restart loop's "
+                           "(float*int)[] out; the fs:434 loop is decided on the device"},
+            "families": families,
             "gpu_launches": launches, "gpu_launches_e2e_per_step": launches_e2e,
             "clocks": clocks,
         }
@@ -430,6 +481,7 @@ def main() -> None:
                     help="reference family of the step; bpv = the BASELINE.json workload (the only one the driver runs)")
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-families", action="store_true", help="skip the short runs of the other reference families")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

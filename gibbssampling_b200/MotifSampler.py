@@ -55,7 +55,7 @@ def _split_motif_state(motifMem) -> tuple[np.ndarray, np.ndarray]:
 
 def _run(phase_mask: int, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, *, start=None,
          n_chains: int = 1, seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
-         max_sweeps: int = 0, ppM=None):
+         max_sweeps: int = 0, ppM=None, best_of: Optional[int] = None):
     """pcv given -> the PCV family (fixed background); pcv None -> the data-derived family (fs:885-1038)."""
     _check_m(motifAmount)
     if pcv is None:
@@ -74,7 +74,10 @@ def _run(phase_mask: int, motifAmount, motifLength, pseudoCount, cutOff, alphabe
         if ppM is not None:
             eng.set_start_ppm(ppM, motifLength)
         try:
-            return eng.run(params, n_chains, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+            if best_of is None:
+                return eng.run(params, n_chains, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+            eng.run_device(params, n_chains, chain_id_base=chain, seed=seed, uniforms=u)
+            return eng.fetch_best(best_of)   # the restart loop (fs:857-881) runs on the GPU; only the winner comes back
         finally:
             if ppM is not None:
                 eng.set_start_ppm(None)
@@ -161,8 +164,9 @@ def findBestInormationContentContainingMotifsWithPCV(numberOfRepetitions, motifA
     """fs:856-881: restarts run as parallel chains, the promote-or-restart loop is replayed over their results."""
     n_restarts = max(int(numberOfRepetitions) + 1, 1)
     res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, n_chains=n_restarts,
-               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps)
-    return replay_motif_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
+               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps,
+               best_of=int(numberOfRepetitions))
+    return _to_motif_array(res.scores, res.sites)
 
 
 # ---- data-derived background (fs:885-1038): one background per held-out sequence (fs:896-905) -------------
@@ -194,8 +198,9 @@ def getMotifsWithBestInformationContents(numberOfRepetitions, motifAmount, motif
     """fs:973-998 -- the reference script's second live call (fsx:407; there with motifAmount = 2, out of scope)."""
     n_restarts = max(int(numberOfRepetitions) + 1, 1)
     res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
-               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps)
-    return replay_motif_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
+               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps,
+               best_of=int(numberOfRepetitions))
+    return _to_motif_array(res.scores, res.sites)
 
 
 def doMotifSamplingWithPPM(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, **kw) -> list:
@@ -214,5 +219,6 @@ def getBestPWMSsOfPPM(numberOfRepetitions, motifAmount, motifLength, pseudoCount
         raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "ppM is null (ArgumentNullException)")
     n_restarts = max(int(numberOfRepetitions) + 1, 1)
     res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
-               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps, ppM=ppM)
-    return replay_motif_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
+               seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps, ppM=ppM,
+               best_of=int(numberOfRepetitions))
+    return _to_motif_array(res.scores, res.sites)

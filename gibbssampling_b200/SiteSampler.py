@@ -133,7 +133,8 @@ def doSiteSamplingWithBPV(motifLength, pseudoCount, alphabet, sources, pcv, **kw
 
 def replay_restart_loop(numberOfRepetitions: int, restart_scores: np.ndarray, restart_sites: np.ndarray,
                         restart_sums: Optional[np.ndarray] = None) -> SiteArray:
-    """The promote-or-restart loop of fs:435-459 (quirk A.6-8) over restarts that already ran.
+    """The promote-or-restart loop of fs:435-459 (quirk A.6-8) over restarts that already ran -- the host-side model
+    of what gibbs_fetch_best decides on the GPU (tests compare the two; multi-process runs use it on gathered results).
 
     The reference runs restarts one after another; here restart r is chain r of one kernel launch,
     and this function replays the loop's decisions over their results in the same order, so the
@@ -195,11 +196,12 @@ def _restart_loop(numberOfRepetitions, motifLength, pseudoCount, alphabet, sourc
         if ppM is not None:
             eng.set_start_ppm(ppM, motifLength)
         try:
-            res = eng.run(params, n_restarts, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
+            eng.run_device(params, n_restarts, chain_id_base=chain, seed=seed, uniforms=u)
         finally:
             if ppM is not None:
                 eng.set_start_ppm(None)
-        return replay_restart_loop(int(numberOfRepetitions), res.scores, res.sites, res.sums)
+        best = eng.fetch_best(int(numberOfRepetitions))   # the loop of fs:435-459 runs on the GPU; only the winner comes back
+        return _to_site_array(best.scores, best.sites)
     finally:
         if own:
             eng.close()

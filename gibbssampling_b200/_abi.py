@@ -36,7 +36,12 @@ EXPORTS = [
     "gibbs_loo_counts", "gibbs_window_scores", "gibbs_pick_argmax", "gibbs_pick_roulette",
     "gibbs_set_start_ppm", "gibbs_set_start_state", "gibbs_run_device", "gibbs_fetch", "gibbs_run", "gibbs_device_results",
     "gibbs_host_alloc", "gibbs_host_free", "gibbs_measure_smem_bandwidth",
+    "gibbs_set_option", "gibbs_fetch_best",
+    "gibbs_multi_create", "gibbs_multi_destroy", "gibbs_multi_num_devices", "gibbs_multi_handle",
+    "gibbs_multi_run_device", "gibbs_multi_fetch_best",
 ]
+GIBBS_OPT_INIT_PATH, GIBBS_OPT_EXACT_SCANS = 1, 2
+GIBBS_INIT_AUTO, GIBBS_INIT_CHAIN, GIBBS_INIT_WIDE, GIBBS_INIT_SMEM = 0, 1, 2, 3
 
 
 class GibbsError(RuntimeError):
@@ -109,7 +114,7 @@ class RunStats(C.Structure):
         ("kernel_launches", C.c_int32),
         ("fast_path", C.c_int32),
         ("team_warps", C.c_int32),
-        ("reserved", C.c_int32),
+        ("init_path", C.c_int32),
         ("kernel_ms", C.c_double),
     ]
 
@@ -157,10 +162,19 @@ def load() -> C.CDLL:
                               P(i32), P(RunStats)]
     lib.gibbs_device_results.argtypes = [vp, P(vp), P(vp), P(vp)]
     lib.gibbs_measure_smem_bandwidth.argtypes = [i32, i32, P(f64), P(f64)]
+    lib.gibbs_set_option.argtypes = [vp, i32, i32]
+    lib.gibbs_fetch_best.argtypes = [vp, i32, P(i32), P(f64), P(i32), P(f64), P(i32), P(i32), P(RunStats)]
+    lib.gibbs_multi_create.argtypes = [P(C.c_uint8), P(i64), i32, P(i32), i32, P(vp)]
+    lib.gibbs_multi_destroy.argtypes = [vp]
+    lib.gibbs_multi_num_devices.argtypes = [vp]
+    lib.gibbs_multi_handle.argtypes = [vp, i32]
+    lib.gibbs_multi_run_device.argtypes = [vp, P(Params), i32, i64, u64, i32, P(f64), i64]
+    lib.gibbs_multi_fetch_best.argtypes = [vp, i32, P(i32), P(f64), P(i32), P(f64), P(i32), P(i32), P(RunStats)]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("gibbs_last_error",):
+        if name not in ("gibbs_last_error", "gibbs_multi_handle"):
             fn.restype = i32
+    lib.gibbs_multi_handle.restype = vp
     _lib = lib
     return lib
 

@@ -139,6 +139,14 @@ struct gibbs_handle {
     int32_t team_warps = 0;   // 0 = choose per launch; 1, 4, 8 or 16 = forced (gibbs_set_team_warps)
     int32_t run_team = 0;
     int sm_count = 0;
+    std::vector<int32_t> len_host;     // sequence lengths (known from the offsets at upload: no read-back needed)
+    int32_t start_max_excess = 0;      // max over the staged start sites of (site - length of its sequence)
+    int32_t opt_init_path = 0;         // gibbs_set_option(GIBBS_OPT_INIT_PATH)
+    int32_t opt_exact_scans = 0;       // gibbs_set_option(GIBBS_OPT_EXACT_SCANS)
+    int32_t run_init_path = 0;         // where the random starts of the last run ran (GIBBS_INIT_*)
+    DevBuf<int32_t> win_sites;         // gibbs_fetch_best: the winner's rows + [n] restart index
+    DevBuf<double> win_scores;         // [n] scores + [n] sum
+    size_t smem_optin = 0;             // largest dynamic shared memory a block may opt in to
 };
 
 namespace {
@@ -242,26 +250,49 @@ int32_t launch_team(gibbs_handle *h, int team, bool masked, bool drift, const Ch
 template <int KPV>
 int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
     h->run_extra_launches = 0;
-    const char *init_env = getenv("GIBBS_B200_INIT_KERNEL"); // measurement switch: "0" keeps the random starts in the chain kernel
-    // Random starts are N independent site updates of N-1 draws each. With many chains of few sequences the
-    // chain kernel's own INIT sweep already fills the GPU (measured 6.6 vs 7.5 ms on C2); with few chains or
-    // many sequences the grid-wide kernel is the only way to use all SMs (C4, 8 chains: 17.2 s -> 0.61 s).
-    const bool init_wide = init_env ? init_env[0] != '0' : (a.n_chains < 4 * h->sm_count || a.s.n >= 4096);
+    // Random starts are N independent site updates of N-1 draws each, so they need not run on the chain's own team:
+    //   GIBBS_INIT_SMEM   grid-wide, one CTA per SM holding the whole packed set in shared memory (the draws gather
+    //                     from LDS): whenever the set fits (fixed background, A,C,G,T only) -- C2: 144 KB
+    //   GIBBS_INIT_WIDE   grid-wide with global gathers: few chains or many sequences (C4, 8 chains: 17.2 s -> 0.61 s
+    //                     against the chain kernel's INIT sweep)
+    //   GIBBS_INIT_CHAIN  inside the chain kernel: many chains of few sequences whose set does not fit
     const bool masked = a.s.mask != nullptr; // symbols outside A,C,G,T: one launch of the MASKED instantiation (1 or 4 warps)
-    if ((a.phase_mask & GIBBS_PHASE_INIT) && init_wide && !masked) {
+    int init_path = GIBBS_INIT_CHAIN;
+    if ((a.phase_mask & GIBBS_PHASE_INIT) && !masked) {
+        const bool smem_fits = !drift && init_smem_total_bytes(a.s.n, a.s.row_words, KPV) <= h->smem_optin &&
+                               (long long)a.n_chains * a.s.n >= (long long)h->sm_count * ISM_WARPS;
+        const bool wide_fits = init_smem_bytes(a.s.row_words) <= 200 * 1024;
+        const bool wide_wins = a.n_chains < 4 * h->sm_count || a.s.n >= 4096;
+        init_path = smem_fits ? GIBBS_INIT_SMEM : (wide_fits && wide_wins) ? GIBBS_INIT_WIDE : GIBBS_INIT_CHAIN;
+        if (h->opt_init_path == GIBBS_INIT_CHAIN) init_path = GIBBS_INIT_CHAIN;
+        if (h->opt_init_path == GIBBS_INIT_WIDE && wide_fits) init_path = GIBBS_INIT_WIDE;
+        if (h->opt_init_path == GIBBS_INIT_SMEM && !drift && init_smem_total_bytes(a.s.n, a.s.row_words, KPV) <= h->smem_optin)
+            init_path = GIBBS_INIT_SMEM;
+    }
+    h->run_init_path = init_path;
+    if (init_path == GIBBS_INIT_SMEM) {
+        const int smem = (int)init_smem_total_bytes(a.s.n, a.s.row_words, KPV);
+        int32_t rc = set_smem(init_smem_kernel<KPV>, smem);
+        if (rc) return rc;
+        const long long items = (long long)a.n_chains * a.s.n;
+        long long grid = (items + ISM_WARPS - 1) / ISM_WARPS;
+        if (grid > h->sm_count) grid = h->sm_count;
+        init_smem_kernel<KPV><<<(int)grid, ISM_WARPS * 32, smem, h->stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        a.phase_mask &= ~GIBBS_PHASE_INIT; // the chain kernel continues from the state just written
+        h->run_extra_launches += 1;
+    } else if (init_path == GIBBS_INIT_WIDE) {
         const int smem = init_smem_bytes(a.s.row_words);
-        if (smem <= 200 * 1024) {
-            int32_t rc = drift ? set_smem(init_kernel<KPV, true>, smem) : set_smem(init_kernel<KPV, false>, smem);
-            if (rc) return rc;
-            const long long items = (long long)a.n_chains * a.s.n;
-            long long grid = (items + INIT_WARPS - 1) / INIT_WARPS;
-            if (grid > 4LL * h->sm_count) grid = 4LL * h->sm_count;
-            if (drift) init_kernel<KPV, true><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
-            else init_kernel<KPV, false><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
-            CUDA_TRY(cudaGetLastError());
-            a.phase_mask &= ~GIBBS_PHASE_INIT; // the chain kernel continues from the state just written
-            h->run_extra_launches += 1;
-        }
+        int32_t rc = drift ? set_smem(init_kernel<KPV, true>, smem) : set_smem(init_kernel<KPV, false>, smem);
+        if (rc) return rc;
+        const long long items = (long long)a.n_chains * a.s.n;
+        long long grid = (items + INIT_WARPS - 1) / INIT_WARPS;
+        if (grid > 4LL * h->sm_count) grid = 4LL * h->sm_count;
+        if (drift) init_kernel<KPV, true><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
+        else init_kernel<KPV, false><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        a.phase_mask &= ~GIBBS_PHASE_INIT;
+        h->run_extra_launches += 1;
     }
     // Warps per chain and the straggler hand-over. Chains need very different numbers of sweeps, so a
     // one-wave launch ends with a few chains running on a mostly idle GPU. Stage 1 runs every chain with 4
@@ -537,6 +568,11 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
     if (max_len < 1) return fail(GIBBS_ERR_SHORT_SEQ, "all sequences are empty");
     int32_t rc = set_device(h);
     if (rc) return rc;
+    // whatever the handle held is gone from here on: a failure below must not leave the old n beside new buffers
+    h->n = 0;
+    h->start_chains = 0;
+    h->run_done = false;
+    h->wtab_valid = h->bg_valid = h->drift_valid = h->ss_valid = false;
     const int64_t total = offsets[n_seqs] - offsets[0];
     const int row_words = (int)(((max_len + 15) / 16 + 4 + 3) / 4 * 4);
     if (team_smem_bytes(row_words, 1) > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequence too long for shared-memory staging");
@@ -563,17 +599,18 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
     CUDA_TRY(cudaMemcpyAsync(sym, h->symflags.p, sizeof sym, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream)); // also keeps `rel` alive until the copy is done
     const int bad = sym[0];
-    h->n = 0;
-    h->wtab_valid = false;
-    h->bg_valid = false;
-    h->drift_valid = false;
-    h->run_done = false;
     if (bad)
         return fail(GIBBS_ERR_SYMBOL, "symbol '%c' (0x%02x) is outside '*'..'Z', the range of the 49-slot tables "
                                       "(IndexOutOfRangeException, fs:17-20)",
                     (bad - 1) >= 32 && (bad - 1) < 127 ? (char)(bad - 1) : '?', bad - 1);
     h->n_masked = sym[1];
     h->has_gap = sym[2] != 0;
+    try {
+        h->len_host.resize((size_t)n_seqs);
+    } catch (...) {
+        return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+    }
+    for (int32_t i = 0; i < n_seqs; ++i) h->len_host[i] = (int32_t)(offsets[i + 1] - offsets[i]);
     h->n = n_seqs;
     h->row_words = row_words;
     h->max_len = (int32_t)max_len;
@@ -584,21 +621,11 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
 int32_t stage_sites(gibbs_handle *h, const int32_t *sites, int32_t heldout, int32_t k) {
     if (!sites) return fail(GIBBS_ERR_ARG, "null sites");
     if (heldout < -1 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
-    // positions must address a full k-mer (getSegment, fs:149-153); lengths are validated on the device
-    // side by construction: the host keeps only min/max, so re-read lengths when ragged
+    // positions must address a full k-mer (getSegment, fs:149-153)
     CUDA_TRY(h->prim_sites.reserve((size_t)h->n));
-    if (h->min_len != h->max_len) {
-        std::vector<int32_t> len((size_t)h->n);
-        CUDA_TRY(cudaMemcpyAsync(len.data(), h->len.p, len.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-        for (int32_t i = 0; i < h->n; ++i)
-            if (i != heldout && sites[i] >= 0 && sites[i] + k > len[i])
-                return fail(GIBBS_ERR_ARG, "site %d of sequence %d leaves the sequence (length %d, k %d)", sites[i], i, len[i], k);
-    } else {
-        for (int32_t i = 0; i < h->n; ++i)
-            if (i != heldout && sites[i] >= 0 && sites[i] + k > h->max_len)
-                return fail(GIBBS_ERR_ARG, "site %d of sequence %d leaves the sequence (length %d, k %d)", sites[i], i, h->max_len, k);
-    }
+    for (int32_t i = 0; i < h->n; ++i)
+        if (i != heldout && sites[i] >= 0 && sites[i] + k > h->len_host[i])
+            return fail(GIBBS_ERR_ARG, "site %d of sequence %d leaves the sequence (length %d, k %d)", sites[i], i, h->len_host[i], k);
     CUDA_TRY(cudaMemcpyAsync(h->prim_sites.p, sites, (size_t)h->n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     return GIBBS_OK;
 }
@@ -644,7 +671,10 @@ int32_t gibbs_create(const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs
     }
     if (!rc) {
         cudaError_t e3 = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+        int optin = 0;
+        if (e3 == cudaSuccess) e3 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         if (e3 != cudaSuccess) rc = fail(GIBBS_ERR_CUDA, "device attribute: %s", cudaGetErrorString(e3));
+        h->smem_optin = (size_t)(optin > 0 ? optin : 0);
     }
     if (!rc) rc = upload(h, seqs, offsets, n_seqs);
     if (rc) {
@@ -749,12 +779,7 @@ static int32_t scan_common(gibbs_handle *h, const int32_t *sites, int32_t heldou
     if (rc) return rc;
     rc = ensure_wtab(h, p, nullptr);
     if (rc) return rc;
-    int32_t len_h = h->max_len;
-    if (h->min_len != h->max_len) {
-        CUDA_TRY(cudaMemcpyAsync(&len_h, h->len.p + heldout, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-    }
-    const int W = len_h - p->k + 1;
+    const int W = h->len_host[heldout] - p->k + 1;
     CUDA_TRY(h->prim_f64.reserve((size_t)2 * W + 8));
     CUDA_TRY(h->prim_i32.reserve(GIBBS_MAX_K * 4 + 8));
     PrimArgs a{};
@@ -869,6 +894,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     a.k = p->k;
     a.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 1000000;
     a.fast_ok = p->background == GIBBS_BG_FIXED ? fast_path_ok(h, p->k) : 0;
+    if (h->opt_exact_scans) a.fast_ok = 0;
     a.sampler = p->sampler;
     const int site_phases = GIBBS_PHASE_INIT | GIBBS_PHASE_GREEDY | GIBBS_PHASE_LEFT | GIBBS_PHASE_RIGHT;
     const int motif_phases = GIBBS_PHASE_INIT | GIBBS_PHASE_STOCHASTIC | GIBBS_PHASE_MOTIF_GREEDY;
@@ -880,9 +906,22 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         a.phase_mask = p->phase_mask ? p->phase_mask : motif_phases;
         if (a.phase_mask & ~motif_phases) return fail(GIBBS_ERR_ARG, "phase_mask 0x%x has phases that are not MotifSampler phases", a.phase_mask);
     }
-    if (!(a.phase_mask & GIBBS_PHASE_INIT) && h->start_chains != n_chains)
-        return fail(GIBBS_ERR_ARG, "phase_mask without GIBBS_PHASE_INIT needs gibbs_set_start_state for %d chains", n_chains);
+    if (!(a.phase_mask & GIBBS_PHASE_INIT)) {
+        if (h->start_chains != n_chains)
+            return fail(GIBBS_ERR_ARG, "phase_mask without GIBBS_PHASE_INIT needs gibbs_set_start_state for %d chains", n_chains);
+        if (h->start_max_excess > -p->k) // getSegment -> Array.take on a start position that leaves its sequence (fs:149-153)
+            return fail(GIBBS_ERR_SHORT_SEQ, "a start site lies within %d symbols of the end of its sequence: no room for k = %d "
+                                             "(InvalidOperationException from Array.take, fs:152)", -h->start_max_excess, p->k);
+    }
     h->start_chains = 0;
+    if (rng_mode == GIBBS_RNG_INJECTED) { // a stream that is too short must not turn into silent u = 0 draws
+        int64_t need = 0;
+        if (a.phase_mask & GIBBS_PHASE_INIT) need = (int64_t)h->n * (h->n - 1);
+        if (a.phase_mask & GIBBS_PHASE_STOCHASTIC) need = (int64_t)h->n * (h->n - 1) + h->n; // draw index of fs:851 follows the random starts
+        if (uniforms_per_chain < need)
+            return fail(GIBBS_ERR_ARG, "uniforms_per_chain = %lld, but the phases of this run consume draws up to index %lld "
+                                       "(N(N-1) random starts, then N roulette picks)", (long long)uniforms_per_chain, (long long)need);
+    }
     a.rng_mode = rng_mode;
     a.seed = seed;
     a.chain_id_base = chain_id_base;
@@ -954,7 +993,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             m.c.pc = m.pc;
         }
         m.roulette_scan_ok = 1;
-        if (getenv("GIBBS_B200_MOTIF_EXACT")) { // measurement / test switch: every window in float64, sequential roulette walk
+        if (h->opt_exact_scans) { // gibbs_set_option(GIBBS_OPT_EXACT_SCANS): every window in float64, sequential roulette walk
             m.greedy_fast_ok = 0;
             m.roulette_scan_ok = 0;
         }
@@ -978,7 +1017,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             const double bases = (double)h->gcnt[0] + h->gcnt[1] + h->gcnt[2] + h->gcnt[3] + (double)h->max_len;
             const double den = (bases > (double)h->n ? bases : (double)h->n) + a.alpha_pc;
             a.drift_fast_ok = (p->pseudocount >= 1e-30 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
-            if (getenv("GIBBS_B200_DRIFT_EXACT")) a.drift_fast_ok = 0; // measurement / test switch: every window in float64
+            if (h->opt_exact_scans) a.drift_fast_ok = 0; // gibbs_set_option(GIBBS_OPT_EXACT_SCANS): every window in float64
             a.fast_ok = a.drift_fast_ok;
         }
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
@@ -994,7 +1033,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     h->run_sampler = p->sampler;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     ++launches;
-    best_chain_kernel<<<1, 32, 0, h->stream>>>(h->sums.p, n_chains, h->best.p);
+    best_chain_kernel<<<1, 256, 0, h->stream>>>(h->sums.p, n_chains, h->best.p);
     CUDA_TRY(cudaGetLastError());
     ++launches;
     h->run_chains = n_chains;
@@ -1027,16 +1066,15 @@ int32_t gibbs_set_start_state(gibbs_handle *h, int32_t n_chains, const int32_t *
     int32_t rc = set_device(h);
     if (rc) return rc;
     const size_t cells = (size_t)n_chains * h->n;
-    std::vector<int32_t> len;
-    if (h->min_len != h->max_len) {
-        len.resize((size_t)h->n);
-        CUDA_TRY(cudaMemcpyAsync(len.data(), h->len.p, len.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-    }
+    // k is not known yet: remember how close a site comes to the end of its sequence; gibbs_run_device requires
+    // site + k <= length (getSegment -> Array.take throws otherwise, fs:149-153)
+    int32_t excess = INT32_MIN;
     for (size_t c = 0; c < cells; ++c) {
-        const int32_t l = len.empty() ? h->max_len : len[c % (size_t)h->n];
+        const int32_t l = h->len_host[c % (size_t)h->n];
         if (sites[c] < -1 || sites[c] >= l) return fail(GIBBS_ERR_ARG, "start site %d outside its sequence", sites[c]);
+        if (sites[c] >= 0 && sites[c] - l > excess) excess = sites[c] - l;
     }
+    h->start_max_excess = excess;
     CUDA_TRY(h->sites.reserve(cells));
     CUDA_TRY(h->hv.reserve(cells));
     CUDA_TRY(h->scores.reserve(cells));
@@ -1089,9 +1127,86 @@ int32_t gibbs_fetch(gibbs_handle *h, int32_t *sites_out, double *scores_out, dou
         stats_out->kernel_launches = h->run_launches + extra_launches;
         stats_out->fast_path = h->run_fast;
         stats_out->team_warps = h->run_team;
+        stats_out->init_path = h->run_init_path;
         stats_out->kernel_ms = (double)ms;
     }
     return GIBBS_OK;
+}
+
+int32_t gibbs_fetch_best(gibbs_handle *h, int32_t repetitions, int32_t *sites_out, double *scores_out, int32_t *n_out,
+                         double *sum_out, int32_t *restart_out, int32_t *counts_out, gibbs_run_stats *stats_out) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    if (!h->run_done) return fail(GIBBS_ERR_ARG, "gibbs_fetch_best without a preceding gibbs_run_device");
+    if (repetitions < 0) repetitions = 0;
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    const int32_t N = h->n;
+    CUDA_TRY(h->win_sites.reserve((size_t)N + 1));
+    CUDA_TRY(h->win_scores.reserve((size_t)N + 1));
+    restart_select_kernel<<<1, 32, 0, h->stream>>>(h->sums.p, h->sites.p, h->scores.p, h->run_chains, N, repetitions,
+                                                  h->run_sampler == GIBBS_MOTIF_SAMPLER ? 1 : 0, h->win_sites.p + N,
+                                                  h->win_sites.p, h->win_scores.p, h->win_scores.p + N);
+    CUDA_TRY(cudaGetLastError());
+    int extra_launches = 1;
+    // the winner is at a fixed device address: everything is queued before the one synchronisation
+    int32_t best = -1;
+    double sum = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&best, h->win_sites.p + N, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(&sum, h->win_scores.p + N, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sites_out) CUDA_TRY(cudaMemcpyAsync(sites_out, h->win_sites.p, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (scores_out) CUDA_TRY(cudaMemcpyAsync(scores_out, h->win_scores.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (counts_out) { // PWM counts of the winner's sites (all zero when the initial value survived)
+        rc = launch_all_counts(h, dev_seqs(h), h->win_sites.p, h->run_k, h->best.p + 1);
+        if (rc) return rc;
+        ++extra_launches;
+        CUDA_TRY(cudaMemcpyAsync(counts_out, h->best.p + 1, (size_t)h->run_k * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    unsigned long long st[ST_NSLOTS];
+    CUDA_TRY(cudaMemcpyAsync(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    int32_t roulette_error = 0;
+    if (h->run_sampler == GIBBS_MOTIF_SAMPLER)
+        CUDA_TRY(cudaMemcpyAsync(&roulette_error, h->err_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (roulette_error) return fail(GIBBS_ERR_ROULETTE, "a roulette pick lay beyond the accumulated mass (ArgumentException, fs:753)");
+    if (best < 0) { // loop 0 [||] [|(0., 0)|] returned its initial value (quirk A.6-8)
+        if (sites_out) sites_out[0] = h->run_sampler == GIBBS_MOTIF_SAMPLER ? -1 : 0;
+        if (scores_out) scores_out[0] = 0.0;
+        if (counts_out) memset(counts_out, 0, (size_t)h->run_k * 4 * sizeof(int32_t));
+    }
+    if (n_out) *n_out = best < 0 ? 1 : N;
+    if (sum_out) *sum_out = sum;
+    if (restart_out) *restart_out = best;
+    if (stats_out) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        stats_out->site_updates = (int64_t)st[ST_SITE_UPDATES];
+        stats_out->window_scores = (int64_t)st[ST_WINDOW_SCORES];
+        stats_out->sweeps = (int64_t)st[ST_SWEEPS];
+        stats_out->exact_rescans = (int64_t)st[ST_EXACT_RESCANS];
+        stats_out->capped_chains = (int64_t)st[ST_CAPPED];
+        stats_out->speculative_discards = (int64_t)st[ST_SPECULATED];
+        stats_out->kernel_launches = h->run_launches + extra_launches;
+        stats_out->fast_path = h->run_fast;
+        stats_out->team_warps = h->run_team;
+        stats_out->init_path = h->run_init_path;
+        stats_out->kernel_ms = (double)ms;
+    }
+    return GIBBS_OK;
+}
+
+int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value) {
+    if (!h) return fail(GIBBS_ERR_ARG, "null handle");
+    switch (option) {
+    case GIBBS_OPT_INIT_PATH:
+        if (value < GIBBS_INIT_AUTO || value > GIBBS_INIT_SMEM) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_INIT_PATH takes GIBBS_INIT_AUTO .. GIBBS_INIT_SMEM");
+        h->opt_init_path = value;
+        return GIBBS_OK;
+    case GIBBS_OPT_EXACT_SCANS:
+        h->opt_exact_scans = value != 0;
+        return GIBBS_OK;
+    default:
+        return fail(GIBBS_ERR_ARG, "unknown option %d", option);
+    }
 }
 
 int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base, uint64_t seed,
@@ -1101,6 +1216,184 @@ int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int6
     int32_t rc = gibbs_run_device(h, p, n_chains, chain_id_base, seed, rng_mode, uniforms, uniforms_per_chain);
     if (rc) return rc;
     return gibbs_fetch(h, sites_out, scores_out, sums_out, best_chain_out, counts_out, stats_out);
+}
+
+/* ---- one process, several devices ------------------------------------------------------------------------------- */
+struct gibbs_multi {
+    std::vector<gibbs_handle *> dev;
+    std::vector<int32_t> first, count; // chains [first, first + count) of the last run live on device i
+    std::vector<double> sums;          // sums of every restart of the last run, in restart order
+    int32_t run_chains = 0;
+    bool run_done = false;
+};
+
+int32_t gibbs_multi_create(const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs, const int32_t *devices,
+                           int32_t n_devices, gibbs_multi **out) {
+    if (!out) return fail(GIBBS_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    const int32_t visible = gibbs_device_count();
+    if (visible < 1) return fail(GIBBS_ERR_CUDA, "no CUDA device available; libgibbs_b200 has no CPU fallback");
+    if (n_devices == 0) n_devices = visible; // 0 = every visible device
+    if (n_devices < 1 || n_devices > visible) return fail(GIBBS_ERR_ARG, "n_devices = %d, %d visible", n_devices, visible);
+    gibbs_multi *m = new (std::nothrow) gibbs_multi();
+    if (!m) return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+    for (int32_t i = 0; i < n_devices; ++i) {
+        gibbs_handle *h = nullptr;
+        const int32_t rc = gibbs_create(seqs, offsets, n_seqs, devices ? devices[i] : i, &h); // the set is replicated
+        if (rc) {
+            gibbs_multi_destroy(m);
+            return rc;
+        }
+        m->dev.push_back(h);
+    }
+    m->first.assign((size_t)n_devices, 0);
+    m->count.assign((size_t)n_devices, 0);
+    *out = m;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_multi_destroy(gibbs_multi *m) {
+    if (!m) return GIBBS_OK;
+    for (gibbs_handle *h : m->dev) gibbs_destroy(h);
+    delete m;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_multi_num_devices(const gibbs_multi *m) { return m ? (int32_t)m->dev.size() : 0; }
+
+gibbs_handle *gibbs_multi_handle(gibbs_multi *m, int32_t i) {
+    return (m && i >= 0 && i < (int32_t)m->dev.size()) ? m->dev[(size_t)i] : nullptr;
+}
+
+int32_t gibbs_multi_run_device(gibbs_multi *m, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base, uint64_t seed,
+                               int32_t rng_mode, const double *uniforms, int64_t uniforms_per_chain) {
+    if (!m || m->dev.empty()) return fail(GIBBS_ERR_ARG, "null multi-device handle");
+    if (n_chains < 1) return fail(GIBBS_ERR_ARG, "n_chains must be >= 1");
+    m->run_done = false;
+    const int32_t G = (int32_t)m->dev.size();
+    // contiguous blocks of restarts per device; streams are keyed by the global chain id, so the result of every
+    // restart is the one a single device would compute. Launches are asynchronous: the devices run concurrently.
+    int32_t next = 0;
+    for (int32_t i = 0; i < G; ++i) {
+        const int32_t cnt = n_chains / G + (i < n_chains % G ? 1 : 0);
+        m->first[(size_t)i] = next;
+        m->count[(size_t)i] = cnt;
+        if (cnt > 0) {
+            const double *u = (rng_mode == GIBBS_RNG_INJECTED && uniforms) ? uniforms + (size_t)next * (size_t)uniforms_per_chain : uniforms;
+            const int32_t rc = gibbs_run_device(m->dev[(size_t)i], p, cnt, chain_id_base + next, seed, rng_mode, u, uniforms_per_chain);
+            if (rc) return rc;
+        }
+        next += cnt;
+    }
+    m->run_chains = n_chains;
+    m->run_done = true;
+    return GIBBS_OK;
+}
+
+namespace {
+// rows of restart r (global index) of the last multi-device run
+int32_t multi_rows(gibbs_multi *m, int32_t r, int32_t *sites_out, double *scores_out) {
+    for (size_t i = 0; i < m->dev.size(); ++i) {
+        if (r < m->first[i] || r >= m->first[i] + m->count[i]) continue;
+        gibbs_handle *h = m->dev[i];
+        int32_t rc = set_device(h);
+        if (rc) return rc;
+        const size_t o = (size_t)(r - m->first[i]) * h->n;
+        if (sites_out) CUDA_TRY(cudaMemcpyAsync(sites_out, h->sites.p + o, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (scores_out) CUDA_TRY(cudaMemcpyAsync(scores_out, h->scores.p + o, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        return GIBBS_OK;
+    }
+    return fail(GIBBS_ERR_ARG, "restart %d is not part of the last run", r);
+}
+} // namespace
+
+int32_t gibbs_multi_fetch_best(gibbs_multi *m, int32_t repetitions, int32_t *sites_out, double *scores_out, int32_t *n_out,
+                               double *sum_out, int32_t *restart_out, int32_t *counts_out, gibbs_run_stats *stats_out) {
+    if (!m || m->dev.empty()) return fail(GIBBS_ERR_ARG, "null multi-device handle");
+    if (!m->run_done) return fail(GIBBS_ERR_ARG, "gibbs_multi_fetch_best without a preceding gibbs_multi_run_device");
+    if (repetitions < 0) repetitions = 0;
+    const int32_t N = m->dev[0]->n, R = m->run_chains;
+    try {
+        m->sums.assign((size_t)R, 0.0);
+    } catch (...) {
+        return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+    }
+    gibbs_run_stats total{};
+    for (size_t i = 0; i < m->dev.size(); ++i) { // 8 B per restart and the counters of each device: all that always crosses PCIe
+        if (m->count[i] == 0) continue;
+        gibbs_run_stats st{};
+        const int32_t rc = gibbs_fetch(m->dev[i], nullptr, nullptr, m->sums.data() + m->first[i], nullptr, nullptr, &st);
+        if (rc) return rc;
+        total.site_updates += st.site_updates; total.window_scores += st.window_scores; total.sweeps += st.sweeps;
+        total.exact_rescans += st.exact_rescans; total.capped_chains += st.capped_chains;
+        total.speculative_discards += st.speculative_discards; total.kernel_launches += st.kernel_launches;
+        total.fast_path = st.fast_path; total.team_warps = st.team_warps; total.init_path = st.init_path;
+        if (st.kernel_ms > total.kernel_ms) total.kernel_ms = st.kernel_ms; // the devices ran concurrently
+    }
+    // the promote-or-restart loop of fs:435-459 (quirk A.6-8) over the restarts in their global order; see
+    // restart_select_kernel for the single-device twin. `acc = best` needs the arrays only when two sums are equal.
+    const bool motif = m->dev[0]->run_sampler == GIBBS_MOTIF_SAMPLER;
+    std::vector<int32_t> sa, sb;
+    std::vector<double> va, vb;
+    int32_t best = -1, acc = -1, r = 0; // acc -1 = [||]
+    double bsum = 0.0;
+    for (long long n = 0; n <= (long long)repetitions; ++n) {
+        if (acc >= 0 && m->sums[(size_t)acc] == bsum) { // acc = best ?
+            bool same;
+            try {
+                sa.resize((size_t)N); va.resize((size_t)N);
+                int32_t rc = multi_rows(m, acc, sa.data(), va.data());
+                if (rc) return rc;
+                if (best < 0) {
+                    same = N == 1 && va[0] == 0.0 && sa[0] == (motif ? -1 : 0);
+                } else {
+                    sb.resize((size_t)N); vb.resize((size_t)N);
+                    rc = multi_rows(m, best, sb.data(), vb.data());
+                    if (rc) return rc;
+                    same = true;
+                    for (int32_t i = 0; i < N && same; ++i) same = sa[(size_t)i] == sb[(size_t)i] && va[(size_t)i] == vb[(size_t)i];
+                }
+            } catch (...) {
+                return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+            }
+            if (same) break;
+        }
+        const double asum = acc >= 0 ? m->sums[(size_t)acc] : 0.0;
+        if (asum > bsum) { // promote (an empty acc leaves best as it is)
+            if (acc >= 0) { best = acc; bsum = asum; }
+            acc = -1;
+        } else {
+            if (r >= R) break; // (cannot happen with n_chains >= repetitions + 1)
+            acc = r++;
+        }
+    }
+    if (best >= 0) {
+        const int32_t rc = multi_rows(m, best, sites_out, scores_out);
+        if (rc) return rc;
+        if (counts_out) {
+            for (size_t i = 0; i < m->dev.size(); ++i) {
+                if (best < m->first[i] || best >= m->first[i] + m->count[i]) continue;
+                gibbs_handle *h = m->dev[i];
+                int32_t rc2 = set_device(h);
+                if (rc2) return rc2;
+                rc2 = launch_all_counts(h, dev_seqs(h), h->sites.p + (size_t)(best - m->first[i]) * h->n, h->run_k, h->best.p + 1);
+                if (rc2) return rc2;
+                CUDA_TRY(cudaMemcpyAsync(counts_out, h->best.p + 1, (size_t)h->run_k * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(cudaStreamSynchronize(h->stream));
+                total.kernel_launches += 1;
+            }
+        }
+    } else {
+        if (sites_out) sites_out[0] = motif ? -1 : 0;
+        if (scores_out) scores_out[0] = 0.0;
+        if (counts_out) memset(counts_out, 0, (size_t)m->dev[0]->run_k * 4 * sizeof(int32_t));
+    }
+    if (n_out) *n_out = best < 0 ? 1 : N;
+    if (sum_out) *sum_out = best < 0 ? 0.0 : m->sums[(size_t)best];
+    if (restart_out) *restart_out = best;
+    if (stats_out) *stats_out = total;
+    return GIBBS_OK;
 }
 
 int32_t gibbs_device_results(gibbs_handle *h, void **sites_dev, void **scores_dev, void **sums_dev) {

@@ -399,6 +399,110 @@ struct Hist {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// bit-sliced base counters for the random starts (fs:418-426): no table lookups
+// ------------------------------------------------------------------------------------------------
+// A k-mer is 2 bits per column. f_b = a 1 in the even bit of every column whose base is b (b = 1, 2, 3: three LOP3;
+// base 0 is what is left: count_0 = k-mers added - count_1 - count_2 - count_3). Four k-mers are added at once (one
+// Philox block): f(x0) + f(x1) + f(x2) fits the 2-bit column fields, and together with f(x3) the even / odd columns go
+// into 4-bit fields (8 per word), which take 3 such quads before they are spread into 8-bit fields (255 k-mers per
+// lane between warp reductions). ~11 integer instructions per k-mer against ~45 for the pair-LUT histogram (6 shared
+// loads + extraction per k-mer), which is what the random starts of a C2 step spent half their instructions on.
+template <int KP>
+struct KmerCounter {
+    static constexpr int NW = (KP > 8) ? 2 : 1; // 32-bit words of a k-mer (16 columns each)
+    uint32_t nib[NW][3][2];      // [word][base - 1][column parity]: 4-bit fields, field m = column 16 word + 2 m + parity
+    uint32_t byt[NW][3][2][2];   // [..][nibble parity h]: 8-bit fields, field q = column 16 word + 4 q + 2 h + parity
+    int quads;                   // quads since the last nibble spill (<= 3)
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) nib[w][b][p] = byt[w][b][p][0] = byt[w][b][p][1] = 0;
+        quads = 0;
+    }
+    __device__ __forceinline__ void spill() {
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    byt[w][b][p][0] += nib[w][b][p] & 0x0F0F0F0Fu;
+                    byt[w][b][p][1] += (nib[w][b][p] >> 4) & 0x0F0F0F0Fu;
+                    nib[w][b][p] = 0;
+                }
+        quads = 0;
+    }
+    // four k-mers (an invalid draw passes 0: base 0 everywhere, counted nowhere)
+    __device__ __forceinline__ void add4(const uint64_t x[4]) {
+        if (quads == 3) spill();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            uint32_t f[4][3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t v = (uint32_t)(x[i] >> (32 * w)), t = v >> 1;
+                f[i][0] = v & ~t & 0x55555555u;
+                f[i][1] = ~v & t & 0x55555555u;
+                f[i][2] = v & t & 0x55555555u;
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const uint32_t s3 = f[0][b] + f[1][b] + f[2][b]; // <= 3 per 2-bit field
+                nib[w][b][0] += (s3 & 0x33333333u) + (f[3][b] & 0x11111111u);
+                nib[w][b][1] += ((s3 >> 2) & 0x33333333u) + ((f[3][b] >> 2) & 0x11111111u);
+            }
+        }
+        ++quads;
+    }
+    // dst[j*4 + b] = warp totals for b = 1, 2, 3 and columns j < k; dst[j*4] = added - the three (added = k-mers the
+    // whole warp added since the last flush). At most 252 k-mers per lane between flushes. dst is overwritten when
+    // first, else increased.
+    __device__ __forceinline__ void flush(int32_t *dst, int k, int added, bool first, int lane) {
+        spill();
+        if (first) {
+            for (int e = lane; e < 8 * KP; e += 32) dst[e] = 0; // columns 0 .. 2 KP - 1 (k or k + 1 of them)
+            __syncwarp();
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) { // g = 0: byte fields 0, 2; g = 1: byte fields 1, 3
+                            const int c0 = 16 * w + 4 * g + 2 * h + p, c1 = c0 + 8; // columns of the two 16-bit halves
+                            if (c0 < 2 * KP) {
+                                const uint32_t s = __reduce_add_sync(FULL, (byt[w][b][p][h] >> (8 * g)) & 0x00FF00FFu);
+                                if (lane == ((c0 + 5 * b) & 31)) {
+                                    if (c0 < k) dst[c0 * 4 + b + 1] += (int32_t)(s & 0xFFFFu);
+                                    if (c1 < k) dst[c1 * 4 + b + 1] += (int32_t)(s >> 16);
+                                }
+                            }
+                        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) byt[w][b][p][0] = byt[w][b][p][1] = 0;
+        __syncwarp();
+        if (lane < k) dst[lane * 4] += added;
+        __syncwarp();
+    }
+    // after the last flush: base 0 = what the other three left
+    static __device__ __forceinline__ void finish(int32_t *dst, int k, int lane) {
+        if (lane < k) dst[lane * 4] -= dst[lane * 4 + 1] + dst[lane * 4 + 2] + dst[lane * 4 + 3];
+        __syncwarp();
+    }
+};
+
 // counts over the sites of all sequences except `exclude` (sites < 0 = no site), positions shifted
 // by `mode`: the fused PFM of fs:392-396 (exclude = held-out) or the all-sites total. All T warps
 // of the team take part; ends with a team sync.

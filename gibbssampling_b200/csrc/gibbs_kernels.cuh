@@ -113,43 +113,51 @@ static __global__ void wtab_kernel(int n, double pc, double den, double q0, doub
 #endif
 // MASKED = the set holds symbols outside A,C,G,T: a separate instantiation, so that the ACGT loop stays free of calls
 // and keeps its loads batched (with the check inline the random starts of C2 cost 60 % more instructions).
-template <int KP, int NB, bool MASKED>
+// SROWS = `rows` is a copy of the packed set in shared memory (init_smem_kernel): the gathers are LDS, not L1 sectors.
+// The base counts are kept bit-sliced in registers (KmerCounter): no lookup table.
+template <int KP, int NB, bool MASKED, bool SROWS = false>
 __device__ __forceinline__ void random_loo_counts_impl(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
-                                                       int32_t *counts, const uint32_t *lut, int lane, int32_t *fix) {
+                                                       int32_t *counts, int lane, int32_t *fix,
+                                                       const uint32_t *rows = nullptr) {
     const int N = a.s.n, k = a.k;
-    for (int e = lane; e < MAX_COLS * 4; e += 32) counts[e] = 0;
     if (MASKED) fix[lane] = 0; // fix[] = the warp's lgcol, free until build_tables
-    __syncwarp();
-    if (N < 2) return;
+    if (N < 2) {
+        for (int e = lane; e < 8 * KP; e += 32) counts[e] = 0;
+        __syncwarp();
+        return;
+    }
+    const uint32_t *const base_rows = SROWS ? rows : a.s.packed;
+    const int row_words = a.s.row_words;
     const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
     const uint64_t d_end = base + (uint64_t)(N - 1);
     const uint64_t blk0 = base >> 2, blk1 = (d_end + 3) >> 2;
-    const int iters = (int)((blk1 - blk0 + 32 * NB - 1) / (32 * NB));
+    const int n_blk = (int)(blk1 - blk0);
+    const int iters = (n_blk + 32 * NB - 1) / (32 * NB);
+    const int r_first = (int)((int64_t)(blk0 << 2) - (int64_t)base); // rank of the first draw of block blk0: -3 .. 0
     const int ulen = a.s.uniform_len;
-    Hist<KP> h;
+    const uint32_t key0 = (uint32_t)a.seed, key1 = (uint32_t)(a.seed >> 32);
+    const uint32_t c2 = (uint32_t)chain_uid, c3 = (uint32_t)(chain_uid >> 32);
+    KmerCounter<KP> h;
     h.clear();
-    constexpr int FLUSH_ROUNDS = 255 / (4 * NB); // byte counters hold 255 adds per lane
+    constexpr int FLUSH_ROUNDS = 63 / NB; // 63 quads = 252 k-mers per lane between warp reductions
+    bool first = true;
     for (int it0 = 0; it0 < iters; it0 += FLUSH_ROUNDS) {
         const int it1 = min(iters, it0 + FLUSH_ROUNDS);
         for (int it = it0; it < it1; ++it) {
-            uint64_t kmer[4 * NB];
-            bool valid[4 * NB];
+            uint64_t kmer[NB][4];
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
-                const uint64_t blk = blk0 + ((uint64_t)it * NB + q) * 32 + lane;
+                const int bi = (it * NB + q) * 32 + lane; // block index inside this held-out sequence's draw range
+                const uint64_t blk = blk0 + (uint64_t)bi;
                 uint32_t wd[4] = {0, 0, 0, 0};
                 if (a.rng_mode == 0) {
-                    const uint4 r = philox4x32_10(
-                        make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
-                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3), make_uint2(key0, key1));
                     wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
                 }
-                // rank of draw x of this block among the held-out sequence's draws; valid iff 0 <= r < N-1
-                const int r0 = (int)((int64_t)(blk << 2) - (int64_t)base);
+                const int r0 = r_first + 4 * bi; // rank of draw 0 of this block; a draw is valid iff 0 <= rank < N-1
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     const bool ok = (unsigned)(r0 + x) < (unsigned)(N - 1);
-                    valid[q * 4 + x] = ok;
                     const int r = ok ? r0 + x : 0;
                     const int i = r + (r >= n ? 1 : 0); // always a valid sequence index (N >= 2)
                     const int range = (ulen > 0 ? ulen : __ldg(a.s.len + i)) - k + 1;
@@ -158,27 +166,24 @@ __device__ __forceinline__ void random_loo_counts_impl(const ChainArgs &a, uint6
                         pos = (int)__umulhi(wd[x], (uint32_t)range); // floor(word * 2^-32 * range), exact
                     } else {
                         const int64_t d = (int64_t)base + r;
-                        const double u = (ok && d < a.uniforms_per_chain)
-                                             ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
-                                             : 0.0;
+                        const double u = d < a.uniforms_per_chain ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
+                                                                  : 0.0; // (the host rejects streams that are too short)
                         pos = (int)(u * (double)range);      // rnd.Next(0, L-k+1), fs:145
                         pos = min(max(pos, 0), range - 1);   // memory safety for u outside [0,1)
                     }
-                    kmer[q * 4 + x] = kmer_global<KP>(a.s.packed + (size_t)i * a.s.row_words, pos);
-                    if (MASKED && ok && __ldg(a.s.rowflag + i) != 0) hist_fix(a.s.mask, a.s.row_words, i, pos, k, fix);
+                    const uint32_t *rp = base_rows + (size_t)i * row_words;
+                    const uint64_t km = SROWS ? kmer_shared<KP>(rp, pos) : kmer_global<KP>(rp, pos);
+                    kmer[q][x] = ok ? km : 0ull; // code 0 in every column: counted nowhere
+                    if (MASKED && ok && __ldg(a.s.rowflag + i) != 0) hist_fix(a.s.mask, row_words, i, pos, k, fix);
                 }
             }
 #pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                h.maybe_spill(4);
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (valid[q * 4 + x]) h.add(kmer[q * 4 + x], lut); // invalid only at the two ends of the draw range
-            }
+            for (int q = 0; q < NB; ++q) h.add4(kmer[q]);
         }
-        h.template flush_add<false>(counts, k, lane);
+        h.flush(counts, k, it1 == iters ? N - 1 : 0, first, lane);
+        first = false;
     }
-    __syncwarp();
+    KmerCounter<KP>::finish(counts, k, lane);
     if (MASKED) {
         if (lane < k) counts[lane * 4] -= fix[lane];
         __syncwarp();
@@ -246,7 +251,7 @@ static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS)
         const uint32_t *row = rows + (v & 1u) * row_words;
         const int chain = (int)(item / N), n = (int)(item % N);
         const int Wn = __ldg(a.s.len + n) - k + 1;
-        random_loo_counts_impl<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE), false>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lut, lane, WT.lgcol);
+        random_loo_counts_impl<KP, (KP <= 6 ? GIBBS_P0_NB_INIT_SMALL : GIBBS_P0_NB_INIT_LARGE), false>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts, lane, WT.lgcol);
         double p;
         int w;
         bool slow;
@@ -270,6 +275,79 @@ static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS)
         __syncwarp();
         item = next;
         ++v;
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
+        atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
+        atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
+    }
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)a.n_chains);
+}
+
+// ------------------------------------------------------------------------------------------------
+// random starts with the whole packed set resident in shared memory
+// ------------------------------------------------------------------------------------------------
+// The N(N-1) draws of a restart gather a k-mer at a random position of every other sequence. From global memory that
+// is 2-3 L1 sector requests per draw, each a wavefront of its own (random rows); when the packed set fits beside the
+// per-warp tables (C2: 144 KB of 227 KB) one CTA per SM keeps a copy in shared memory and the gathers become LDS with
+// a few-way bank conflict. One warp per (chain, held-out sequence) item, grid-stride; the held-out row is scanned from
+// the same copy, so this kernel issues no TMA at all.
+#ifndef GIBBS_ISM_WARPS
+#define GIBBS_ISM_WARPS 32 // 64 registers per thread: no spills at k <= 12 (24 warps / 80 registers spill 108 B)
+#endif
+#ifndef GIBBS_P0_NB_ISM
+#define GIBBS_P0_NB_ISM 1  // LDS latency is short: one Philox block (4 gathers) in flight per lane is enough
+#endif
+constexpr int ISM_WARPS = GIBBS_ISM_WARPS;
+
+// per-warp tables sized for the k at hand: wcol 64 KP + ptab 64 KP + lgcol 32 KP + counts 32 KP bytes
+__host__ __device__ constexpr int ism_table_bytes(int kp) { return 192 * kp; }
+__host__ __device__ inline size_t init_smem_rows_bytes(int n, int row_words) { return (size_t)n * row_words * 4; }
+__host__ __device__ inline size_t init_smem_total_bytes(int n, int row_words, int kp) {
+    return init_smem_rows_bytes(n, row_words) + (size_t)ISM_WARPS * ism_table_bytes(kp);
+}
+
+template <int KP>
+static __global__ void __launch_bounds__(ISM_WARPS * 32, 1) init_smem_kernel(const ChainArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.s.n, k = a.k, row_words = a.s.row_words;
+    uint32_t *rows = reinterpret_cast<uint32_t *>(smem_raw);
+    WarpTables WT;
+    {
+        unsigned char *b = smem_raw + init_smem_rows_bytes(N, row_words) + warp * ism_table_bytes(KP);
+        WT.wcol = reinterpret_cast<double *>(b);
+        WT.ptab = reinterpret_cast<int32_t *>(b + 64 * KP);
+        WT.lgcol = reinterpret_cast<int32_t *>(b + 128 * KP);
+        WT.counts = reinterpret_cast<int32_t *>(b + 160 * KP);
+    }
+    {   // rows are multiples of 16 B
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.s.packed);
+        uint4 *dst = reinterpret_cast<uint4 *>(rows);
+        const int n16 = N * (row_words >> 2);
+        for (int i = tid; i < n16; i += ISM_WARPS * 32) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const long long total = (long long)a.n_chains * N;
+    const long long stride = (long long)gridDim.x * ISM_WARPS;
+    unsigned long long st_updates = 0, st_windows = 0, st_slow = 0;
+    for (long long item = (long long)blockIdx.x * ISM_WARPS + warp; item < total; item += stride) {
+        const int chain = (int)(item / N), n = (int)(item % N);
+        const int Wn = __ldg(a.s.len + n) - k + 1;
+        random_loo_counts_impl<KP, GIBBS_P0_NB_ISM, false, true>(a, (uint64_t)a.chain_id_base + (uint64_t)chain, chain, n, WT.counts,
+                                                                 lane, WT.lgcol, rows);
+        build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+        double p;
+        int w;
+        const bool slow = pick_argmax<KP>(WT, rows + (size_t)n * row_words, Wn, k, a.fast_ok, lane, p, w);
+        if (lane == 0) {
+            a.sites[(size_t)chain * N + n] = w;
+            a.hv[(size_t)chain * N + n] = p;
+        }
+        st_updates += 1;
+        st_windows += (unsigned long long)Wn;
+        st_slow += slow ? 1 : 0;
+        __syncwarp();
     }
     if (lane == 0) {
         atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
@@ -341,6 +419,9 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
         // +new site), once per sweep for the shift phases (they read the shifted snapshot, fs:357)
         if (phase == PH_LEFT || phase == PH_RIGHT || (phase == PH_GREEDY && (sweeps_in_phase == 0 || resumed)))
             site_counts<KP, T>(a.s, sites, -1, k, mode, S.total, S.lut, S.fix, tid);
+        else
+            team_sync<T>(); // the last round of the previous sweep wrote sites / hv after its only barrier: the block
+                            // loads below must see them (a stale hv_n could flip an accept of the sequential sweep)
         resumed = false;
         // state of two 32-sequence blocks (lengths, sites, raw scores): coalesced loads, kept one block ahead
         auto load_block = [&](int b) {
@@ -388,7 +469,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
                     const bool given = phase == PH_INIT && a.ppm_given != nullptr;
                     const bool fast = a.drift_fast_ok && !given; // (a supplied PPM may hold zeros or denormals: exact scan)
                     if (phase == PH_INIT) {
-                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, lane, WT.lgcol);
                         drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
                     } else {
                         site_n = S.blk_site[o];
@@ -401,7 +482,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
                     slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w, MASKED ? masked_n : -1, n);
                 } else {
                     if (phase == PH_INIT) {
-                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                        random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, lane, WT.lgcol);
                         build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                     } else {
                         site_n = S.blk_site[o];
@@ -614,18 +695,113 @@ static __global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, con
     for (int e = lane; e < k * 4; e += 32) counts_out[e] = S.total[e];
 }
 
-// first chain with the largest sum (strict >), the restart selection of fs:450 / fs:156-170
-static __global__ void best_chain_kernel(const double *sums, int n_chains, int *best_out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int best = 0;
-        double bs = sums[0];
-        for (int c = 1; c < n_chains; ++c)
-            if (sums[c] > bs) {
-                bs = sums[c];
-                best = c;
-            }
-        *best_out = best;
+// first chain with the largest sum (strict >), the restart selection of fs:450 / fs:156-170: what the sequential
+//   best = 0; for c = 1 ..: if sums[c] > sums[best] then best = c
+// returns (a NaN sum never wins a comparison; with sums[0] = NaN nothing beats it). One CTA.
+static __global__ void __launch_bounds__(256) best_chain_kernel(const double *sums, int n_chains, int *best_out) {
+    __shared__ double s_v[256];
+    __shared__ int s_i[256];
+    double bv = -INFINITY;
+    int bi = INT32_MAX;
+    for (int c = threadIdx.x; c < n_chains; c += 256) {
+        const double v = sums[c];
+        if (v > bv || (v == bv && c < bi)) { // ascending c per thread: ties keep the lowest index
+            bv = v;
+            bi = c;
+        }
     }
+    s_v[threadIdx.x] = bv;
+    s_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double ov = s_v[threadIdx.x + o];
+            const int oi = s_i[threadIdx.x + o];
+            if (ov > s_v[threadIdx.x] || (ov == s_v[threadIdx.x] && oi < s_i[threadIdx.x])) {
+                s_v[threadIdx.x] = ov;
+                s_i[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double s0 = sums[0];
+        // every sum NaN or -inf: nothing is > sums[0]
+        *best_out = (s0 != s0 || s_i[0] == INT32_MAX || !(s_v[0] > s0)) ? 0 : s_i[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the promote-or-restart loop of fs:435-459 (= fs:616-640, fs:665-689, fs:857-881, fs:974-998; quirk A.6-8), decided on
+// the device over the restarts of one run (chain r = restart r)
+// ------------------------------------------------------------------------------------------------
+//   loop n acc best:  n > reps -> best | acc = best -> best | sum acc > sum best -> loop (n+1) [||] (acc unless empty)
+//                     | else -> loop (n+1) (next restart) best          starting from  loop 0 [||] [|(0., 0)|]
+// Every restart costs one iteration and every promotion one more, so restart r sits in `acc` at iteration
+// r + 1 + 2 * (promotions so far). One warp walks the sums 32 restarts at a time and stops only at EVENTS: the iteration
+// cap, a sum equal to the best one (acc = best needs the arrays compared, rare) or a larger sum (promotion). A promoted
+// restart with a negative sum ends the loop (0. > sum best then burns the remaining iterations without running anything).
+// out[0] = index of the returned restart, -1 = the initial value survived (the caller returns [|(0., 0)|]);
+// the winner's rows are copied to win_sites / win_scores so that one fixed-address copy brings them to the host.
+// motif = the MotifIndex flavour of the initial value: {PWMS 0.; Positions []} (site -1) instead of (0., 0).
+static __global__ void __launch_bounds__(32) restart_select_kernel(const double *sums, const int32_t *sites, const double *scores,
+                                                                   int n_chains, int N, int reps, int motif, int32_t *out,
+                                                                   int32_t *win_sites, double *win_scores, double *win_sum) {
+    const int lane = threadIdx.x;
+    int best = -1;
+    double bsum = 0.0;
+    int r_next = 0;       // next restart to look at ...
+    long long n_next = 1; // ... and the iteration at which it sits in acc (restart 0 was run at iteration 0)
+    bool done = false;
+    while (!done && r_next < n_chains) {
+        const int r = r_next + lane;
+        const bool valid = r < n_chains;
+        const double s = valid ? sums[r] : 0.0;
+        const long long nj = n_next + lane;
+        const unsigned evs = __ballot_sync(FULL, valid && (nj > (long long)reps || s == bsum || s > bsum));
+        if (!evs) { // 32 restarts that are neither promoted nor equal to the best: one iteration each
+            const int cnt = min(32, n_chains - r_next);
+            r_next += cnt;
+            n_next += cnt;
+            continue;
+        }
+        const int j = __ffs(evs) - 1;
+        const int r_j = r_next + j;
+        const long long n_j = n_next + j;
+        const double s_j = __shfl_sync(FULL, s, j);
+        if (n_j > (long long)reps) break; // n > reps: the restart in acc is returned past, never compared
+        if (s_j == bsum) {                // acc = best? structural equality of the two arrays (F# (=): NaN <> NaN)
+            bool same;
+            if (best < 0) {
+                same = N == 1 && scores[(size_t)r_j * N] == 0.0 && sites[(size_t)r_j * N] == (motif ? -1 : 0);
+            } else {
+                bool diff = false;
+                for (int i = lane; i < N; i += 32)
+                    diff |= sites[(size_t)r_j * N + i] != sites[(size_t)best * N + i] ||
+                            !(scores[(size_t)r_j * N + i] == scores[(size_t)best * N + i]);
+                same = !__any_sync(FULL, diff);
+            }
+            if (same) break;
+            r_next = r_j + 1; // not promoted: the next restart is run at iteration n_j and sits in acc at n_j + 1
+            n_next = n_j + 1;
+            continue;
+        }
+        // promotion: best <- acc costs iteration n_j; the next restart is run at n_j + 1 and sits in acc at n_j + 2
+        best = r_j;
+        bsum = s_j;
+        if (bsum < 0.0) done = true; // `0. > sum best`: the loop promotes the empty acc until n > reps; nothing else runs
+        r_next = r_j + 1;
+        n_next = n_j + 2;
+    }
+    if (lane == 0) {
+        out[0] = best;
+        *win_sum = best < 0 ? 0.0 : sums[best];
+    }
+    if (best >= 0)
+        for (int i = lane; i < N; i += 32) {
+            win_sites[i] = sites[(size_t)best * N + i];
+            win_scores[i] = scores[(size_t)best * N + i];
+        }
 }
 
 // ------------------------------------------------------------------------------------------------

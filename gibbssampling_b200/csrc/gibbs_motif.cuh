@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
             const int len_n = __ldg(a.s.len + n);
             const int W = len_n - k + 1;
             if (phase == MPH_INIT) { // getPWMOfRandomStarts[WithBPV] |> createMotifIndex prob [position] (fs:876-877, fs:993-994)
-                random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, false>(a, chain_uid, chain, n, WT.counts, S.lut, lane, WT.lgcol);
+                random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, false>(a, chain_uid, chain, n, WT.counts, lane, WT.lgcol);
                 double p;
                 int w;
                 if (!m.data_bg) {

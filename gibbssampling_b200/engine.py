@@ -64,6 +64,17 @@ def _ptr(a: Optional[np.ndarray], t):
 
 
 @dataclass
+class BestResult:
+    """What the reference's restart loops return (fs:434, fs:615, fs:856, fs:973): one (float*int)[] / MotifIndex[]."""
+    sites: np.ndarray        # int32 [n] (or [1] when the loop's initial value survived)
+    scores: np.ndarray       # float64, same length
+    total: float             # Array.sum of the scores
+    restart: int             # which restart it is, -1 = the initial value [|(0., 0)|]
+    counts: Optional[np.ndarray]
+    stats: dict
+
+
+@dataclass
 class RunResult:
     sites: np.ndarray        # int32 [chains, n]  (-1 = no site)
     scores: np.ndarray       # float64 [chains, n]
@@ -150,6 +161,10 @@ class GibbsEngine:
 
     def synchronize(self) -> None:
         _abi.check(self._lib.gibbs_synchronize(self._h))
+
+    def set_option(self, option: int, value: int) -> None:
+        """Explicit test / measurement switches (_abi.GIBBS_OPT_*); none changes a result."""
+        _abi.check(self._lib.gibbs_set_option(self._h, C.c_int32(option), C.c_int32(value)))
 
     # -- primitives ---------------------------------------------------------------------------
     def _sites(self, sites) -> np.ndarray:
@@ -279,6 +294,24 @@ class GibbsEngine:
         stats = {f: getattr(st, f) for f, _ in RunStats._fields_}
         return RunResult(sites, scores, sums, int(best.value), counts, stats)
 
+    def fetch_best(self, repetitions: int, *, want_counts: bool = False, pinned: bool = False) -> BestResult:
+        """The promote-or-restart loop of fs:435-459 over the restarts of the last run_device, decided on the GPU:
+        only the winner's rows come back (gibbs_fetch_best)."""
+        n_chains, k = self._last
+        if pinned:
+            sites = self._pinned("best_sites", (self.n,), np.int32)
+            scores = self._pinned("best_scores", (self.n,), np.float64)
+        else:
+            sites = np.zeros(self.n, dtype=np.int32)
+            scores = np.zeros(self.n, dtype=np.float64)
+        counts = np.zeros((k, 4), dtype=np.int32) if want_counts else None
+        n_out, restart, total, st = C.c_int32(), C.c_int32(), C.c_double(), RunStats()
+        _abi.check(self._lib.gibbs_fetch_best(self._h, C.c_int32(repetitions), _ptr(sites, C.c_int32),
+                                              _ptr(scores, C.c_double), C.byref(n_out), C.byref(total),
+                                              C.byref(restart), _ptr(counts, C.c_int32), C.byref(st)))
+        stats = {f: getattr(st, f) for f, _ in RunStats._fields_}
+        return BestResult(sites[: n_out.value], scores[: n_out.value], total.value, int(restart.value), counts, stats)
+
     def run(self, params: Params, n_chains: int, *, chain_id_base: int = 0, seed: int = 0,
             uniforms: Optional[np.ndarray] = None, **fetch_kw) -> RunResult:
         self.run_device(params, n_chains, chain_id_base=chain_id_base, seed=seed, uniforms=uniforms)
@@ -289,6 +322,69 @@ class GibbsEngine:
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _abi.check(self._lib.gibbs_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+class MultiEngine:
+    """One process, several GPUs (gibbs_multi_*): the sequences replicated on every device, the restarts of a run
+    split into contiguous blocks over them. The F# shim uses the same calls for the restart loops."""
+
+    def __init__(self, sources: Sequence, n_devices: int = 0, devices: Optional[Sequence[int]] = None):
+        self._lib = _abi.load()
+        self._m = C.c_void_p()
+        buf, off = flatten_sources(sources)
+        self.n = len(off) - 1
+        dev = np.ascontiguousarray(devices, dtype=np.int32) if devices is not None else None
+        if dev is not None:
+            n_devices = len(dev)
+        _abi.check(self._lib.gibbs_multi_create(_ptr(buf, C.c_uint8), _ptr(off, C.c_int64), C.c_int32(self.n),
+                                                _ptr(dev, C.c_int32), C.c_int32(n_devices), C.byref(self._m)))
+        self.n_devices = int(self._lib.gibbs_multi_num_devices(self._m))
+        self._k = 0
+
+    def close(self) -> None:
+        if getattr(self, "_m", None) is not None and self._m.value:
+            self._lib.gibbs_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, option: int, value: int) -> None:
+        for i in range(self.n_devices):
+            h = self._lib.gibbs_multi_handle(self._m, C.c_int32(i))
+            _abi.check(self._lib.gibbs_set_option(C.c_void_p(h), C.c_int32(option), C.c_int32(value)))
+
+    def run_device(self, params: Params, n_chains: int, *, chain_id_base: int = 0, seed: int = 0,
+                   uniforms: Optional[np.ndarray] = None) -> None:
+        if uniforms is not None:
+            u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(n_chains, -1)
+            _abi.check(self._lib.gibbs_multi_run_device(self._m, C.byref(params), C.c_int32(n_chains), C.c_int64(chain_id_base),
+                                                        C.c_uint64(seed), C.c_int32(_abi.GIBBS_RNG_INJECTED),
+                                                        _ptr(u, C.c_double), C.c_int64(u.shape[1])))
+        else:
+            _abi.check(self._lib.gibbs_multi_run_device(self._m, C.byref(params), C.c_int32(n_chains), C.c_int64(chain_id_base),
+                                                        C.c_uint64(seed), C.c_int32(_abi.GIBBS_RNG_PHILOX), None, C.c_int64(0)))
+        self._k = int(params.k)
+
+    def fetch_best(self, repetitions: int, *, want_counts: bool = False) -> BestResult:
+        sites = np.zeros(self.n, dtype=np.int32)
+        scores = np.zeros(self.n, dtype=np.float64)
+        counts = np.zeros((self._k, 4), dtype=np.int32) if want_counts else None
+        n_out, restart, total, st = C.c_int32(), C.c_int32(), C.c_double(), RunStats()
+        _abi.check(self._lib.gibbs_multi_fetch_best(self._m, C.c_int32(repetitions), _ptr(sites, C.c_int32),
+                                                    _ptr(scores, C.c_double), C.byref(n_out), C.byref(total),
+                                                    C.byref(restart), _ptr(counts, C.c_int32), C.byref(st)))
+        stats = {f: getattr(st, f) for f, _ in RunStats._fields_}
+        return BestResult(sites[: n_out.value], scores[: n_out.value], total.value, int(restart.value), counts, stats)
 
 
 def device_count() -> int:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GIBBS_ABI_VERSION 1
+#define GIBBS_ABI_VERSION 2
 #define GIBBS_MAX_K 32          /* motif width limit of the packed 64-bit window register      */
 #define GIBBS_MAX_LEN (1 << 20) /* longest sequence                                            */
 
@@ -45,7 +45,8 @@ typedef enum gibbs_status {
     GIBBS_ERR_SYMBOL = 2,      /* IndexOutOfRangeException: symbol outside '*'..'Z' (fs:17, fs:20)   */
     GIBBS_ERR_SHORT_SEQ = 3,   /* InvalidOperationException from Array.take when L < k (fs:152)     */
     GIBBS_ERR_CUDA = 4,        /* CUDA runtime / launch failure or no usable device                 */
-    GIBBS_ERR_NCCL = 5,        /* reserved: collectives run in the host layer (torch.distributed)   */
+    GIBBS_ERR_NCCL = 5,        /* reserved: the one-process multi-device calls need no collective; one process */
+                               /* per GPU uses the host layer's all_gather (torch.distributed)      */
     GIBBS_ERR_NOMEM = 6,       /* host or device allocation failed                                  */
     GIBBS_ERR_ROULETTE = 7,    /* ArgumentException of fs:753: pick beyond the accumulated mass     */
     GIBBS_ERR_UNSUPPORTED = 8  /* a mode outside the built hot path (out of scope)   */
@@ -96,7 +97,7 @@ typedef struct gibbs_run_stats {
     int32_t kernel_launches; /* CUDA kernels launched by the call                               */
     int32_t fast_path;     /* 1 = fixed-point filter + float64 verification was usable          */
     int32_t team_warps;    /* warps per chain of the first launch (1, 4, 8 or 16)               */
-    int32_t reserved;
+    int32_t init_path;     /* where the random starts ran: GIBBS_INIT_CHAIN / _WIDE / _SMEM       */
     double kernel_ms;      /* device time of the chain kernel (CUDA events on the handle stream) */
 } gibbs_run_stats;
 
@@ -126,6 +127,21 @@ int32_t gibbs_num_sequences(const gibbs_handle *h);
  * 2 (1) chains per SM are handed over to launches with 8 (16) warps per chain */
 int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps);
 int32_t gibbs_synchronize(gibbs_handle *h);
+/*
+ * Explicit per-handle switches for tests and measurements (no environment variable changes what a caller gets).
+ * None of them changes a result.
+ *   GIBBS_OPT_INIT_PATH    where the random starts (fs:412-430) run: GIBBS_INIT_AUTO (default) picks per launch;
+ *                          _CHAIN = inside the chain kernel, _WIDE = grid-wide kernel gathering from global memory,
+ *                          _SMEM = grid-wide kernel with the packed set in shared memory (used only when it fits)
+ *   GIBBS_OPT_EXACT_SCANS  1 = no ranking pass anywhere: every window in float64, sequential roulette walk
+ */
+#define GIBBS_OPT_INIT_PATH 1
+#define GIBBS_OPT_EXACT_SCANS 2
+#define GIBBS_INIT_AUTO 0
+#define GIBBS_INIT_CHAIN 1
+#define GIBBS_INIT_WIDE 2
+#define GIBBS_INIT_SMEM 3
+int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value);
 
 /* ---- primitives: parity can be checked at the level the reference composes them -------------- */
 /*
@@ -199,6 +215,19 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
  */
 int32_t gibbs_fetch(gibbs_handle *h, int32_t *sites_out, double *scores_out, double *sums_out,
                     int32_t *best_chain_out, int32_t *counts_out, gibbs_run_stats *stats_out);
+/*
+ * Replaces: the promote-or-restart loop of getMotifsWithBestInformationContentWithBPV (fs:435-459; the same loop is
+ * fs:616-640, fs:665-689, fs:857-881, fs:974-998; quirk A.6-8) over the restarts of the last gibbs_run_device, chain r
+ * being restart r, with numberOfRepetitions = repetitions. The loop is decided on the device and only its result
+ * crosses PCIe:
+ *   sites_out  int32 [n_seqs], scores_out double [n_seqs]   the returned (float*int)[] / MotifIndex[]
+ *   n_out      its length: n_seqs, or 1 when the loop's initial value [|(0., 0)|] survives
+ *   sum_out    Array.sum of its scores; restart_out  which restart it is (-1 = the initial value)
+ *   counts_out int32 [k][4]  PWM counts of its sites
+ */
+int32_t gibbs_fetch_best(gibbs_handle *h, int32_t repetitions, int32_t *sites_out, double *scores_out,
+                         int32_t *n_out, double *sum_out, int32_t *restart_out, int32_t *counts_out,
+                         gibbs_run_stats *stats_out);
 /* gibbs_run_device + gibbs_fetch */
 int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base,
                   uint64_t seed, int32_t rng_mode, const double *uniforms_or_null,
@@ -207,6 +236,35 @@ int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int6
                   gibbs_run_stats *stats_out);
 /* device pointers of the last run, for zero-copy collectives in the host layer (may be NULL) */
 int32_t gibbs_device_results(gibbs_handle *h, void **sites_dev, void **scores_dev, void **sums_dev);
+
+/* ---- one process, several devices ------------------------------------------------------------------------------ */
+/*
+ * Replaces: the restart axis the reference's author parallelised in the commented-out lines
+ *   PSeq.map (fun _ -> doSiteSampling ...) (fsx:430)  /  PSeq.init 10 (fun _ -> doMotifSamplingWithPPM ...) (fsx:1162).
+ * One handle per device with the sequences replicated on each; the restarts of a run are split into contiguous blocks
+ * over the devices and run concurrently. Restart r uses the uniform stream (seed, chain_id_base + r) whatever device
+ * it lands on, so results do not depend on the number of devices. No device-to-device traffic: the promote-or-restart
+ * loop (fs:435-459) is decided on the host from one float64 sum per restart, then the winner's rows are fetched from
+ * the device that holds them. (One process per GPU with a final NCCL all_gather is the other way to shard the same
+ * axis; that is what bench.py --gpus N does through gibbssampling_b200/distributed.py.)
+ * devices = NULL: devices 0 .. n_devices-1; n_devices = 0: every visible device.
+ */
+typedef struct gibbs_multi gibbs_multi;
+int32_t gibbs_multi_create(const uint8_t *seqs, const int64_t *offsets, int32_t n_seqs, const int32_t *devices,
+                           int32_t n_devices, gibbs_multi **out);
+int32_t gibbs_multi_destroy(gibbs_multi *m);
+int32_t gibbs_multi_num_devices(const gibbs_multi *m);
+/* the handle of device slot i (for gibbs_set_option, gibbs_set_start_ppm ...); owned by m */
+gibbs_handle *gibbs_multi_handle(gibbs_multi *m, int32_t i);
+/* gibbs_run_device on every device: n_chains restarts in total */
+int32_t gibbs_multi_run_device(gibbs_multi *m, const gibbs_params *p, int32_t n_chains, int64_t chain_id_base,
+                               uint64_t seed, int32_t rng_mode, const double *uniforms_or_null,
+                               int64_t uniforms_per_chain);
+/* gibbs_fetch_best over the restarts of all devices (restart_out is the global restart index);
+ * stats: counters summed over the devices, kernel_ms = the slowest device */
+int32_t gibbs_multi_fetch_best(gibbs_multi *m, int32_t repetitions, int32_t *sites_out, double *scores_out,
+                               int32_t *n_out, double *sum_out, int32_t *restart_out, int32_t *counts_out,
+                               gibbs_run_stats *stats_out);
 
 /* ---- host buffers ------------------------------------------------------------------------------- */
 /* Page-locked host memory for the *_out arrays above (results of 1024 chains x 1000 sequences are

@@ -997,3 +997,371 @@ int or_get_best_information_content(const double *scores, const int32_t *lens, i
     *best_index_out = best;
     return OR_OK;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* INCREMENTAL MODE of the SiteSampler pipelines (test infrastructure for full-size parity)    */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * The faithful functions above cost O(N (L + 49 k) + W (L + 49 k)) per site update because they
+ * repeat the reference's redundant work (from-scratch leave-one-out rebuilds fs:392-396, a PWM
+ * per window fs:309, Array.skip / Array.append copies). At the BASELINE sizes (1000 x 500 bp x
+ * 1024 chains, 10 k x 1 kb, 100 k x 200 bp) that is hours of CPU. This section computes the SAME
+ * values with the SAME float64 operations -- it calls the same static helpers ppm_of_pfm
+ * (fs:249-261), pwm_create (fs:282-287), pwm_segment_score (fs:290-293), pcv_normalized_of_fcv
+ * (fs:115-120), fcv_subtract_segment (fs:84-88) -- and only changes how the INTEGER inputs of
+ * those helpers are obtained:
+ *   - leave-one-out counts = counts over all current sites minus the held-out one-hot (integer
+ *     adds: exact), updated -old site / +new site when a greedy sweep moves a site;
+ *   - fixed background: the PWM is built once per site update instead of once per window (same
+ *     inputs, same divisions, same values);
+ *   - data-derived background: symbol counts per sequence are tabulated once, so
+ *     increaseInPlaceFCVOf (fs:79) is 49 integer adds instead of a pass over L symbols, and
+ *     createFCVWithout |> fuse (fs:565-568) is a running integer total;
+ *   - random starts: the Philox block of four draws is computed once, not once per draw; held-out
+ *     sequences are independent there (fresh draws for every other sequence, fs:595-598) and run
+ *     on n_threads OpenMP threads, each addressing the uniform stream by draw index.
+ * tests/test_oracle_fast.py requires bit-identical (scores, positions) from both modes on every
+ * small case of the existing suites; the golden fixtures of the BASELINE sizes
+ * (tests/golden/make_fullsize_golden.py) are generated with this mode.
+ */
+#include <pthread.h>
+
+/* dynamic parallel-for over [0, n_items) on n_threads POSIX threads (chunked, atomic cursor) */
+typedef void (*pf_body)(void *ctx, int32_t item, int32_t thread);
+typedef struct { pf_body body; void *ctx; int32_t n_items, chunk, thread; volatile int32_t *cursor; } pf_arg;
+static void *pf_worker(void *p) {
+    pf_arg *a = (pf_arg *)p;
+    for (;;) {
+        int32_t i0 = __sync_fetch_and_add(a->cursor, a->chunk);
+        if (i0 >= a->n_items) break;
+        int32_t i1 = i0 + a->chunk < a->n_items ? i0 + a->chunk : a->n_items;
+        for (int32_t i = i0; i < i1; ++i) a->body(a->ctx, i, a->thread);
+    }
+    return NULL;
+}
+static void parallel_for(int32_t n_items, int32_t n_threads, int32_t chunk, pf_body body, void *ctx) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    volatile int32_t cursor = 0;
+    pf_arg args[256];
+    pthread_t th[256];
+    for (int32_t t = 0; t < n_threads; ++t) {
+        args[t].body = body; args[t].ctx = ctx; args[t].n_items = n_items; args[t].chunk = chunk > 0 ? chunk : 1;
+        args[t].thread = t; args[t].cursor = &cursor;
+    }
+    int32_t started = 0;
+    for (int32_t t = 1; t < n_threads; ++t) {
+        if (pthread_create(&th[t], NULL, pf_worker, &args[t]) != 0) break;
+        started = t;
+    }
+    pf_worker(&args[0]);
+    for (int32_t t = 1; t <= started; ++t) pthread_join(th[t], NULL);
+}
+
+typedef struct {
+    const ctx_t *c;
+    int32_t *tot;      /* 49 * k: counts over all (shifted) sites                              */
+    int32_t *cnt;      /* n * 49: symbol counts per sequence (data-derived background only)    */
+    int64_t gtot[NS];  /* data background: sum over sequences of (cnt_i - k-mer counts of site) */
+    int32_t mult[NS];  /* how often a slot occurs in `alphabet` (fuse adds once per occurrence) */
+    double *ppm, *pwm; /* 49 * k                                                               */
+    int data_bg;
+} fast_t;
+
+static void fast_free(fast_t *f) { free(f->tot); free(f->cnt); free(f->ppm); free(f->pwm); }
+
+static int fast_init(fast_t *f, const ctx_t *c, int data_bg) {
+    memset(f, 0, sizeof *f);
+    f->c = c;
+    f->data_bg = data_bg;
+    size_t cells = (size_t)NS * c->k;
+    f->tot = (int32_t *)calloc(cells, sizeof(int32_t));
+    f->ppm = (double *)malloc(cells * sizeof(double));
+    f->pwm = (double *)calloc(cells, sizeof(double));
+    if (data_bg) f->cnt = (int32_t *)calloc((size_t)c->n * NS, sizeof(int32_t));
+    if (!f->tot || !f->ppm || !f->pwm || (data_bg && !f->cnt)) return OR_ERR_NOMEM;
+    for (int32_t a = 0; a < c->alen; ++a) f->mult[slot(c->alpha[a])] += 1;
+    if (data_bg)
+        for (int32_t i = 0; i < c->n; ++i) fcv_increase_in_place_of(seq_of(c, i), len_of(c, i), f->cnt + (size_t)i * NS);
+    return OR_OK;
+}
+
+static void onehot_add(const ctx_t *c, int32_t *pfm, int32_t i, int32_t p, int32_t d) {
+    const uint8_t *s = seq_of(c, i) + p;
+    for (int32_t j = 0; j < c->k; ++j) pfm[slot(s[j]) * c->k + j] += d;
+}
+
+/* fs:301-314 with the PWM hoisted out of the window loop */
+static void fast_scan_bpv(const ctx_t *c, const double *pwm, const uint8_t *src, int32_t len, double *score_out,
+                          int32_t *pos_out, or_stats *st) {
+    double high = 0.0;
+    int32_t hi = 0, k = c->k;
+    for (int32_t n = 0; n + k <= len; ++n) {
+        double tmp = pwm_segment_score(pwm, src + n, k);
+        if (tmp > high) { high = tmp; hi = n; }
+    }
+    if (st) { st->window_scores += len - k + 1; st->site_updates++; }
+    *score_out = log2_ref(high);
+    *pos_out = hi;
+}
+
+/* pwm_create (fs:282-287) for a matrix whose non-alphabet rows are already 0 */
+static void pwm_rows(const ctx_t *c, const double *pcv, const double *ppm, double *pwm) {
+    int32_t k = c->k;
+    for (int32_t a = 0; a < c->alen; ++a) {
+        int s = slot(c->alpha[a]);
+        for (int32_t j = 0; j < k; ++j) pwm[s * k + j] = ppm[s * k + j] / pcv[s];
+    }
+}
+
+/* fs:462-479: fcv starts as the fused background of the others; cnt_h = symbol counts of src */
+static void fast_scan_drift(const ctx_t *c, int32_t *fcv, const int32_t *cnt_h, const double *ppm, double *pwm,
+                            const uint8_t *src, int32_t len, double *score_out, int32_t *pos_out, or_stats *st) {
+    double high = 0.0, pcv[NS];
+    int32_t hi = 0, k = c->k;
+    for (int32_t n = 0; n + k <= len; ++n) {
+        for (int s = 0; s < NS; ++s) fcv[s] += cnt_h[s];   /* increaseInPlaceFCVOf source, fs:471 */
+        fcv_subtract_segment(src + n, k, fcv);             /* fs:472 */
+        pcv_normalized_of_fcv(c, fcv, pcv);                /* fs:473 */
+        pwm_rows(c, pcv, ppm, pwm);                        /* fs:474 */
+        double tmp = pwm_segment_score(pwm, src + n, k);
+        if (tmp > high) { high = tmp; hi = n; }
+    }
+    if (st) { st->window_scores += len - k + 1; st->site_updates++; }
+    *score_out = log2_ref(high);
+    *pos_out = hi;
+}
+
+/* one site update from leave-one-out counts `pfm` (49 x k) and, data background, the fused fcv of the others */
+static void fast_update(const fast_t *f, const int32_t *pfm, double *ppm, double *pwm, int32_t *fcv, const double *pcv,
+                        int32_t h, double *ts, int32_t *tp, or_stats *st) {
+    const ctx_t *c = f->c;
+    ppm_of_pfm(c, pfm, c->n - 1, ppm);
+    if (!f->data_bg) {
+        pwm_rows(c, pcv, ppm, pwm);
+        fast_scan_bpv(c, pwm, seq_of(c, h), len_of(c, h), ts, tp, st);
+    } else {
+        fast_scan_drift(c, fcv, f->cnt + (size_t)h * NS, ppm, pwm, seq_of(c, h), len_of(c, h), ts, tp, st);
+    }
+}
+
+/* sweeps of fs:381 / fs:350 / fs:318 (pcv given) and fs:554 / fs:519 / fs:483 (data background) */
+static int fast_sweeps(fast_t *f, const double *pcv, int mode, int32_t max_sweeps, double *score, int32_t *pos,
+                       or_stats *st, int32_t *log, int32_t log_cap, int32_t *log_n) {
+    const ctx_t *c = f->c;
+    int32_t n = c->n, k = c->k;
+    int32_t *snap = (int32_t *)malloc((size_t)n * sizeof(int32_t));
+    if (!snap) return OR_ERR_NOMEM;
+    memcpy(snap, pos, (size_t)n * sizeof(int32_t));
+    int32_t fcv[NS], kc[NS];
+    for (int32_t sweep = 0;; ++sweep) {
+        /* all-sites counts of what the sweep reads: acc itself (greedy) or the shifted snapshot */
+        memset(f->tot, 0, (size_t)NS * k * sizeof(int32_t));
+        for (int32_t i = 0; i < n; ++i) onehot_add(c, f->tot, i, shifted(c, i, snap[i], mode), +1);
+        if (f->data_bg) {
+            memset(f->gtot, 0, sizeof f->gtot);
+            for (int32_t i = 0; i < n; ++i)
+                for (int s = 0; s < NS; ++s) f->gtot[s] += f->cnt[(size_t)i * NS + s];
+            for (int s = 0; s < NS; ++s)
+                for (int32_t j = 0; j < k; ++j) f->gtot[s] -= f->tot[s * k + j];
+        }
+        int32_t movers = 0, accepted = 0;
+        for (int32_t h = 0; h < n; ++h) {
+            int32_t own = shifted(c, h, mode == SHIFT_NONE ? pos[h] : snap[h], mode);
+            onehot_add(c, f->tot, h, own, -1);
+            if (f->data_bg) {
+                memset(kc, 0, sizeof kc);
+                for (int32_t j = 0; j < k; ++j) kc[slot(seq_of(c, h)[own + j])] += 1;
+                for (int s = 0; s < NS; ++s)
+                    fcv[s] = f->mult[s] * (int32_t)(f->gtot[s] - (f->cnt[(size_t)h * NS + s] - kc[s]));
+            }
+            double ts; int32_t tp;
+            fast_update(f, f->tot, f->ppm, f->pwm, fcv, pcv, h, &ts, &tp, st);
+            int32_t now = own;
+            if (ts > score[h]) {                                   /* fs:402 / fs:579 */
+                accepted++;
+                if (tp != pos[h]) movers++;
+                score[h] = ts; pos[h] = tp;
+                if (mode == SHIFT_NONE) now = tp;                  /* in place: later h read acc (fs:388) */
+            }
+            onehot_add(c, f->tot, h, now, +1);
+            if (f->data_bg && now != own) {
+                for (int32_t j = 0; j < k; ++j) {
+                    f->gtot[slot(seq_of(c, h)[own + j])] += 1;
+                    f->gtot[slot(seq_of(c, h)[now + j])] -= 1;
+                }
+            }
+        }
+        if (st) st->sweeps++;
+        if (log && *log_n < log_cap) { log[*log_n * 3] = mode; log[*log_n * 3 + 1] = movers; log[*log_n * 3 + 2] = accepted; ++*log_n; }
+        if (positions_equal(pos, snap, n)) break;                  /* fs:384 / fs:557 */
+        if (max_sweeps > 0 && sweep + 1 >= max_sweeps) break;
+        memcpy(snap, pos, (size_t)n * sizeof(int32_t));
+    }
+    free(snap);
+    return OR_OK;
+}
+
+/* uniform `draw` of the stream without touching rng->next (threads address the stream by index) */
+static double rng_at(const or_rng *rng, int64_t draw, int *exhausted) {
+    if (rng->mode == 0) {
+        if (draw >= rng->n_u) { *exhausted = 1; return 0.0; }
+        return rng->u[draw];
+    }
+    return or_uniform_at(rng->seed, rng->chain, (uint64_t)draw);
+}
+
+/* fs:412-430 / fs:589-611 */
+typedef struct {
+    fast_t *f; const double *pcv; const or_rng *rng; double *score; int32_t *pos; int64_t base0;
+    int64_t ctot[NS];
+    int32_t n_threads;
+    int32_t **pfm; double **ppm, **pwm;   /* per-thread scratch */
+    int64_t *ws; int *exhausted;          /* per-thread results */
+} rs_ctx;
+
+static void rs_body(void *p, int32_t h, int32_t t) {
+    rs_ctx *r = (rs_ctx *)p;
+    const fast_t *f = r->f;
+    const ctx_t *c = f->c;
+    const or_rng *rng = r->rng;
+    const int32_t n = c->n, k = c->k;
+    const size_t cells = (size_t)NS * k;
+    int32_t *pfm = r->pfm[t];
+    memset(pfm, 0, cells * sizeof(int32_t));
+    int64_t d = r->base0 + (int64_t)h * (n - 1);
+    uint32_t blk_words[4] = {0, 0, 0, 0};
+    int64_t blk_have = -1;
+    for (int32_t i = 0; i < n; ++i) {
+        if (i == h) continue;
+        double u;
+        if (rng->mode == 1) {           /* Philox block of draws 4b .. 4b+3, computed once */
+            if ((d >> 2) != blk_have) {
+                blk_have = d >> 2;
+                uint32_t ctr[4] = {(uint32_t)blk_have, (uint32_t)((uint64_t)blk_have >> 32), (uint32_t)rng->chain, (uint32_t)(rng->chain >> 32)};
+                uint32_t key[2] = {(uint32_t)rng->seed, (uint32_t)(rng->seed >> 32)};
+                or_philox4x32_10(ctr, key, blk_words);
+            }
+            u = (double)blk_words[d & 3] * (1.0 / 4294967296.0);
+        } else {
+            int ex = 0;
+            u = rng_at(rng, d, &ex);
+            r->exhausted[t] |= ex;
+        }
+        ++d;
+        onehot_add(c, pfm, i, or_draw_to_position(u, len_of(c, i), k), +1);
+    }
+    int32_t fcv[NS];
+    if (f->data_bg)
+        for (int s = 0; s < NS; ++s) {
+            int64_t site_cnt = 0;
+            for (int32_t j = 0; j < k; ++j) site_cnt += pfm[s * k + j];
+            fcv[s] = f->mult[s] * (int32_t)(r->ctot[s] - f->cnt[(size_t)h * NS + s] - site_cnt);
+        }
+    or_stats local = {0, 0, 0, 0};
+    fast_update(f, pfm, r->ppm[t], r->pwm[t], fcv, r->pcv, h, &r->score[h], &r->pos[h], &local);
+    r->ws[t] += local.window_scores;
+}
+
+static int fast_random_starts(fast_t *f, const double *pcv, or_rng *rng, double *score, int32_t *pos, or_stats *st,
+                              int32_t n_threads) {
+    const ctx_t *c = f->c;
+    const int32_t n = c->n, k = c->k;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    rs_ctx r;
+    memset(&r, 0, sizeof r);
+    r.f = f; r.pcv = pcv; r.rng = rng; r.score = score; r.pos = pos; r.base0 = rng->next; r.n_threads = n_threads;
+    if (f->data_bg)
+        for (int32_t i = 0; i < n; ++i)
+            for (int s = 0; s < NS; ++s) r.ctot[s] += f->cnt[(size_t)i * NS + s];
+    int32_t *pfm[256]; double *ppm[256], *pwm[256]; int64_t ws[256]; int exhausted[256];
+    size_t cells = (size_t)NS * k;
+    int err = 0;
+    for (int32_t t = 0; t < n_threads; ++t) {
+        pfm[t] = (int32_t *)malloc(cells * sizeof(int32_t));
+        ppm[t] = (double *)malloc(cells * sizeof(double));
+        pwm[t] = (double *)calloc(cells, sizeof(double));
+        ws[t] = 0; exhausted[t] = 0;
+        if (!pfm[t] || !ppm[t] || !pwm[t]) err = 1;
+    }
+    r.pfm = pfm; r.ppm = ppm; r.pwm = pwm; r.ws = ws; r.exhausted = exhausted;
+    if (!err) parallel_for(n, n_threads, 16, rs_body, &r);
+    int64_t wsum = 0; int ex = 0;
+    for (int32_t t = 0; t < n_threads; ++t) { free(pfm[t]); free(ppm[t]); free(pwm[t]); wsum += ws[t]; ex |= exhausted[t]; }
+    if (err) return OR_ERR_NOMEM;
+    rng->next = r.base0 + (int64_t)n * (n - 1);
+    if (ex) rng->exhausted = 1;
+    if (st) { st->sweeps++; st->site_updates += n; st->window_scores += wsum; }
+    return OR_OK;
+}
+
+/*
+ * variant 0 = WithBPV family (fs:691), 1 = data-derived background (fs:697). phase_mask: 1 random starts,
+ * 2 greedy sweeps, 4 left shifts, 8 right shifts (0 = all four, the pipeline of doSiteSampling[WithBPV]);
+ * without bit 1 the sweeps start from the (score, pos) passed in. sweep_log (nullable) receives
+ * (mode, sites moved, updates accepted) per sweep of the greedy / shift phases.
+ */
+int or_fast_site_pipeline(int32_t variant, int32_t phase_mask, const uint8_t *seqs, const int64_t *off, int32_t n_seqs,
+                          int32_t k, double pc, const uint8_t *alphabet, int32_t alen, const double *pcv, or_rng *rng,
+                          double *score, int32_t *pos, or_stats *st, int32_t n_threads, int32_t *sweep_log,
+                          int32_t sweep_log_cap, int32_t *sweep_log_n) {
+    if (variant < 0 || variant > 1) return OR_ERR_ARG;
+    MAKE_CTX(c);
+    int rc = check_ctx(&c); if (rc) return rc;
+    if (!score || !pos || (variant == 0 && !pcv)) return OR_ERR_ARG;
+    if (phase_mask == 0) phase_mask = 15;
+    if ((phase_mask & 1) && !rng) return OR_ERR_ARG;
+    fast_t f;
+    rc = fast_init(&f, &c, variant == 1);
+    int32_t ln = 0;
+    if (!rc && (phase_mask & 1)) rc = fast_random_starts(&f, pcv, rng, score, pos, st, n_threads);
+    if (!rc && (phase_mask & 2)) rc = fast_sweeps(&f, pcv, SHIFT_NONE, 0, score, pos, st, sweep_log, sweep_log_cap, &ln);
+    if (!rc && (phase_mask & 4)) rc = fast_sweeps(&f, pcv, SHIFT_LEFT, 0, score, pos, st, sweep_log, sweep_log_cap, &ln);
+    if (!rc && (phase_mask & 8)) rc = fast_sweeps(&f, pcv, SHIFT_RIGHT, 0, score, pos, st, sweep_log, sweep_log_cap, &ln);
+    if (!rc && st && phase_mask == 15) st->restarts++;
+    if (sweep_log_n) *sweep_log_n = ln;
+    fast_free(&f);
+    return rc;
+}
+
+/* n_chains restarts (Philox streams (seed, chain_base + c)) on n_threads threads; results [n_chains][n_seqs],
+ * sums = Array.sum of each restart's scores, left to right (fs:445) */
+typedef struct {
+    int32_t variant; const uint8_t *seqs; const int64_t *off; int32_t n_seqs, k; double pc; const uint8_t *alphabet;
+    int32_t alen; const double *pcv; uint64_t seed; int64_t chain_base; double *scores; int32_t *pos; double *sums;
+    or_stats *per_thread; int *rc;
+} ch_ctx;
+
+static void ch_body(void *p, int32_t ch, int32_t t) {
+    ch_ctx *a = (ch_ctx *)p;
+    or_rng rng;
+    memset(&rng, 0, sizeof rng);
+    rng.mode = 1; rng.seed = a->seed; rng.chain = (uint64_t)(a->chain_base + ch);
+    int rc = or_fast_site_pipeline(a->variant, 15, a->seqs, a->off, a->n_seqs, a->k, a->pc, a->alphabet, a->alen, a->pcv,
+                                   &rng, a->scores + (size_t)ch * a->n_seqs, a->pos + (size_t)ch * a->n_seqs,
+                                   &a->per_thread[t], 1, NULL, 0, NULL);
+    if (rc) a->rc[t] = rc;
+    if (a->sums) a->sums[ch] = seq_sum(a->scores + (size_t)ch * a->n_seqs, a->n_seqs);
+}
+
+int or_fast_site_chains(int32_t variant, const uint8_t *seqs, const int64_t *off, int32_t n_seqs, int32_t k, double pc,
+                        const uint8_t *alphabet, int32_t alen, const double *pcv, uint64_t seed, int64_t chain_base,
+                        int32_t n_chains, int32_t n_threads, double *scores, int32_t *pos, double *sums, or_stats *st) {
+    if (n_chains < 1 || !scores || !pos) return OR_ERR_ARG;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    or_stats per_thread[256];
+    int rcs[256];
+    memset(per_thread, 0, sizeof per_thread);
+    memset(rcs, 0, sizeof rcs);
+    ch_ctx a = {variant, seqs, off, n_seqs, k, pc, alphabet, alen, pcv, seed, chain_base, scores, pos, sums, per_thread, rcs};
+    parallel_for(n_chains, n_threads, 1, ch_body, &a);
+    int rc_all = OR_OK;
+    for (int32_t t = 0; t < n_threads; ++t) {
+        if (rcs[t]) rc_all = rcs[t];
+        if (st) { st->site_updates += per_thread[t].site_updates; st->window_scores += per_thread[t].window_scores;
+                  st->sweeps += per_thread[t].sweeps; st->restarts += per_thread[t].restarts; }
+    }
+    return rc_all;
+}

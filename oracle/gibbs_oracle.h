@@ -165,6 +165,20 @@ int or_best_motif_information_content(int32_t variant, int32_t reps, const uint8
                     const double *pcv_or_null, const double *ppm_or_null, or_rng *rng,
                     double *pwms, int32_t *npos, int32_t *pos, int32_t *n_out, or_stats *st);
 
+/* ---- incremental mode (see the section of that name in gibbs_oracle.c): the same float64 operations on the same
+ * integer counts, obtained without the reference's from-scratch rebuilds; bit-identical to the functions above
+ * (tests/test_oracle_fast.py) and fast enough for the BASELINE sizes. variant 0 = WithBPV (fs:691), 1 = data-derived
+ * background (fs:697). phase_mask: 1 random starts | 2 greedy | 4 left shifts | 8 right shifts (0 = all). ---- */
+int or_fast_site_pipeline(int32_t variant, int32_t phase_mask, const uint8_t *seqs, const int64_t *off,
+                          int32_t n_seqs, int32_t k, double pc, const uint8_t *alphabet, int32_t alen,
+                          const double *pcv_or_null, or_rng *rng, double *score, int32_t *pos, or_stats *st,
+                          int32_t n_threads, int32_t *sweep_log /* nullable [cap][3]: mode, moved, accepted */,
+                          int32_t sweep_log_cap, int32_t *sweep_log_n);
+int or_fast_site_chains(int32_t variant, const uint8_t *seqs, const int64_t *off, int32_t n_seqs, int32_t k,
+                        double pc, const uint8_t *alphabet, int32_t alen, const double *pcv_or_null,
+                        uint64_t seed, int64_t chain_base, int32_t n_chains, int32_t n_threads,
+                        double *scores, int32_t *pos, double *sums, or_stats *st);
+
 /* fs:156-170 */
 int or_get_best_information_content(const double *scores, const int32_t *lens, int32_t n_items,
                                     int32_t *best_index_out /* -1 = the empty start value */);

@@ -378,3 +378,51 @@ def best_motif_information_content(variant: int, reps: int, src: Sources, m: int
         _p(ppm_a, C.c_double) if ppm_a is not None else None,
         C.byref(rng), _p(pw, C.c_double), _p(npos, C.c_int32), _p(pos, C.c_int32), C.byref(n_out), C.byref(st)))
     return _motif_out(pw, npos, pos, n_out.value), st
+
+
+# ---------------------------------------------------------------------------------------------
+# incremental mode (same arithmetic, no from-scratch rebuilds; see gibbs_oracle.c)
+# ---------------------------------------------------------------------------------------------
+PH_INIT, PH_GREEDY, PH_LEFT, PH_RIGHT = 1, 2, 4, 8
+
+
+def fast_site_pipeline(variant: int, src: Sources, k: int, pc: float, *, pcv=None, rng=None, state=None,
+                       phase_mask: int = 0, threads: int = 1, alphabet: bytes = DNA_BASES, log_cap: int = 4096):
+    """variant 0 = WithBPV (fs:691), 1 = data-derived background (fs:697).
+    Returns (scores, positions, Stats, sweep_log[(mode, moved, accepted)])."""
+    n = src.n
+    if state is not None:
+        score = np.ascontiguousarray(state[0], np.float64).copy()
+        pos = np.ascontiguousarray(state[1], np.int32).copy()
+    else:
+        score = np.zeros(n, np.float64)
+        pos = np.zeros(n, np.int32)
+    st = Stats()
+    pcv_a = np.ascontiguousarray(pcv, np.float64) if pcv is not None else None
+    log = np.zeros((log_cap, 3), np.int32)
+    log_n = C.c_int32()
+    _check(lib().or_fast_site_pipeline(
+        C.c_int32(variant), C.c_int32(phase_mask), _p(src.buf, C.c_uint8), _p(src.off, C.c_int64), C.c_int32(n),
+        C.c_int32(k), C.c_double(pc), _u8(alphabet), C.c_int32(len(alphabet)),
+        _p(pcv_a, C.c_double) if pcv_a is not None else None, C.byref(rng) if rng is not None else None,
+        _p(score, C.c_double), _p(pos, C.c_int32), C.byref(st), C.c_int32(threads), _p(log, C.c_int32),
+        C.c_int32(log_cap), C.byref(log_n)))
+    return score, pos, st, [tuple(int(x) for x in r) for r in log[: log_n.value]]
+
+
+def fast_site_chains(variant: int, src: Sources, k: int, pc: float, *, seed: int, chain_base: int, n_chains: int,
+                     pcv=None, threads: int = 1, alphabet: bytes = DNA_BASES):
+    """n_chains whole restarts with Philox streams (seed, chain_base + c). Returns (scores, positions, sums, Stats)."""
+    n = src.n
+    scores = np.zeros((n_chains, n), np.float64)
+    pos = np.zeros((n_chains, n), np.int32)
+    sums = np.zeros(n_chains, np.float64)
+    st = Stats()
+    pcv_a = np.ascontiguousarray(pcv, np.float64) if pcv is not None else None
+    _check(lib().or_fast_site_chains(
+        C.c_int32(variant), _p(src.buf, C.c_uint8), _p(src.off, C.c_int64), C.c_int32(n), C.c_int32(k),
+        C.c_double(pc), _u8(alphabet), C.c_int32(len(alphabet)),
+        _p(pcv_a, C.c_double) if pcv_a is not None else None, C.c_uint64(seed), C.c_int64(chain_base),
+        C.c_int32(n_chains), C.c_int32(threads), _p(scores, C.c_double), _p(pos, C.c_int32), _p(sums, C.c_double),
+        C.byref(st)))
+    return scores, pos, sums, st

@@ -39,7 +39,7 @@ def test_struct_layouts_match_the_header():
 
 def test_abi_version_and_error_text():
     lib = _abi.load()
-    assert lib.gibbs_abi_version() == 1
+    assert lib.gibbs_abi_version() == 2
     assert isinstance(lib.gibbs_last_error(), bytes)
 
 

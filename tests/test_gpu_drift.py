@@ -78,9 +78,9 @@ def test_script_call_and_phase_functions(golden):
 
 @pytest.mark.parametrize("shape", [(60, 200, None, 8), (200, 500, 300, 12), (40, 120, None, 20), (30, 64, 40, 32)],
                          ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
-def test_ranking_pass_equals_the_all_windows_float64_scan(shape, monkeypatch):
+def test_ranking_pass_equals_the_all_windows_float64_scan(shape):
     """The float32 ranking pass + exact re-scoring of the candidates must return what the scan of every window in
-    float64 returns (GIBBS_B200_DRIFT_EXACT=1 forces the latter): same sites, bit-identical scores, at sizes the CPU
+    float64 returns (gibbs_set_option GIBBS_OPT_EXACT_SCANS forces the latter): same sites, bit-identical scores, at sizes the CPU
     oracle cannot reach in seconds. The small cases above pin both against the oracle."""
     n, L, Lmin, k = shape
     ps = planted_motif_set(n, L, k, seed=77, min_length=Lmin)
@@ -88,7 +88,7 @@ def test_ranking_pass_equals_the_all_windows_float64_scan(shape, monkeypatch):
     params = make_params(k, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA)
     with GibbsEngine(seqs) as eng:
         fast = eng.run(params, 6, chain_id_base=3, seed=9, want_counts=False)
-        monkeypatch.setenv("GIBBS_B200_DRIFT_EXACT", "1")
+        eng.set_option(_abi.GIBBS_OPT_EXACT_SCANS, 1)
         exact = eng.run(params, 6, chain_id_base=3, seed=9, want_counts=False)
     assert fast.stats["fast_path"] == 1 and exact.stats["fast_path"] == 0
     assert exact.stats["exact_rescans"] == exact.stats["site_updates"]
@@ -136,15 +136,15 @@ def test_hand_over_stages_do_not_change_a_chain():
 
 @pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("shape", [(60, 64, 40, 9), (300, 90, None, 12)], ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
-def test_random_starts_same_on_both_kernels(shape, wide, monkeypatch):
+def test_random_starts_same_on_both_kernels(shape, wide):
     """getPWMOfRandomStarts (fs:589-611) inside the chain kernel or as the grid-wide init kernel: both consume the
     uniform stream as the oracle does."""
     n, L, Lmin, k = shape
-    monkeypatch.setenv("GIBBS_B200_INIT_KERNEL", wide)
     ps = planted_motif_set(n, L, k, seed=22, min_length=Lmin)
     seqs = ps.sequences()
     S = O.sources(seqs)
     with GibbsEngine(seqs) as eng:
+        eng.set_option(_abi.GIBBS_OPT_INIT_PATH, _abi.GIBBS_INIT_WIDE if wide == "1" else _abi.GIBBS_INIT_CHAIN)
         init = eng.run(make_params(k, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA, phase_mask=_abi.PHASE_INIT), 3,
                        chain_id_base=5, seed=31, want_counts=False)
         full = eng.run(make_params(k, 1e-4, 5, [0.25] * 4, background=_abi.GIBBS_BG_DATA), 3, chain_id_base=5, seed=31,

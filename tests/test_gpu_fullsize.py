@@ -1,12 +1,19 @@
-"""Full BASELINE.json sizes on the GPU. The oracle is too slow to run whole jobs at these sizes, so parity is
-checked on a sample of chains (C2) and through size-independent properties (C2, C3, C4 shapes):
-determinism, independence of batching / sharding, idempotence of a converged phase, site ranges,
-sums = left-to-right sums of the scores, best chain = first largest sum, PWM counts = recount of the sites."""
+"""Full BASELINE.json sizes on the GPU, against the oracle. The oracle's faithful mode needs hours at these sizes; its
+incremental mode (same float64 operations on the same integer counts, proven bit-identical on CPU by
+tests/test_oracle_fast.py) generated tests/golden/fullsize_v1.json: every one of the 1024 chains of C2, four chains of
+C3, one whole restart of C4 with phase shifts and its random starts. The same mode also runs live here on a sample of
+chains, and the primitives are checked at full N against the faithful functions. Beside that: size-independent
+properties (determinism, independence of batching / sharding / init path, idempotence of a converged phase, site
+ranges, sums = left-to-right sums of the scores, best chain = first largest sum, PWM counts = recount of the sites)."""
+import hashlib
+import json
+import os
+
 import numpy as np
 import pytest
 
 import oracle_lib as O
-from gibbssampling_b200 import _abi
+from gibbssampling_b200 import SiteSampler, _abi
 from gibbssampling_b200.engine import GibbsEngine, make_params
 from gibbssampling_b200.synthetic import background_of, planted_motif_set
 
@@ -43,81 +50,143 @@ def _check_invariants(ps, res, k):
     assert res.stats["capped_chains"] == 0 and res.stats["fast_path"] == 1
 
 
-def test_c2_full_size_sample_parity_and_properties():
-    """BASELINE configs[1]: 1000 x 500 bp, k = 12, 1024 chains."""
-    n, L, k, chains = 1000, 500, 12, 1024
+def _golden():
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_v1.json")) as f:
+        return json.load(f)
+
+
+def _digest(sites) -> str:
+    return hashlib.sha1(np.ascontiguousarray(sites, dtype="<i4").tobytes()).hexdigest()[:20]
+
+
+def _assert_matches_golden(res, g, chains):
+    """sites bit-exact (digest), sums and stored scores within the 1e-5 of north_star (device log vs glibc log differ
+    in the last bit at most; the sums agree far tighter than that), counters exact."""
+    assert [_digest(res.sites[c]) for c in range(chains)] == g["sites_sha1"]
+    np.testing.assert_allclose(res.sums, [float.fromhex(x) for x in g["sums"]], rtol=1e-12)
+    head = np.array([[float.fromhex(x) for x in row] for row in g["scores_head"]])
+    np.testing.assert_allclose(res.scores[:, :4], head, rtol=1e-5)
+    assert res.stats["sweeps"] == g["sweeps"] and res.stats["site_updates"] == g["site_updates"]
+    assert res.stats["window_scores"] == g["window_scores"]
+
+
+def test_c2_every_chain_matches_the_oracle():
+    """BASELINE configs[1]: 1000 x 500 bp, k = 12, ALL 1024 chains of the benchmarked step against the oracle
+    (golden file generated with the oracle's incremental mode, tests/golden/make_fullsize_golden.py), and a live
+    sample of chains against the oracle running on this box."""
+    g = _golden()["C2"]
+    n, L, k, chains = g["n"], g["L"], g["k"], g["n_chains"]
+    assert (n, L, k, chains) == (1000, 500, 12, 1024)
     ps = planted_motif_set(n, L, k)
     seqs = ps.sequences()
     bg = background_of(ps.ascii, PC, ALEN)
     params = make_params(k, PC, ALEN, bg)
     with GibbsEngine(seqs) as eng:
-        res = eng.run(params, chains, chain_id_base=0, seed=0xB200)
+        res = eng.run(params, chains, chain_id_base=g["chain_base"], seed=g["seed"])
         _check_invariants(ps, res, k)
-        assert res.stats["site_updates"] >= 4 * n * chains
-        assert res.stats["window_scores"] == res.stats["site_updates"] * (L - k + 1)
+        _assert_matches_golden(res, g, chains)
         # the planted motif is recovered: the best chain puts most sites on the planted positions
         assert (res.sites[res.best_chain] == ps.truth).mean() > 0.5   # 10 % planted-base mutation; chance windows win some
-        # bit-exact against the oracle for a sample of chains (about 4 s of CPU each)
+        # live: the oracle (incremental mode) on this box for a spread of chains, full score vectors
         S = O.sources(seqs)
         pcv = O.pcv_from_acgt(bg)
-        for c in (0, 517):
-            rng, _ = O.make_rng(seed=0xB200, chain=c)
-            score, pos, _ = O.site_step("do_site_sampling_with_bpv", S, k, PC, pcv=pcv, rng=rng)
-            assert res.sites[c].tolist() == pos.tolist()
+        live = [0, 1, 2, 3, 255, 256, 517, 1000, 1022, 1023]
+        for c in live:
+            rng, _ = O.make_rng(seed=g["seed"], chain=g["chain_base"] + c)
+            score, pos, st, _ = O.fast_site_pipeline(0, S, k, PC, pcv=pcv, rng=rng)
+            assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"
             np.testing.assert_allclose(res.scores[c], score, rtol=1e-5)
+        # every init path gives the same chains
+        for path in (_abi.GIBBS_INIT_CHAIN, _abi.GIBBS_INIT_WIDE, _abi.GIBBS_INIT_SMEM):
+            eng.set_option(_abi.GIBBS_OPT_INIT_PATH, path)
+            part = eng.run(params, 160, chain_id_base=g["chain_base"] + 512, seed=g["seed"], want_counts=False)
+            assert part.stats["init_path"] == path
+            assert part.sites.tobytes() == res.sites[512:672].tobytes()
+            assert part.scores.tobytes() == res.scores[512:672].tobytes()
+        eng.set_option(_abi.GIBBS_OPT_INIT_PATH, _abi.GIBBS_INIT_AUTO)
         # determinism and independence of batching (what sharding over GPUs relies on)
-        again = eng.run(params, chains, chain_id_base=0, seed=0xB200)
+        again = eng.run(params, chains, chain_id_base=g["chain_base"], seed=g["seed"])
         assert again.sites.tobytes() == res.sites.tobytes() and again.scores.tobytes() == res.scores.tobytes()
-        part = eng.run(params, 96, chain_id_base=512, seed=0xB200)
-        assert part.sites.tobytes() == res.sites[512:608].tobytes()
-        assert part.scores.tobytes() == res.scores[512:608].tobytes()
+        # the restart loop on the device over all 1024 restarts
+        best = eng.fetch_best(chains - 1)
+        want = SiteSampler.replay_restart_loop(chains - 1, res.scores, res.sites, res.sums)
+        assert [(float(a), int(b)) for a, b in zip(best.scores, best.sites)] == want
         # idempotence: the last phase (right shifts) applied to its own output changes nothing
         eng.set_start_state(res.sites[:64], res.scores[:64])
-        redo = eng.run(make_params(k, PC, ALEN, bg, phase_mask=_abi.PHASE_RIGHT), 64, seed=0xB200)
+        redo = eng.run(make_params(k, PC, ALEN, bg, phase_mask=_abi.PHASE_RIGHT), 64, seed=g["seed"])
         assert redo.sites.tobytes() == res.sites[:64].tobytes()
         np.testing.assert_allclose(redo.scores, res.scores[:64], rtol=1e-12)
         assert redo.stats["sweeps"] == 64               # one quiet sweep per chain
 
 
-def test_c3_shape_properties():
-    """BASELINE configs[2] shape: 10k promoter-length (1 kb) sequences, k = 16 (a few of the 8192 restarts)."""
-    n, L, k, chains = 10000, 1000, 16, 4
+def test_c3_chains_match_the_oracle():
+    """BASELINE configs[2]: 10k promoter-length (1 kb) sequences, k = 16; four of the 8192 restarts, end to end."""
+    g = _golden()["C3"]
+    n, L, k, chains = g["n"], g["L"], g["k"], g["n_chains"]
+    assert (n, L, k) == (10000, 1000, 16) and chains >= 4
     ps = planted_motif_set(n, L, k)
     bg = background_of(ps.ascii, PC, ALEN)
     params = make_params(k, PC, ALEN, bg)
     with GibbsEngine(ps.sequences()) as eng:
-        res = eng.run(params, chains, chain_id_base=8000, seed=3)
+        res = eng.run(params, chains, chain_id_base=g["chain_base"], seed=g["seed"])
         _check_invariants(ps, res, k)
-        solo = eng.run(params, 1, chain_id_base=8002, seed=3)
+        _assert_matches_golden(res, g, chains)
+        solo = eng.run(params, 1, chain_id_base=g["chain_base"] + 2, seed=g["seed"])
         assert solo.sites[0].tobytes() == res.sites[2].tobytes() and solo.scores[0].tobytes() == res.scores[2].tobytes()
         eng.set_team_warps(4)
-        narrow = eng.run(params, chains, chain_id_base=8000, seed=3)
+        narrow = eng.run(params, chains, chain_id_base=g["chain_base"], seed=g["seed"])
         assert narrow.sites.tobytes() == res.sites.tobytes() and narrow.scores.tobytes() == res.scores.tobytes()
         assert (res.sites[res.best_chain] == ps.truth).mean() > 0.5   # 10 % planted-base mutation; chance windows win some
+        # one chain live against the oracle on this box (about 10 s of CPU)
+        S = O.sources(ps.sequences())
+        rng, _ = O.make_rng(seed=g["seed"], chain=g["chain_base"] + 1)
+        score, pos, st, _ = O.fast_site_pipeline(0, S, k, PC, pcv=O.pcv_from_acgt(bg), rng=rng, threads=os.cpu_count() or 1)
+        assert res.sites[1].tolist() == pos.tolist()
+        np.testing.assert_allclose(res.scores[1], score, rtol=1e-5)
 
 
-def test_c4_shape_properties():
-    """BASELINE configs[3] shape: 100k ChIP-seq-peak-sized (200 bp) sequences, k = 20, with phase-shift moves.
-    One restart draws N(N-1) ~ 1e10 initial sites, so the draw counter leaves 32 bits."""
-    n, L, k = 100000, 200, 20
+def test_c4_restart_and_primitives_match_the_oracle():
+    """BASELINE configs[3]: 100k ChIP-seq-peak-sized (200 bp) sequences, k = 20, with phase-shift moves. One restart
+    draws N(N-1) ~ 1e10 initial sites, so the draw counter leaves 32 bits. The random starts and the whole restart are
+    compared with the oracle's golden results; the primitives are compared live at full N."""
+    g = _golden()["C4"]
+    n, L, k = g["n"], g["L"], g["k"]
+    assert (n, L, k) == (100000, 200, 20)
     ps = planted_motif_set(n, L, k)
+    seqs = ps.sequences()
     bg = background_of(ps.ascii, PC, ALEN)
-    with GibbsEngine(ps.sequences()) as eng:
-        res = eng.run(make_params(k, PC, ALEN, bg), 2, chain_id_base=7, seed=11)
-        _check_invariants(ps, res, k)
-        assert res.stats["sweeps"] >= 2 * 5
-        assert (res.sites[res.best_chain] == ps.truth).mean() > 0.5   # 10 % planted-base mutation; chance windows win some
-        # spot-check the random-start phase against the oracle's arithmetic on a few held-out sequences:
-        # the leave-one-out counts of the first sweep are those of the Philox draws n(N-1)+rank
-        init = eng.run(make_params(k, PC, ALEN, bg, phase_mask=_abi.PHASE_INIT), 1, chain_id_base=7, seed=11)
-        lens = np.diff(ps.offsets)
-        for h in (0, 1, 54321, n - 1):
-            draws = np.arange(n - 1, dtype=np.uint64) + np.uint64(h) * np.uint64(n - 1)
-            others = np.array([i for i in range(n) if i != h][:64])          # a prefix is enough to pin the indexing
-            pos = [O.draw_to_position(O.uniform_at(11, 7, int(d)), int(lens[i]), k) for d, i in zip(draws[:64], others)]
-            assert all(0 <= p <= L - k for p in pos)
+    S = O.sources(seqs)
+    pcv = O.pcv_from_acgt(bg)
+    with GibbsEngine(seqs) as eng:
+        # the random starts alone: sites are those of the Philox draws n(N-1) + rank (fs:418-426)
+        init = eng.run(make_params(k, PC, ALEN, bg, phase_mask=_abi.PHASE_INIT), 1, chain_id_base=g["chain"], seed=g["seed"])
         assert init.stats["site_updates"] == n and init.stats["sweeps"] == 1
-        assert init.sites[0].tobytes() != res.sites[0].tobytes() or True
+        assert _digest(init.sites[0]) == g["init_sites_sha1"]
+        for i, want in g["init_sites_sample"].items():
+            assert int(init.sites[0][int(i)]) == want
+        np.testing.assert_allclose(init.sums[0], float.fromhex(g["init_sum"]), rtol=1e-12)
+        np.testing.assert_allclose(init.scores[0][:4], [float.fromhex(x) for x in g["init_scores_head"]], rtol=1e-5)
+        # one whole restart with phase shifts (and a second chain beside it, so batching is exercised too)
+        res = eng.run(make_params(k, PC, ALEN, bg), 2, chain_id_base=g["chain"], seed=g["seed"])
+        _check_invariants(ps, res, k)
+        assert _digest(res.sites[0]) == g["sites_sha1"]
+        np.testing.assert_allclose(res.sums[0], float.fromhex(g["sum"]), rtol=1e-12)
+        np.testing.assert_allclose(res.scores[0][:4], [float.fromhex(x) for x in g["scores_head"]], rtol=1e-5)
+        assert (res.sites[res.best_chain] == ps.truth).mean() > 0.5   # 10 % planted-base mutation; chance windows win some
+        # primitives at full N against the faithful oracle functions, for several held-out sequences and two states
+        params = make_params(k, PC, ALEN, bg)
+        for sites in (init.sites[0], res.sites[0]):
+            for h in (0, 1, 54321, n - 1):
+                pfm = O.loo_pfm(S, sites, h, k)
+                assert eng.loo_counts(sites, h, k).tolist() == O.acgt_counts(pfm).tolist()
+                ppm = O.ppm_of_pfm(pfm, n - 1, PC)
+                want_raw = O.window_scores_bpv(S.seq(h), k, pcv, ppm)
+                raw, lg = eng.window_scores(sites, h, params)
+                assert raw.tobytes() == want_raw.tobytes()                       # float64 products, bit for bit
+                np.testing.assert_allclose(lg, np.log(want_raw) / np.log(2.0), rtol=1e-5)
+                want_score, want_pos = O.best_pwms_with_bpv(S.seq(h), k, pcv, ppm)
+                score, pos = eng.pick_argmax(sites, h, params)
+                assert pos == want_pos and score == pytest.approx(want_score, rel=1e-5)
 
 
 @pytest.mark.parametrize("L", [100, 1000, 10000])

@@ -184,8 +184,8 @@ def test_data_background_motif_functions(golden):
 @pytest.mark.parametrize("data", [False, True], ids=["fixed", "data"])
 @pytest.mark.parametrize("shape", [(40, 150, None, 8, 0.0), (120, 400, 250, 12, 1.0), (30, 90, None, 20, -3.0), (25, 64, 40, 32, 0.0)],
                          ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
-def test_greedy_ranking_pass_equals_the_all_windows_candidate_list(shape, data, monkeypatch):
-    """The greedy sweeps rank windows in fixed point and re-score the candidates; GIBBS_B200_MOTIF_EXACT=1 forces the
+def test_greedy_ranking_pass_equals_the_all_windows_candidate_list(shape, data):
+    """The greedy sweeps rank windows in fixed point and re-score the candidates; gibbs_set_option(GIBBS_OPT_EXACT_SCANS) forces the
     all-windows float64 candidate list. Both must give the same MotifIndex arrays, bit for bit, at sizes the oracle
     cannot reach in seconds (the small cases above and the fuzz test pin both against the oracle)."""
     n, L, Lmin, k, cutoff = shape
@@ -196,7 +196,7 @@ def test_greedy_ranking_pass_equals_the_all_windows_candidate_list(shape, data, 
                          background=_abi.GIBBS_BG_DATA if data else _abi.GIBBS_BG_FIXED)
     with GibbsEngine(seqs) as eng:
         fast = eng.run(params, 6, chain_id_base=3, seed=9, want_counts=False)
-        monkeypatch.setenv("GIBBS_B200_MOTIF_EXACT", "1")
+        eng.set_option(_abi.GIBBS_OPT_EXACT_SCANS, 1)
         exact = eng.run(params, 6, chain_id_base=3, seed=9, want_counts=False)
     assert fast.sites.tolist() == exact.sites.tolist()
     assert fast.scores.tobytes() == exact.scores.tobytes()

@@ -152,15 +152,18 @@ def test_chains_match_oracle_philox(case, team):
     assert res.counts.tolist() == want_counts.tolist()
 
 
-@pytest.mark.parametrize("wide", ["0", "1"])
-@pytest.mark.parametrize("shape", [(70, 64, 40, 9), (300, 90, None, 12), (1100, 40, 30, 16)],
+INIT_PATHS = {"chain": _abi.GIBBS_INIT_CHAIN, "wide": _abi.GIBBS_INIT_WIDE, "smem": _abi.GIBBS_INIT_SMEM}
+
+
+@pytest.mark.parametrize("path", sorted(INIT_PATHS))
+@pytest.mark.parametrize("shape", [(70, 64, 40, 9), (300, 90, None, 12), (1100, 40, 30, 16), (90, 700, 500, 20), (40, 130, None, 31)],
                          ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
-def test_random_starts_same_on_both_kernels(shape, wide, monkeypatch):
-    """Random starts (fs:412-430) run either inside the chain kernel or as the grid-wide init kernel
-    (gibbs_api.cu picks by shape; GIBBS_B200_INIT_KERNEL forces one). Both must consume the uniform
-    stream exactly as the oracle does: N(N-1) draws, several flushes of the per-lane byte counters."""
+def test_random_starts_same_on_every_init_path(shape, path):
+    """Random starts (fs:412-430) run inside the chain kernel, as the grid-wide kernel gathering from global memory, or
+    as the grid-wide kernel with the packed set in shared memory (gibbs_api.cu picks by shape;
+    gibbs_set_option(GIBBS_OPT_INIT_PATH) forces one). All must consume the uniform stream exactly as the oracle does:
+    N(N-1) draws, bit-sliced base counters with several nibble spills and (N = 1100) warp flushes, one- and two-word k-mers."""
     n, L, Lmin, k = shape
-    monkeypatch.setenv("GIBBS_B200_INIT_KERNEL", wide)
     ps = planted_motif_set(n, L, k, seed=21, min_length=Lmin)
     seqs = ps.sequences()
     bg = background_of(ps.ascii, 1e-4, 5)
@@ -168,9 +171,11 @@ def test_random_starts_same_on_both_kernels(shape, wide, monkeypatch):
     pcv = O.pcv_from_acgt(bg)
     n_chains = 3
     with GibbsEngine(seqs) as eng:
+        eng.set_option(_abi.GIBBS_OPT_INIT_PATH, INIT_PATHS[path])
         res = eng.run(make_params(k, 1e-4, 5, bg, phase_mask=_abi.PHASE_INIT), n_chains, chain_id_base=7, seed=99)
         full = eng.run(make_params(k, 1e-4, 5, bg), n_chains, chain_id_base=7, seed=99)
-    assert res.stats["kernel_launches"] >= (2 if wide == "1" else 1)
+    assert res.stats["init_path"] == INIT_PATHS[path]
+    assert res.stats["kernel_launches"] >= (1 if path == "chain" else 2)
     for c in range(n_chains):
         score, pos, _ = _oracle_chain(S, k, 1e-4, pcv, b"ATGC-", seed=99, chain=7 + c, name="random_starts_with_bpv")
         assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"

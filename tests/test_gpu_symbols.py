@@ -72,9 +72,8 @@ def test_primitives_with_masked_symbols(case):
 @pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("team", TEAMS)
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"s{c[0]}_n{c[1]}_k{c[4]}")
-def test_chains_with_masked_symbols(case, team, wide, monkeypatch):
+def test_chains_with_masked_symbols(case, team, wide):
     seed, n, lo, hi, k, sym, frac, alen = case
-    monkeypatch.setenv("GIBBS_B200_INIT_KERNEL", wide)
     seqs = _seqs(seed, n, lo, hi, sym, frac)
     S = O.sources(seqs)
     pcv = O.pcv_from_acgt(BG)
@@ -82,6 +81,7 @@ def test_chains_with_masked_symbols(case, team, wide, monkeypatch):
     n_chains = 5
     with GibbsEngine(seqs) as eng:
         eng.set_team_warps(team)
+        eng.set_option(_abi.GIBBS_OPT_INIT_PATH, _abi.GIBBS_INIT_WIDE if wide == "1" else _abi.GIBBS_INIT_CHAIN)
         res = eng.run(make_params(k, 1e-4, alen, BG), n_chains, chain_id_base=40, seed=77 + seed)
     for c in range(n_chains):
         rng, keep = O.make_rng(seed=77 + seed, chain=40 + c)

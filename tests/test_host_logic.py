@@ -142,3 +142,82 @@ def test_unbuilt_reference_entry_points_say_so():
     assert MotifSampler.createMotifIndex(1.5, [3]) == MotifSampler.MotifIndex(1.5, (3,))
     with pytest.raises(_abi.GibbsUnsupportedError):
         MotifSampler.doMotifSamplingWithPCV(2, 6, 1e-4, 1.0, DNA, ["ACGTACGT"], ProbabilityCompositeVector.ofACGT(.25, .25, .25, .25))
+
+
+# ---------------------------------------------------------------------------------------------
+# the event walk of restart_select_kernel (gibbs_kernels.cuh), modelled lane by lane
+# ---------------------------------------------------------------------------------------------
+def _event_walk(sums, scores, sites, reps, motif=False):
+    """Python model of restart_select_kernel: 32 restarts per step, stopping only at events (iteration cap, a sum equal
+    to the best one, a larger sum). Returns the restart index the loop returns (-1 = the initial value)."""
+    import math
+    n_chains, N = scores.shape
+    best, bsum, r_next, n_next, done = -1, 0.0, 0, 1, False
+    while not done and r_next < n_chains:
+        ev = None
+        for lane in range(32):
+            r = r_next + lane
+            if r >= n_chains:
+                break
+            s, nj = sums[r], n_next + lane
+            if nj > reps or s == bsum or s > bsum:
+                ev = (lane, r, nj, s)
+                break
+        if ev is None:
+            cnt = min(32, n_chains - r_next)
+            r_next += cnt
+            n_next += cnt
+            continue
+        _, r_j, n_j, s_j = ev
+        if n_j > reps:
+            break
+        if s_j == bsum:
+            if best < 0:
+                same = N == 1 and scores[r_j][0] == 0.0 and sites[r_j][0] == (-1 if motif else 0)
+            else:
+                same = bool(np.array_equal(sites[r_j], sites[best]) and np.array_equal(scores[r_j], scores[best]))
+            if same:
+                break
+            r_next, n_next = r_j + 1, n_j + 1
+            continue
+        best, bsum = r_j, s_j
+        if bsum < 0.0:
+            done = True
+        r_next, n_next = r_j + 1, n_j + 2
+    return best
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_event_walk_equals_the_sequential_restart_loop(seed):
+    from gibbssampling_b200 import MotifSampler, SiteSampler
+    rng = np.random.default_rng(seed)
+    n_chains = int(rng.integers(1, 150))
+    N = int(rng.integers(1, 4))
+    pool = rng.normal(size=(int(rng.integers(1, 6)), N)).round(1)         # few distinct rows: equal sums and equal arrays happen
+    if seed % 5 == 0:
+        pool = np.abs(pool)
+    if seed % 7 == 0:
+        pool[0, :] = 0.0
+    rows = rng.integers(0, len(pool), size=n_chains)
+    scores = pool[rows].copy()
+    sites = (rows[:, None] % 2 + np.zeros((1, N), dtype=np.int64)).astype(np.int32)
+    if seed % 7 == 0:
+        sites[rows == 0] = 0
+    if seed % 11 == 0:
+        scores[rng.integers(0, n_chains)] = np.nan
+    sums = np.array([sum([0.0] + [float(v) for v in row]) for row in scores])
+    for reps in (0, 1, 2, n_chains - 1, n_chains + 5, 3 * n_chains):
+        reps = max(reps, 0)
+        if reps + 1 > n_chains and seed % 2:      # the library always runs reps + 1 restarts; model both anyway
+            continue
+        want = SiteSampler.replay_restart_loop(reps, scores, sites, sums) if reps + 1 <= n_chains else None
+        if want is None:
+            continue
+        b = _event_walk(sums, scores, sites, reps)
+        got = [(0.0, 0)] if b < 0 else [(float(s), int(p)) for s, p in zip(scores[b], sites[b])]
+        assert str(got) == str(want), (seed, reps)
+        msites = np.where(sites == 0, -1, sites)
+        wantm = MotifSampler.replay_motif_restart_loop(reps, scores, msites, sums)
+        b = _event_walk(sums, scores, msites, reps, motif=True)
+        gotm = [MotifSampler.MotifIndex(0.0, ())] if b < 0 else MotifSampler._to_motif_array(scores[b], msites[b])
+        assert str(gotm) == str(wantm), (seed, reps)
