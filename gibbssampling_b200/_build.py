@@ -2,6 +2,8 @@
 
 The library is several translation units compiled in parallel and linked by nvcc:
   gibbs_api.cu        the extern "C" boundary, setup / primitive / init / MotifSampler kernels
+  gibbs_cluster_tu.cu one chain on a thread-block cluster of 4 / 8 CTAs (the last hand-over stages), one size per unit
+  gibbs_init_tu.cu    the grid-wide random-start kernels, one kind per unit (same reason as the chain units)
   gibbs_chain_tu.cu   compiled once per GROUP of chain_kernel instantiations (warps per chain x masked symbols x
                       drifting background), without --split-compile: small modules give reproducible code for the
                       register-limited hot kernel (see the header of that file)
@@ -19,8 +21,10 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 LIB_PATH = os.path.join(PKG_DIR, "libgibbs_b200.so")
 API_SOURCE = os.path.join(CSRC, "gibbs_api.cu")
 CHAIN_SOURCE = os.path.join(CSRC, "gibbs_chain_tu.cu")
-DEPS = [API_SOURCE, CHAIN_SOURCE] + [os.path.join(CSRC, f) for f in (
-    "gibbs_device.cuh", "gibbs_kernels.cuh", "gibbs_motif.cuh", "gibbs_drift.cuh", "gibbs_drift_dev.cuh",
+INIT_SOURCE = os.path.join(CSRC, "gibbs_init_tu.cu")
+CLUSTER_SOURCE = os.path.join(CSRC, "gibbs_cluster_tu.cu")
+DEPS = [API_SOURCE, CHAIN_SOURCE, INIT_SOURCE, CLUSTER_SOURCE] + [os.path.join(CSRC, f) for f in (
+    "gibbs_device.cuh", "gibbs_kernels.cuh", "gibbs_motif.cuh", "gibbs_drift.cuh", "gibbs_drift_dev.cuh", "gibbs_cluster.cuh",
 )] + [os.path.join(ROOT, "include", "gibbs_b200.h"), os.path.abspath(__file__)]
 
 # (entry point declared in gibbs_api.cu, warps per chain, masked symbols, drifting background)
@@ -36,6 +40,14 @@ CHAIN_GROUPS = [
     ("launch_chain_masked_t1", 1, 1, 0),
     ("launch_chain_masked_drift_t4", 4, 1, 1),
     ("launch_chain_masked_drift_t1", 1, 1, 1),
+]
+
+# the random starts on the chain's own team (chain_kernel<.., INIT_ONLY = true>): 1 or 4 warps
+CHAIN_INIT_GROUPS = [
+    ("launch_chain_init_t4", 4, 0, 0), ("launch_chain_init_t1", 1, 0, 0),
+    ("launch_chain_init_drift_t4", 4, 0, 1), ("launch_chain_init_drift_t1", 1, 0, 1),
+    ("launch_chain_init_masked_t4", 4, 1, 0), ("launch_chain_init_masked_t1", 1, 1, 0),
+    ("launch_chain_init_masked_drift_t4", 4, 1, 1), ("launch_chain_init_masked_drift_t1", 1, 1, 1),
 ]
 
 COMMON_FLAGS = [
@@ -67,19 +79,37 @@ def _jobs(nvcc: str, verbose: bool) -> list[tuple[str, list[str]]]:
         jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [
             f"-DGIBBS_TU_NAME={name}", f"-DGIBBS_TU_T={team}", f"-DGIBBS_TU_MASKED={masked}", f"-DGIBBS_TU_DRIFT={drift}",
             "-c", "-o", obj, CHAIN_SOURCE]))
+    for name, team, masked, drift in CHAIN_INIT_GROUPS:
+        obj = os.path.join(OBJ_DIR, name + ".o")
+        jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [
+            f"-DGIBBS_TU_NAME={name}", f"-DGIBBS_TU_T={team}", f"-DGIBBS_TU_MASKED={masked}", f"-DGIBBS_TU_DRIFT={drift}",
+            "-DGIBBS_TU_INIT_ONLY=1", "-c", "-o", obj, CHAIN_SOURCE]))
+    for kind, name in enumerate(("launch_init_wide", "launch_init_wide_drift", "launch_init_smem")):
+        obj = os.path.join(OBJ_DIR, name + ".o")
+        jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [f"-DGIBBS_INIT_TU_KIND={kind}", "-c", "-o", obj, INIT_SOURCE]))
+    for c in (4, 8):
+        obj = os.path.join(OBJ_DIR, f"launch_chain_cluster{c}.o")
+        jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [f"-DGIBBS_CLUSTER_C={c}", "-c", "-o", obj, CLUSTER_SOURCE]))
     return jobs
 
 
-def build(force: bool = False, verbose: bool = False, out: str | None = None, extra_flags: list[str] | None = None) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra_flags: list[str] | None = None,
+          only: list[str] | None = None) -> str:
     """Compile the CUDA library with nvcc (cross-compiles without a GPU).
-    out / extra_flags: a variant build (tools/build_variant.sh) beside the in-tree library, e.g. other -D tuning macros."""
+    out / extra_flags: a variant build (tools/build_variant.sh) beside the in-tree library, e.g. other -D tuning macros.
+    only: unit names (object basenames, e.g. launch_chain_t4) the flags apply to; the other units are linked from the
+    in-tree build as they are (a variant that touches one kernel group compiles one unit)."""
     if out is None and not force and not is_stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     obj_dir = OBJ_DIR if out is None else OBJ_DIR + "_" + os.path.splitext(os.path.basename(out))[0]
     os.makedirs(obj_dir, exist_ok=True)
     jobs = _jobs(nvcc, verbose)
+    reused = []
     if out is not None or extra_flags:
+        if only:
+            reused = [o for o, _ in jobs if os.path.splitext(os.path.basename(o))[0] not in only]
+            jobs = [(o, cmd) for o, cmd in jobs if os.path.splitext(os.path.basename(o))[0] in only]
         jobs = [(o.replace(OBJ_DIR, obj_dir, 1), [c.replace(OBJ_DIR, obj_dir, 1) for c in cmd[:1] + list(extra_flags or []) + cmd[1:]])
                 for o, cmd in jobs]
 
@@ -94,7 +124,7 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, ex
             log.append(res.stderr)
     target = LIB_PATH if out is None else out
     link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target]
-    res = subprocess.run(link + [j[0] for j in jobs], capture_output=True, text=True)
+    res = subprocess.run(link + [j[0] for j in jobs] + reused, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:

@@ -30,7 +30,23 @@ GIBBS_CHAIN_TU(launch_chain_masked_drift_t4);
 GIBBS_CHAIN_TU(launch_chain_drift_t1);
 GIBBS_CHAIN_TU(launch_chain_drift_t4);
 GIBBS_CHAIN_TU(launch_chain_drift_t8);
+GIBBS_CHAIN_TU(launch_chain_init_t4);   // chain_kernel<.., INIT_ONLY>: the random starts on the chain's own team
+GIBBS_CHAIN_TU(launch_chain_init_t1);
+GIBBS_CHAIN_TU(launch_chain_init_drift_t4);
+GIBBS_CHAIN_TU(launch_chain_init_drift_t1);
+GIBBS_CHAIN_TU(launch_chain_init_masked_t4);
+GIBBS_CHAIN_TU(launch_chain_init_masked_t1);
+GIBBS_CHAIN_TU(launch_chain_init_masked_drift_t4);
+GIBBS_CHAIN_TU(launch_chain_init_masked_drift_t1);
+GIBBS_CHAIN_TU(launch_init_wide);       // gibbs_init_tu.cu: the grid-wide random-start kernels
+GIBBS_CHAIN_TU(launch_init_wide_drift);
+GIBBS_CHAIN_TU(launch_init_smem);
 #undef GIBBS_CHAIN_TU
+// gibbs_cluster_tu.cu: one chain on a cluster of 4 / 8 CTAs (capacity_out != null: only report how many clusters fit)
+cudaError_t launch_chain_cluster4(const ChainArgs &a, int n_clusters, cudaStream_t stream, int *capacity_out);
+cudaError_t launch_chain_cluster8(const ChainArgs &a, int n_clusters, cudaStream_t stream, int *capacity_out);
+size_t launch_chain_cluster4_smem(int n, int row_words);
+size_t launch_chain_cluster8_smem(int n, int row_words);
 }
 
 using namespace gibbs;
@@ -143,6 +159,11 @@ struct gibbs_handle {
     int32_t start_max_excess = 0;      // max over the staged start sites of (site - length of its sequence)
     int32_t opt_init_path = 0;         // gibbs_set_option(GIBBS_OPT_INIT_PATH)
     int32_t opt_exact_scans = 0;       // gibbs_set_option(GIBBS_OPT_EXACT_SCANS)
+    int32_t opt_stage2_at = 2, opt_stage3_at = 1; // hand-over thresholds in chains per SM (GIBBS_OPT_STAGE2_AT / _STAGE3_AT)
+    int32_t opt_cluster = 8;           // largest cluster the last hand-over stages may use: 0 (none), 4 or 8 (GIBBS_OPT_CLUSTER)
+    int32_t cluster_cap[2] = {-1, -1}; // clusters of 4 / 8 CTAs the device holds at once (queried once per shape)
+    int32_t cluster_cap_n = 0, cluster_cap_rw = 0, cluster_cap_k = 0;
+    int32_t run_stages = 0;            // launches of the chain kernel family in the last run
     int32_t run_init_path = 0;         // where the random starts of the last run ran (GIBBS_INIT_*)
     DevBuf<int32_t> win_sites;         // gibbs_fetch_best: the winner's rows + [n] restart index
     DevBuf<double> win_scores;         // [n] scores + [n] sum
@@ -247,52 +268,70 @@ int32_t launch_team(gibbs_handle *h, int team, bool masked, bool drift, const Ch
     return GIBBS_OK;
 }
 
+// Random starts are N independent site updates of N-1 draws each, so they need not run on the chain's own team:
+//   GIBBS_INIT_SMEM   grid-wide, one CTA per SM holding the whole packed set in shared memory (the draws gather
+//                     from LDS): whenever the set fits (fixed background, A,C,G,T only) -- C2: 144 KB
+//   GIBBS_INIT_WIDE   grid-wide with global gathers: few chains or many sequences (C4, 8 chains: 17.2 s -> 0.61 s
+//                     against the chain kernel's INIT sweep)
+//   GIBBS_INIT_CHAIN  inside the chain kernel: many chains of few sequences whose set does not fit
+// Launches the grid-wide kernel if one is chosen and clears GIBBS_PHASE_INIT from a.phase_mask.
 template <int KPV>
-int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
-    h->run_extra_launches = 0;
-    // Random starts are N independent site updates of N-1 draws each, so they need not run on the chain's own team:
-    //   GIBBS_INIT_SMEM   grid-wide, one CTA per SM holding the whole packed set in shared memory (the draws gather
-    //                     from LDS): whenever the set fits (fixed background, A,C,G,T only) -- C2: 144 KB
-    //   GIBBS_INIT_WIDE   grid-wide with global gathers: few chains or many sequences (C4, 8 chains: 17.2 s -> 0.61 s
-    //                     against the chain kernel's INIT sweep)
-    //   GIBBS_INIT_CHAIN  inside the chain kernel: many chains of few sequences whose set does not fit
-    const bool masked = a.s.mask != nullptr; // symbols outside A,C,G,T: one launch of the MASKED instantiation (1 or 4 warps)
+int32_t launch_random_starts(gibbs_handle *h, ChainArgs &a, bool drift) {
+    const bool masked = a.s.mask != nullptr; // symbols outside A,C,G,T: inside the MASKED chain kernel
     int init_path = GIBBS_INIT_CHAIN;
     if ((a.phase_mask & GIBBS_PHASE_INIT) && !masked) {
-        const bool smem_fits = !drift && init_smem_total_bytes(a.s.n, a.s.row_words, KPV) <= h->smem_optin &&
-                               (long long)a.n_chains * a.s.n >= (long long)h->sm_count * ISM_WARPS;
+        const bool smem_ok = !drift && init_smem_total_bytes(a.s.n, a.s.row_words, KPV) <= h->smem_optin;
+        const bool smem_fits = smem_ok && (long long)a.n_chains * a.s.n >= (long long)h->sm_count * ISM_WARPS;
         const bool wide_fits = init_smem_bytes(a.s.row_words) <= 200 * 1024;
-        const bool wide_wins = a.n_chains < 4 * h->sm_count || a.s.n >= 4096;
+        const bool wide_wins = a.n_chains < 4 * h->sm_count || a.s.n >= 4096 || a.sampler == GIBBS_MOTIF_SAMPLER;
         init_path = smem_fits ? GIBBS_INIT_SMEM : (wide_fits && wide_wins) ? GIBBS_INIT_WIDE : GIBBS_INIT_CHAIN;
         if (h->opt_init_path == GIBBS_INIT_CHAIN) init_path = GIBBS_INIT_CHAIN;
         if (h->opt_init_path == GIBBS_INIT_WIDE && wide_fits) init_path = GIBBS_INIT_WIDE;
-        if (h->opt_init_path == GIBBS_INIT_SMEM && !drift && init_smem_total_bytes(a.s.n, a.s.row_words, KPV) <= h->smem_optin)
-            init_path = GIBBS_INIT_SMEM;
+        if (h->opt_init_path == GIBBS_INIT_SMEM && smem_ok) init_path = GIBBS_INIT_SMEM;
     }
     h->run_init_path = init_path;
     if (init_path == GIBBS_INIT_SMEM) {
         const int smem = (int)init_smem_total_bytes(a.s.n, a.s.row_words, KPV);
-        int32_t rc = set_smem(init_smem_kernel<KPV>, smem);
-        if (rc) return rc;
         const long long items = (long long)a.n_chains * a.s.n;
         long long grid = (items + ISM_WARPS - 1) / ISM_WARPS;
         if (grid > h->sm_count) grid = h->sm_count;
-        init_smem_kernel<KPV><<<(int)grid, ISM_WARPS * 32, smem, h->stream>>>(a);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch_init_smem(a, (int)grid, smem, h->stream));
         a.phase_mask &= ~GIBBS_PHASE_INIT; // the chain kernel continues from the state just written
         h->run_extra_launches += 1;
     } else if (init_path == GIBBS_INIT_WIDE) {
         const int smem = init_smem_bytes(a.s.row_words);
-        int32_t rc = drift ? set_smem(init_kernel<KPV, true>, smem) : set_smem(init_kernel<KPV, false>, smem);
-        if (rc) return rc;
         const long long items = (long long)a.n_chains * a.s.n;
         long long grid = (items + INIT_WARPS - 1) / INIT_WARPS;
         if (grid > 4LL * h->sm_count) grid = 4LL * h->sm_count;
-        if (drift) init_kernel<KPV, true><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
-        else init_kernel<KPV, false><<<(int)grid, INIT_WARPS * 32, smem, h->stream>>>(a);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(drift ? launch_init_wide_drift(a, (int)grid, smem, h->stream) : launch_init_wide(a, (int)grid, smem, h->stream));
         a.phase_mask &= ~GIBBS_PHASE_INIT;
         h->run_extra_launches += 1;
+    } else if (a.phase_mask & GIBBS_PHASE_INIT) { // on the chain's own team: one CTA of 4 warps (or 1) per chain
+        const int team = (a.s.n >= 4 && team_smem_bytes(a.s.row_words, 4) <= 200 * 1024 && h->team_warps != 1) ? 4 : 1;
+        const int smem = team_smem_bytes(a.s.row_words, team);
+        if (smem > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequences too long for shared-memory staging");
+        ChainArgs b = a;
+        b.from_list = 0;
+        b.pause_below = 0;
+        cudaError_t e;
+        if (masked && drift) e = team == 4 ? launch_chain_init_masked_drift_t4(b, a.n_chains, smem, h->stream) : launch_chain_init_masked_drift_t1(b, a.n_chains, smem, h->stream);
+        else if (masked) e = team == 4 ? launch_chain_init_masked_t4(b, a.n_chains, smem, h->stream) : launch_chain_init_masked_t1(b, a.n_chains, smem, h->stream);
+        else if (drift) e = team == 4 ? launch_chain_init_drift_t4(b, a.n_chains, smem, h->stream) : launch_chain_init_drift_t1(b, a.n_chains, smem, h->stream);
+        else e = team == 4 ? launch_chain_init_t4(b, a.n_chains, smem, h->stream) : launch_chain_init_t1(b, a.n_chains, smem, h->stream);
+        CUDA_TRY(e);
+        a.phase_mask &= ~GIBBS_PHASE_INIT;
+        h->run_extra_launches += 1;
+    }
+    return GIBBS_OK;
+}
+
+template <int KPV>
+int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
+    h->run_extra_launches = 0;
+    const bool masked = a.s.mask != nullptr; // one launch of the MASKED instantiation (1 or 4 warps)
+    {
+        const int32_t rc = launch_random_starts<KPV>(h, a, drift);
+        if (rc) return rc;
     }
     // Warps per chain and the straggler hand-over. Chains need very different numbers of sweeps, so a
     // one-wave launch ends with a few chains running on a mostly idle GPU. Stage 1 runs every chain with 4
@@ -301,51 +340,75 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
     // with 16 warps. Late sweeps move few sites, so the wider speculative rounds are rarely discarded.
     const int N = a.s.n, sms = h->sm_count;
     auto fits = [&](int t) { return N >= t && team_smem_bytes(a.s.row_words, t) <= 200 * 1024; };
-    struct Stage { int team, pause_below; };
-    Stage stages[3];
+    struct Stage { int team, pause_below, cluster; };
+    Stage stages[5];
     int n_stages = 0;
     if (masked) {
-        stages[n_stages++] = {team_smem_bytes(a.s.row_words, 4) <= 200 * 1024 ? 4 : 1, 0};
+        stages[n_stages++] = {team_smem_bytes(a.s.row_words, 4) <= 200 * 1024 ? 4 : 1, 0, 0};
     } else if (drift) { // data-derived background: 4 warps per chain (4 chains per SM), the last 2 per SM continue with 8
         const int forced = h->team_warps == 16 ? 8 : h->team_warps;
         if (forced != 0) {
-            stages[n_stages++] = {forced, 0};
+            stages[n_stages++] = {forced, 0, 0};
         } else {
             int first = a.n_chains > 2 * sms ? 4 : 8;
             if (first == 8 && !fits(8)) first = 4;
             if (first == 4 && !fits(4)) first = 1;
-            stages[n_stages++] = {first, 0};
+            stages[n_stages++] = {first, 0, 0};
             if (first == 4 && fits(8)) {
                 stages[n_stages - 1].pause_below = 2 * sms;
-                stages[n_stages++] = {8, 0};
+                stages[n_stages++] = {8, 0, 0};
             }
         }
     } else if (h->team_warps != 0) {
-        stages[n_stages++] = {h->team_warps, 0};
+        stages[n_stages++] = {h->team_warps, 0, 0};
     } else {
-        int first = a.n_chains > 2 * sms ? 4 : a.n_chains > sms ? 8 : 16; // wider teams only while warp slots are idle
+        int first = a.n_chains > h->opt_stage2_at * sms ? 4 : a.n_chains > h->opt_stage3_at * sms ? 8 : 16; // wider teams only while warp slots are idle
         if (first == 16 && !fits(16)) first = 8;
         if (first == 8 && !fits(8)) first = 4;
         if (first == 4 && !fits(4)) first = 1;
-        stages[n_stages++] = {first, 0};
+        stages[n_stages++] = {first, 0, 0};
         if (first == 4 && fits(8)) {
-            stages[n_stages - 1].pause_below = 2 * sms;
-            stages[n_stages++] = {8, 0};
+            stages[n_stages - 1].pause_below = h->opt_stage2_at * sms;
+            stages[n_stages++] = {8, 0, 0};
         }
         if (stages[n_stages - 1].team == 8 && fits(16)) {
-            stages[n_stages - 1].pause_below = sms;
-            stages[n_stages++] = {16, 0};
+            stages[n_stages - 1].pause_below = h->opt_stage3_at * sms;
+            stages[n_stages++] = {16, 0, 0};
+        }
+        // With fewer chains than SMs left, one chain gets several SMs: a thread-block cluster of 4, then 8 CTAs of 16 warps
+        // (chain_cluster_kernel). Needs the ranking pass, the W table in shared memory and rounds of 64 sequences to fill.
+        if (stages[n_stages - 1].team == 16 && h->opt_cluster >= 4 && a.fast_ok && N >= 128) {
+            if (h->cluster_cap_n != N || h->cluster_cap_rw != a.s.row_words || h->cluster_cap_k != a.k) {
+                h->cluster_cap[0] = h->cluster_cap[1] = 0;
+                int cap = 0;
+                if (launch_chain_cluster4_smem(N, a.s.row_words) <= h->smem_optin &&
+                    launch_chain_cluster4(a, 1, h->stream, &cap) == cudaSuccess) h->cluster_cap[0] = cap;
+                cap = 0;
+                if (launch_chain_cluster8_smem(N, a.s.row_words) <= h->smem_optin &&
+                    launch_chain_cluster8(a, 1, h->stream, &cap) == cudaSuccess) h->cluster_cap[1] = cap;
+                cudaGetLastError();
+                h->cluster_cap_n = N; h->cluster_cap_rw = a.s.row_words; h->cluster_cap_k = a.k;
+            }
+            if (h->cluster_cap[0] > 0) {
+                stages[n_stages - 1].pause_below = h->cluster_cap[0];
+                stages[n_stages++] = {16, 0, 4};
+                if (h->opt_cluster >= 8 && h->cluster_cap[1] > 0 && h->cluster_cap[1] < h->cluster_cap[0]) {
+                    stages[n_stages - 1].pause_below = h->cluster_cap[1];
+                    stages[n_stages++] = {16, 0, 8};
+                }
+            }
         }
     }
     h->run_team = stages[0].team;
-    // control words: [0] chains still running, [1] / [2] number of chains paused by stage 1 / 2
-    CUDA_TRY(h->ctl.reserve(4));
-    const int32_t ctl0[4] = {a.n_chains, 0, 0, 0};
+    h->run_stages = n_stages;
+    // control words: [0] chains still running, [s] number of chains paused by stage s
+    CUDA_TRY(h->ctl.reserve(8));
+    const int32_t ctl0[8] = {a.n_chains, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(h->ctl.p, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, h->stream));
     a.active = h->ctl.p;
     if (n_stages > 1) {
         CUDA_TRY(h->resume.reserve((size_t)a.n_chains));
-        CUDA_TRY(h->pending.reserve(2 * (size_t)a.n_chains));
+        CUDA_TRY(h->pending.reserve((size_t)(n_stages - 1) * (size_t)a.n_chains));
         a.resume = h->resume.p;
     }
     for (int st = 0; st < n_stages; ++st) {
@@ -357,8 +420,12 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
         b.pending_out = st + 1 < n_stages ? h->pending.p + (size_t)st * a.n_chains : nullptr;
         b.pending_out_n = st + 1 < n_stages ? h->ctl.p + st + 1 : nullptr;
         const int grid = st == 0 ? a.n_chains : stages[st - 1].pause_below; // at most that many chains were paused
-        int32_t rc = launch_team(h, stages[st].team, masked, drift, b, grid);
-        if (rc) return rc;
+        if (stages[st].cluster) {
+            CUDA_TRY(stages[st].cluster == 4 ? launch_chain_cluster4(b, grid, h->stream, nullptr) : launch_chain_cluster8(b, grid, h->stream, nullptr));
+        } else {
+            int32_t rc = launch_team(h, stages[st].team, masked, drift, b, grid);
+            if (rc) return rc;
+        }
         if (st > 0) h->run_extra_launches += 1;
     }
     return GIBBS_OK;
@@ -504,23 +571,44 @@ BgTables bg_tables(const gibbs_handle *h) {
     return b;
 }
 
-int32_t launch_motif(gibbs_handle *h, const MotifArgs &m) {
-    const int kp = (m.c.k + 1) / 2;
-    const int smem = team_smem_bytes(m.c.s.row_words, 1);
-    switch (kp) {
-#define X(KPV)                                                                          \
-    case KPV: {                                                                         \
-        int32_t rc = set_smem(motif_kernel<KPV>, smem);                                 \
-        if (rc) return rc;                                                              \
-        motif_kernel<KPV><<<m.c.n_chains, 32, smem, h->stream>>>(m);                    \
-        break;                                                                          \
+// warps per chain of the MotifSampler kernel
+int motif_team(const gibbs_handle *h) {
+    if (h->team_warps == 1) return 1;
+    return (h->n >= 4 && team_smem_bytes(h->row_words, 4) <= 200 * 1024) ? 4 : 1;
+}
+
+template <int KPV>
+int32_t launch_motif_kp(gibbs_handle *h, MotifArgs m) {
+    h->run_extra_launches = 0;
+    {   // the random starts are the SiteSampler's (fs:876, fs:993): run them grid-wide whenever a kernel fits
+        const int before = m.c.phase_mask;
+        const int32_t rc = launch_random_starts<KPV>(h, m.c, m.data_bg != 0);
+        if (rc) return rc;
+        m.init_done = (before & GIBBS_PHASE_INIT) && !(m.c.phase_mask & GIBBS_PHASE_INIT);
     }
+    const int team = motif_team(h);
+    const int smem = team_smem_bytes(m.c.s.row_words, team);
+    if (team == 4) {
+        int32_t rc = set_smem(motif_kernel<KPV, 4>, smem);
+        if (rc) return rc;
+        motif_kernel<KPV, 4><<<m.c.n_chains, 128, smem, h->stream>>>(m);
+    } else {
+        int32_t rc = set_smem(motif_kernel<KPV, 1>, smem);
+        if (rc) return rc;
+        motif_kernel<KPV, 1><<<m.c.n_chains, 32, smem, h->stream>>>(m);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->run_team = team;
+    return GIBBS_OK;
+}
+
+int32_t launch_motif(gibbs_handle *h, const MotifArgs &m) {
+    switch ((m.c.k + 1) / 2) {
+#define X(KPV) case KPV: return launch_motif_kp<KPV>(h, m);
         KP_CASES(X)
 #undef X
     default: return fail(GIBBS_ERR_ARG, "unsupported k");
     }
-    CUDA_TRY(cudaGetLastError());
-    return GIBBS_OK;
 }
 
 int32_t launch_roulette(gibbs_handle *h, const RouletteArgs &r) {
@@ -957,10 +1045,10 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         } else {
             h->bg_valid = false; // the fixed-background tables are not used; only the window stride is
             h->bg_wstride = h->max_len - p->k + 1;
-            CUDA_TRY(h->gbuf.reserve((size_t)n_chains * h->bg_wstride));
+            CUDA_TRY(h->gbuf.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride));
         }
-        CUDA_TRY(h->cand_l.reserve((size_t)n_chains * h->bg_wstride));
-        CUDA_TRY(h->cand_w.reserve((size_t)n_chains * h->bg_wstride));
+        CUDA_TRY(h->cand_l.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride)); // one scratch list per warp
+        CUDA_TRY(h->cand_w.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride));
         CUDA_TRY(h->err_flag.reserve(1));
         CUDA_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int32_t), h->stream));
         MotifArgs m{};
@@ -997,10 +1085,11 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             m.greedy_fast_ok = 0;
             m.roulette_scan_ok = 0;
         }
+        m.c.drift_fast_ok = m.data_bg ? m.greedy_fast_ok : 0; // what the grid-wide random starts (init_kernel<.., DRIFT>) read
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
         rc = launch_motif(h, m);
         if (rc) return rc;
-        h->run_team = 1;
+        launches += h->run_extra_launches;
     } else if (p->background == GIBBS_BG_DATA) {
         // teams of warps, speculative rounds and the hand-over of chain_kernel, with the drifting-background scan
         a.pvals = h->pvals.p;
@@ -1204,6 +1293,16 @@ int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value) {
     case GIBBS_OPT_EXACT_SCANS:
         h->opt_exact_scans = value != 0;
         return GIBBS_OK;
+    case GIBBS_OPT_CLUSTER:
+        if (value != 0 && value != 4 && value != 8) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_CLUSTER takes 0, 4 or 8");
+        h->opt_cluster = value;
+        return GIBBS_OK;
+    case GIBBS_OPT_STAGE2_AT:
+    case GIBBS_OPT_STAGE3_AT:
+        if (value < 1 || value > 16) return fail(GIBBS_ERR_ARG, "hand-over thresholds are 1 .. 16 chains per SM");
+        (option == GIBBS_OPT_STAGE2_AT ? h->opt_stage2_at : h->opt_stage3_at) = value;
+        if (h->opt_stage3_at > h->opt_stage2_at) h->opt_stage3_at = h->opt_stage2_at;
+        return GIBBS_OK;
     default:
         return fail(GIBBS_ERR_ARG, "unknown option %d", option);
     }
@@ -1234,7 +1333,8 @@ int32_t gibbs_multi_create(const uint8_t *seqs, const int64_t *offsets, int32_t 
     const int32_t visible = gibbs_device_count();
     if (visible < 1) return fail(GIBBS_ERR_CUDA, "no CUDA device available; libgibbs_b200 has no CPU fallback");
     if (n_devices == 0) n_devices = visible; // 0 = every visible device
-    if (n_devices < 1 || n_devices > visible) return fail(GIBBS_ERR_ARG, "n_devices = %d, %d visible", n_devices, visible);
+    // (an explicit device list may name a device twice: two slots then share it)
+    if (n_devices < 1 || (!devices && n_devices > visible)) return fail(GIBBS_ERR_ARG, "n_devices = %d, %d visible", n_devices, visible);
     gibbs_multi *m = new (std::nothrow) gibbs_multi();
     if (!m) return fail(GIBBS_ERR_NOMEM, "host allocation failed");
     for (int32_t i = 0; i < n_devices; ++i) {

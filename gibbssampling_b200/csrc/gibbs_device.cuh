@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace gibbs {
 
@@ -411,6 +412,7 @@ struct Hist {
 template <int KP>
 struct KmerCounter {
     static constexpr int NW = (KP > 8) ? 2 : 1; // 32-bit words of a k-mer (16 columns each)
+    using Word = typename std::conditional<(KP > 8), uint64_t, uint32_t>::type; // a k-mer as the gathers deliver it
     uint32_t nib[NW][3][2];      // [word][base - 1][column parity]: 4-bit fields, field m = column 16 word + 2 m + parity
     uint32_t byt[NW][3][2][2];   // [..][nibble parity h]: 8-bit fields, field q = column 16 word + 4 q + 2 h + parity
     int quads;                   // quads since the last nibble spill (<= 3)
@@ -437,7 +439,7 @@ struct KmerCounter {
         quads = 0;
     }
     // four k-mers (an invalid draw passes 0: base 0 everywhere, counted nowhere)
-    __device__ __forceinline__ void add4(const uint64_t x[4]) {
+    __device__ __forceinline__ void add4(const Word x[4]) {
         if (quads == 3) spill();
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -458,15 +460,14 @@ struct KmerCounter {
         }
         ++quads;
     }
-    // dst[j*4 + b] = warp totals for b = 1, 2, 3 and columns j < k; dst[j*4] = added - the three (added = k-mers the
-    // whole warp added since the last flush). At most 252 k-mers per lane between flushes. dst is overwritten when
-    // first, else increased.
+    // Warp totals into dst[j*4 + b] for b = 1, 2, 3 and columns j < k; dst[j*4] gets `added` (the k-mers the whole warp
+    // added since the last flush; finish() turns it into the count of base 0). At most 252 k-mers per lane between
+    // flushes. first: dst is written, else increased. Reduction number `it` (two byte fields widened to 16 bits, one
+    // REDUX.SUM) is kept by lane `it`, so the results leave with two stores per lane instead of a predicated
+    // read-modify-write per reduction.
     __device__ __forceinline__ void flush(int32_t *dst, int k, int added, bool first, int lane) {
         spill();
-        if (first) {
-            for (int e = lane; e < 8 * KP; e += 32) dst[e] = 0; // columns 0 .. 2 KP - 1 (k or k + 1 of them)
-            __syncwarp();
-        }
+        uint32_t mine[NW] = {};
 #pragma unroll
         for (int w = 0; w < NW; ++w)
 #pragma unroll
@@ -477,23 +478,29 @@ struct KmerCounter {
                     for (int h = 0; h < 2; ++h)
 #pragma unroll
                         for (int g = 0; g < 2; ++g) { // g = 0: byte fields 0, 2; g = 1: byte fields 1, 3
-                            const int c0 = 16 * w + 4 * g + 2 * h + p, c1 = c0 + 8; // columns of the two 16-bit halves
-                            if (c0 < 2 * KP) {
+                            const int it = (((b * 2 + p) * 2 + h) * 2 + g); // 0 .. 23 within word w
+                            if (16 * w + 4 * g + 2 * h + p < 2 * KP) {      // (first column of the pair exists)
                                 const uint32_t s = __reduce_add_sync(FULL, (byt[w][b][p][h] >> (8 * g)) & 0x00FF00FFu);
-                                if (lane == ((c0 + 5 * b) & 31)) {
-                                    if (c0 < k) dst[c0 * 4 + b + 1] += (int32_t)(s & 0xFFFFu);
-                                    if (c1 < k) dst[c1 * 4 + b + 1] += (int32_t)(s >> 16);
-                                }
+                                if (lane == it) mine[w] = s;
                             }
                         }
+        if (lane < 24) {
+            const int g = lane & 1, h = (lane >> 1) & 1, p = (lane >> 2) & 1, b = lane >> 3;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int c0 = 16 * w + 4 * g + 2 * h + p, c1 = c0 + 8; // columns of the two 16-bit halves
+                const int32_t v0 = (int32_t)(mine[w] & 0xFFFFu), v1 = (int32_t)(mine[w] >> 16);
+                if (c0 < k) dst[c0 * 4 + b + 1] = first ? v0 : dst[c0 * 4 + b + 1] + v0;
+                if (c1 < k) dst[c1 * 4 + b + 1] = first ? v1 : dst[c1 * 4 + b + 1] + v1;
+            }
+        }
 #pragma unroll
         for (int w = 0; w < NW; ++w)
 #pragma unroll
             for (int b = 0; b < 3; ++b)
 #pragma unroll
                 for (int p = 0; p < 2; ++p) byt[w][b][p][0] = byt[w][b][p][1] = 0;
-        __syncwarp();
-        if (lane < k) dst[lane * 4] += added;
+        if (lane < k) dst[lane * 4] = first ? added : dst[lane * 4] + added;
         __syncwarp();
     }
     // after the last flush: base 0 = what the other three left
@@ -502,6 +509,30 @@ struct KmerCounter {
         __syncwarp();
     }
 };
+
+// k-mer at base `pos` of row i of a packed set, as one (k <= 16) or two 32-bit words. SROWS: the set is in shared memory.
+// (__funnelshift_r shifts by its count & 31, and (2 pos) & 31 = 2 (pos & 15).)
+template <int KP, bool SROWS>
+__device__ __forceinline__ typename KmerCounter<KP>::Word gather_kmer(const uint32_t *__restrict__ rows, int row_words, int i, int pos) {
+    uint32_t w0, w1, w2 = 0;
+    if (SROWS) {
+        const uint32_t *p = rows + (i * row_words + (pos >> 4));
+        w0 = p[0];
+        w1 = p[1];
+        if (KP > 8) w2 = p[2];
+    } else {
+        const uint32_t *p = rows + (size_t)i * row_words + (pos >> 4);
+        w0 = __ldg(p);
+        w1 = __ldg(p + 1);
+        if (KP > 8) w2 = __ldg(p + 2);
+    }
+    const uint32_t lo = __funnelshift_r(w0, w1, 2 * pos);
+    if constexpr (KP > 8) {
+        return ((uint64_t)__funnelshift_r(w1, w2, 2 * pos) << 32) | lo;
+    } else {
+        return lo;
+    }
+}
 
 // counts over the sites of all sequences except `exclude` (sites < 0 = no site), positions shifted
 // by `mode`: the fused PFM of fs:392-396 (exclude = held-out) or the all-sites total. All T warps
@@ -545,7 +576,8 @@ __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *
 // Leave-one-out count c = counts - own, then W(c, b) and its fixed-point log2 are gathered from the
 // precomputed table (normalizePPM fs:255-261 + createPositionWeightMatrix fs:282-287 evaluated once
 // per distinct count instead of once per window).
-template <int KP, bool MASKED>
+// WSMEM: wtab is a copy in shared memory (chain_cluster_kernel), else global memory read through the read-only path
+template <int KP, bool MASKED, bool WSMEM = false>
 __device__ __forceinline__ void build_tables_impl(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
                                                   const WEnt *__restrict__ wtab, int lane, uint64_t own_mask) {
 #pragma unroll
@@ -556,7 +588,8 @@ __device__ __forceinline__ void build_tables_impl(const WarpTables &W, const int
         if (j < k) {
             int c = counts[e];
             if (has_own && (int)((own >> (2 * j)) & 3u) == b && !(MASKED && ((own_mask >> (2 * j)) & 1u))) c -= 1; // (a masked own base was never counted)
-            const int4 raw = __ldg(reinterpret_cast<const int4 *>(wtab + (size_t)c * 4 + b));
+            const int4 *ent = reinterpret_cast<const int4 *>(wtab + (size_t)c * 4 + b);
+            const int4 raw = WSMEM ? *ent : __ldg(ent);
             w = __hiloint2double(raw.y, raw.x);
             lg = raw.z;
         }

@@ -108,6 +108,12 @@ static __global__ void wtab_kernel(int n, double pc, double den, double q0, doub
 #ifndef GIBBS_T4_MIN_BLOCKS
 #define GIBBS_T4_MIN_BLOCKS 7 // 72 registers per thread; measured against 6 (80) and 8 (64)
 #endif
+#ifndef GIBBS_T8_MIN_BLOCKS
+#define GIBBS_T8_MIN_BLOCKS 3
+#endif
+#ifndef GIBBS_T16_MIN_BLOCKS
+#define GIBBS_T16_MIN_BLOCKS 1
+#endif
 #ifndef GIBBS_INIT_MIN_BLOCKS
 #define GIBBS_INIT_MIN_BLOCKS 2
 #endif
@@ -115,6 +121,70 @@ static __global__ void wtab_kernel(int n, double pc, double den, double q0, doub
 // and keeps its loads batched (with the check inline the random starts of C2 cost 60 % more instructions).
 // SROWS = `rows` is a copy of the packed set in shared memory (init_smem_kernel): the gathers are LDS, not L1 sectors.
 // The base counts are kept bit-sliced in registers (KmerCounter): no lookup table.
+// UNI = every sequence has the same length (no length load per draw); PHILOX = the counter-based stream (else the
+// injected doubles): warp-uniform properties of the run, hoisted out of the draw loop as template parameters.
+template <int KP, int NB, bool MASKED, bool SROWS, bool UNI, bool PHILOX>
+__device__ __forceinline__ void random_draw_loop(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n, int32_t *counts,
+                                                 int lane, int32_t *fix, const uint32_t *base_rows) {
+    using Word = typename KmerCounter<KP>::Word;
+    const int N = a.s.n, k = a.k;
+    const int row_words = a.s.row_words;
+    const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
+    const uint64_t d_end = base + (uint64_t)(N - 1);
+    const uint64_t blk0 = base >> 2, blk1 = (d_end + 3) >> 2;
+    const int n_blk = (int)(blk1 - blk0);
+    const int iters = (n_blk + 32 * NB - 1) / (32 * NB);
+    const int r_first = (int)((int64_t)(blk0 << 2) - (int64_t)base); // rank of the first draw of block blk0: -3 .. 0
+    const uint32_t range_u = (uint32_t)(a.s.uniform_len - k + 1);
+    KmerCounter<KP> h;
+    h.clear();
+    constexpr int FLUSH_ROUNDS = 63 / NB; // 63 quads = 252 k-mers per lane between warp reductions
+    bool first = true;
+    for (int it0 = 0; it0 < iters; it0 += FLUSH_ROUNDS) {
+        const int it1 = min(iters, it0 + FLUSH_ROUNDS);
+        for (int it = it0; it < it1; ++it) {
+            Word kmer[NB][4];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const int bi = (it * NB + q) * 32 + lane; // block index inside this held-out sequence's draw range
+                uint32_t wd[4] = {0, 0, 0, 0};
+                if (PHILOX) {
+                    const uint64_t blk = blk0 + (uint64_t)bi;
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
+                }
+                const int r0 = r_first + 4 * bi; // rank of draw 0 of this block; a draw is valid iff 0 <= rank < N-1
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const bool ok = (unsigned)(r0 + x) < (unsigned)(N - 1);
+                    const int r = ok ? r0 + x : 0;
+                    const int i = r + (r >= n ? 1 : 0); // always a valid sequence index (N >= 2)
+                    const uint32_t range = UNI ? range_u : (uint32_t)(__ldg(a.s.len + i) - k + 1);
+                    int pos;
+                    if (PHILOX) {
+                        pos = (int)__umulhi(wd[x], range); // floor(word * 2^-32 * range), exact
+                    } else {
+                        const int64_t d = (int64_t)base + r;
+                        const double u = d < a.uniforms_per_chain ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
+                                                                  : 0.0; // (the host rejects streams that are too short)
+                        pos = (int)(u * (double)range);           // rnd.Next(0, L-k+1), fs:145
+                        pos = min(max(pos, 0), (int)range - 1);   // memory safety for u outside [0,1)
+                    }
+                    const Word km = gather_kmer<KP, SROWS>(base_rows, row_words, i, pos);
+                    kmer[q][x] = ok ? km : (Word)0; // code 0 in every column: counted nowhere
+                    if (MASKED && ok && __ldg(a.s.rowflag + i) != 0) hist_fix(a.s.mask, row_words, i, pos, k, fix);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) h.add4(kmer[q]);
+        }
+        h.flush(counts, k, it1 == iters ? N - 1 : 0, first, lane);
+        first = false;
+    }
+    KmerCounter<KP>::finish(counts, k, lane);
+}
+
 template <int KP, int NB, bool MASKED, bool SROWS = false>
 __device__ __forceinline__ void random_loo_counts_impl(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
                                                        int32_t *counts, int lane, int32_t *fix,
@@ -127,67 +197,21 @@ __device__ __forceinline__ void random_loo_counts_impl(const ChainArgs &a, uint6
         return;
     }
     const uint32_t *const base_rows = SROWS ? rows : a.s.packed;
-    const int row_words = a.s.row_words;
-    const uint64_t base = (uint64_t)n * (uint64_t)(N - 1);
-    const uint64_t d_end = base + (uint64_t)(N - 1);
-    const uint64_t blk0 = base >> 2, blk1 = (d_end + 3) >> 2;
-    const int n_blk = (int)(blk1 - blk0);
-    const int iters = (n_blk + 32 * NB - 1) / (32 * NB);
-    const int r_first = (int)((int64_t)(blk0 << 2) - (int64_t)base); // rank of the first draw of block blk0: -3 .. 0
-    const int ulen = a.s.uniform_len;
-    const uint32_t key0 = (uint32_t)a.seed, key1 = (uint32_t)(a.seed >> 32);
-    const uint32_t c2 = (uint32_t)chain_uid, c3 = (uint32_t)(chain_uid >> 32);
-    KmerCounter<KP> h;
-    h.clear();
-    constexpr int FLUSH_ROUNDS = 63 / NB; // 63 quads = 252 k-mers per lane between warp reductions
-    bool first = true;
-    for (int it0 = 0; it0 < iters; it0 += FLUSH_ROUNDS) {
-        const int it1 = min(iters, it0 + FLUSH_ROUNDS);
-        for (int it = it0; it < it1; ++it) {
-            uint64_t kmer[NB][4];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const int bi = (it * NB + q) * 32 + lane; // block index inside this held-out sequence's draw range
-                const uint64_t blk = blk0 + (uint64_t)bi;
-                uint32_t wd[4] = {0, 0, 0, 0};
-                if (a.rng_mode == 0) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3), make_uint2(key0, key1));
-                    wd[0] = r.x; wd[1] = r.y; wd[2] = r.z; wd[3] = r.w;
-                }
-                const int r0 = r_first + 4 * bi; // rank of draw 0 of this block; a draw is valid iff 0 <= rank < N-1
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const bool ok = (unsigned)(r0 + x) < (unsigned)(N - 1);
-                    const int r = ok ? r0 + x : 0;
-                    const int i = r + (r >= n ? 1 : 0); // always a valid sequence index (N >= 2)
-                    const int range = (ulen > 0 ? ulen : __ldg(a.s.len + i)) - k + 1;
-                    int pos;
-                    if (a.rng_mode == 0) {
-                        pos = (int)__umulhi(wd[x], (uint32_t)range); // floor(word * 2^-32 * range), exact
-                    } else {
-                        const int64_t d = (int64_t)base + r;
-                        const double u = d < a.uniforms_per_chain ? __ldg(a.uniforms + (size_t)chain_local * a.uniforms_per_chain + d)
-                                                                  : 0.0; // (the host rejects streams that are too short)
-                        pos = (int)(u * (double)range);      // rnd.Next(0, L-k+1), fs:145
-                        pos = min(max(pos, 0), range - 1);   // memory safety for u outside [0,1)
-                    }
-                    const uint32_t *rp = base_rows + (size_t)i * row_words;
-                    const uint64_t km = SROWS ? kmer_shared<KP>(rp, pos) : kmer_global<KP>(rp, pos);
-                    kmer[q][x] = ok ? km : 0ull; // code 0 in every column: counted nowhere
-                    if (MASKED && ok && __ldg(a.s.rowflag + i) != 0) hist_fix(a.s.mask, row_words, i, pos, k, fix);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NB; ++q) h.add4(kmer[q]);
-        }
-        h.flush(counts, k, it1 == iters ? N - 1 : 0, first, lane);
-        first = false;
-    }
-    KmerCounter<KP>::finish(counts, k, lane);
+    if (a.rng_mode != 0) random_draw_loop<KP, 1, MASKED, SROWS, false, false>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
+    else if (a.s.uniform_len > 0) random_draw_loop<KP, NB, MASKED, SROWS, true, true>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
+    else random_draw_loop<KP, NB, MASKED, SROWS, false, true>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
     if (MASKED) {
         if (lane < k) counts[lane * 4] -= fix[lane];
         __syncwarp();
     }
+}
+
+// The same routine out of line, for kernels whose register budget belongs to their sweeps (chain_kernel sits at 72
+// registers; its INIT phase runs once per restart, and at the benchmarked shapes a grid-wide kernel runs it instead).
+template <int KP, bool MASKED>
+static __device__ __noinline__ void random_loo_counts_call(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n,
+                                                           int32_t *counts, int lane, int32_t *fix) {
+    random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain_local, n, counts, lane, fix);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -293,7 +317,7 @@ static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS)
 // a few-way bank conflict. One warp per (chain, held-out sequence) item, grid-stride; the held-out row is scanned from
 // the same copy, so this kernel issues no TMA at all.
 #ifndef GIBBS_ISM_WARPS
-#define GIBBS_ISM_WARPS 32 // 64 registers per thread: no spills at k <= 12 (24 warps / 80 registers spill 108 B)
+#define GIBBS_ISM_WARPS 24 // 80 registers per thread: no spills at k <= 12 (32 warps / 64 registers spill)
 #endif
 #ifndef GIBBS_P0_NB_ISM
 #define GIBBS_P0_NB_ISM 1  // LDS latency is short: one Philox block (4 gathers) in flight per lane is enough
@@ -374,8 +398,11 @@ static __global__ void __launch_bounds__(ISM_WARPS * 32, 1) init_smem_kernel(con
 // DRIFT = the data-derived background of doSiteSampling (fs:697): same sweeps, rounds and hand-over; the site update
 // builds the PPM instead of the odds table and scans with the per-window background (gibbs_drift_dev.cuh). Same launch
 // bounds (measured on C2: 7 CTAs of 4 warps at 72 registers 166 ms, 6 at 80 178 ms, 4 at 118 registers 185-193 ms).
-template <int KP, int T, bool MASKED = false, bool DRIFT = false>
-static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T4_MIN_BLOCKS : T == 8 ? 3 : 1)) chain_kernel(const ChainArgs a) {
+// INIT_ONLY = the instantiation that runs the random starts (fs:412) on the chain's own team and nothing else; the
+// sweep instantiations (INIT_ONLY = false) contain no random-start code at all, so the register-limited 4-warp kernel
+// pays nothing for a phase that a grid-wide kernel normally runs (gibbs_api.cu, launch_random_starts).
+template <int KP, int T, bool MASKED = false, bool DRIFT = false, bool INIT_ONLY = false>
+static __global__ void __launch_bounds__(32 * T, (INIT_ONLY ? (T == 1 ? 8 : 4) : T == 1 ? 16 : T == 4 ? GIBBS_T4_MIN_BLOCKS : T == 8 ? GIBBS_T8_MIN_BLOCKS : GIBBS_T16_MIN_BLOCKS)) chain_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
@@ -404,7 +431,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
     int st_sweeps = 0, capped = 0;
     uint32_t vbase = 0; // visit index of n = 0 in the current sweep (wraps harmlessly)
 
-    int phase = next_phase(PH_INIT, a.phase_mask);
+    int phase = INIT_ONLY ? PH_INIT : next_phase(PH_GREEDY, a.phase_mask);
     int sweeps_in_phase = 0;
     bool resumed = false, paused = false;
     if (a.from_list) {
@@ -429,7 +456,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
             if (tid < 32 && i < N) {
                 const int o = (b & 1) * 32 + tid;
                 S.blk_len[o] = __ldg(a.s.len + i);
-                if (phase != PH_INIT) {
+                if (!INIT_ONLY) {
                     S.blk_site[o] = __ldcg(sites + i);
                     S.blk_hv[o] = __ldcg(hv + i);
                 }
@@ -466,9 +493,9 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
                 bool slow;
                 if constexpr (DRIFT) {
                     int f0[4], cn[4];
-                    const bool given = phase == PH_INIT && a.ppm_given != nullptr;
+                    const bool given = INIT_ONLY && a.ppm_given != nullptr;
                     const bool fast = a.drift_fast_ok && !given; // (a supplied PPM may hold zeros or denormals: exact scan)
-                    if (phase == PH_INIT) {
+                    if constexpr (INIT_ONLY) {
                         random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, lane, WT.lgcol);
                         drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
                     } else {
@@ -481,7 +508,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
                     }
                     slow = drift_pick<KP>(WT, row, Wn, k, a, fast, f0, cn, lane, p, w, MASKED ? masked_n : -1, n);
                 } else {
-                    if (phase == PH_INIT) {
+                    if constexpr (INIT_ONLY) {
                         random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, MASKED>(a, chain_uid, chain, n, WT.counts, lane, WT.lgcol);
                         build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
                     } else {
@@ -498,7 +525,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
                                   : pick_argmax<KP>(WT, row, Wn, k, a.fast_ok, lane, p, w);
                 }
                 bool accept = true, moved = false;
-                if (phase != PH_INIT) {
+                if (!INIT_ONLY) {
                     accept = score_improves(p, hv_n, hv_n != hv_n ? __ldcg(scores + n) : 0.0); // fs:402
                     moved = accept && (w != site_n);
                     if (moved && phase == PH_GREEDY) neu = kmer_shared<KP>(row, w); // rows are not read after the sync
@@ -558,11 +585,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
         }
         vbase += (uint32_t)N;
         st_sweeps += 1;
-        if (phase == PH_INIT) {
-            phase = next_phase(PH_GREEDY, a.phase_mask);
-            sweeps_in_phase = 0;
-            continue;
-        }
+        if (INIT_ONLY) break; // the sweep kernel continues from the state just written
         ++sweeps_in_phase;
         bool next = !changed; // positions(acc) = positions(bestMotif), fs:384
         if (!next && sweeps_in_phase >= a.max_sweeps) {
@@ -596,6 +619,7 @@ static __global__ void __launch_bounds__(32 * T, (T == 1 ? 16 : T == 4 ? GIBBS_T
         atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
         atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
     }
+    if (INIT_ONLY) return;
     if (paused) {
         if (tid == 0) {
             a.resume[chain] = phase | (sweeps_in_phase << 8);
@@ -797,11 +821,10 @@ static __global__ void __launch_bounds__(32) restart_select_kernel(const double 
         out[0] = best;
         *win_sum = best < 0 ? 0.0 : sums[best];
     }
-    if (best >= 0)
-        for (int i = lane; i < N; i += 32) {
-            win_sites[i] = sites[(size_t)best * N + i];
-            win_scores[i] = scores[(size_t)best * N + i];
-        }
+    for (int i = lane; i < N; i += 32) { // (no winner: -1 = no site, so that the PWM counts of the result are all zero)
+        win_sites[i] = best >= 0 ? sites[(size_t)best * N + i] : -1;
+        win_scores[i] = best >= 0 ? scores[(size_t)best * N + i] : 0.0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

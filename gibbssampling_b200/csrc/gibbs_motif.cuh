@@ -1,7 +1,7 @@
-// gibbssampling_b200/csrc/gibbs_motif.cuh -- MotifSampler with a fixed background, motifAmount = 1
-// (fs:709-881): candidate list, roulette-wheel pick, the synchronous stochastic sweep and the greedy
-// sweeps. One warp runs one chain sequentially; every window is scored in float64 because the candidate
-// list needs every window above the cut-off, not just the maximum.
+// gibbssampling_b200/csrc/gibbs_motif.cuh -- MotifSampler, motifAmount = 1 (fs:709-1038): candidate list,
+// roulette-wheel pick, the synchronous stochastic sweep and the greedy sweeps. A team of warps runs one chain
+// (motif_kernel below); the stochastic sweep scores every window in float64 because the candidate list needs
+// every window above the cut-off, not just the maximum.
 //
 // MotifIndex state per sequence: site (-1 = Positions []) and PWMS (log2 score of the site, or the raw
 // background probability of a window when "no site" was picked, fs:774-777).
@@ -39,6 +39,7 @@ struct MotifArgs {
     double *gbuf;          // [chains][wstride] background window probabilities of the current held-out sequence
     int32_t greedy_fast_ok; // greedy sweeps may rank windows in fixed point (no float64 under/overflow possible, pc > 0)
     int32_t roulette_scan_ok; // stochastic sweep may locate the roulette bucket with a warp scan (0 = always walk)
+    int32_t init_done;      // the random starts already ran (grid-wide kernel): sites + raw products in hv are the state
 };
 
 // one thread per sequence
@@ -293,219 +294,266 @@ __device__ __forceinline__ void fixed_point_tables(const WarpTables &T, int lane
     __syncwarp();
 }
 
-template <int KP>
-__global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
+// ------------------------------------------------------------------------------------------------
+// the MotifSampler kernel: one team (CTA of T warps) = one restart (fs:876-879 / fs:1034-1038)
+// ------------------------------------------------------------------------------------------------
+// Same division of labour as chain_kernel: one warp performs one whole site update, the T warps of a team work on T
+// consecutive held-out sequences at once (a round).
+//   stochastic sweep (fs:828-853 / fs:935-970): every n reads the INPUT state -- its own entry plus the all-sites
+//     counts taken before the sweep -- so all N updates are independent and every result commits;
+//   greedy sweeps (fs:788-822 / fs:885-929) are in place: speculative rounds as in chain_kernel -- results commit in
+//     order up to and including the first warp whose accepted update changes the sites (moves, drops or gains a site).
+// Per warp: candidate scratch (and, data-derived background, the background window products) in global memory.
+#ifndef GIBBS_MOTIF_T4_BLOCKS
+#define GIBBS_MOTIF_T4_BLOCKS 5
+#endif
+constexpr int MOTIF_BSUM_OFFSET = 2144; // 4 ints in the slack of the team's fixed shared memory (TEAM_FIXED_BYTES = 2176)
+
+template <int KP, int T>
+__global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_BLOCKS : 2)) motif_kernel(const MotifArgs m) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int THREADS = 32 * T;
+    constexpr int R = (2 * T < 4) ? 4 : 2 * T;
     const ChainArgs &a = m.c;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chain = blockIdx.x;
-    const TeamSmem S = carve_smem(smem_raw, 1);
-    const WarpTables WT = warp_tables(S, 0);
+    const TeamSmem S = carve_smem(smem_raw, T);
+    const WarpTables WT = warp_tables(S, warp);
+    int32_t *bsum = reinterpret_cast<int32_t *>(smem_raw + MOTIF_BSUM_OFFSET); // data background: base counts over the sequences that have a site
     const int N = a.s.n, k = a.k;
     int32_t *sites = a.sites + (size_t)chain * N;
     double *pw = a.scores + (size_t)chain * N; // PWMS of the MotifIndex state
     double *hv = a.hv + (size_t)chain * N;
-    double *cand_l = m.cand_l + (size_t)chain * m.bg.wstride;
-    int32_t *cand_w = m.cand_w + (size_t)chain * m.bg.wstride;
-    double *gbuf = m.data_bg ? m.gbuf + (size_t)chain * m.bg.wstride : nullptr;
-    int bsum[4] = {0, 0, 0, 0}; // data background: base counts summed over the sequences that have a site
+    double *cand_l = m.cand_l + ((size_t)chain * T + warp) * m.bg.wstride;
+    int32_t *cand_w = m.cand_w + ((size_t)chain * T + warp) * m.bg.wstride;
+    double *gbuf = m.data_bg ? m.gbuf + ((size_t)chain * T + warp) * m.bg.wstride : nullptr;
     const uint64_t chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
     const double raw_gate = exp2(a.cutoff) * (1.0 - 0x1p-30);
 
-    RowRing<4> ring;
-    ring.init(S, a.s, 0, lane);
-    if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
-    __syncwarp();
-    if (lane == 0) ring.fill(4);
+    RowRing<R> ring;
+    ring.init(S, a.s, 0, tid);
+    if (tid < 16) S.lut[tid] = hist_lut_entry(tid);
+    team_sync<T>();
+    if (warp == 0) ring.fill_span(0u, 0, R, lane);
 
-    unsigned long long st_updates = 0, st_windows = 0, st_slow = 0; // st_slow: updates that scored every window in float64
+    unsigned long long st_updates = 0, st_windows = 0, st_slow = 0, st_spec = 0; // st_slow: updates that scored every window in float64
     int st_sweeps = 0, capped = 0;
-    uint32_t v = 0;
+    uint32_t vbase = 0;
 
-    int phase = MPH_INIT;
-    while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_INIT ? 0 : phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
+    if (m.init_done) { // the random starts ran in their own kernel (gibbs_api.cu, launch_random_starts): the state is
+        // SiteSampler.getPWMOfRandomStarts[WithBPV] |> createMotifIndex prob [position] (fs:876-877, fs:993-994)
+        for (int n = tid; n < N; n += THREADS) pw[n] = log2_ref(__ldcg(hv + n));
+        team_sync<T>();
+    }
+    int phase = MPH_STOCH;
+    while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
     int sweeps_in_phase = 0;
     while (phase != MPH_DONE) {
-        if (phase != MPH_INIT && (phase == MPH_STOCH || sweeps_in_phase == 0)) {
-            site_counts<KP, 1>(a.s, sites, -1, k, SHIFT_NONE, S.total, S.lut, S.fix, lane);
+        if (phase == MPH_STOCH || sweeps_in_phase == 0) {
+            site_counts<KP, T>(a.s, sites, -1, k, SHIFT_NONE, S.total, S.lut, S.fix, tid);
             if (m.data_bg) {
+                if (tid < 4) bsum[tid] = 0;
+                team_sync<T>();
+                int part[4] = {0, 0, 0, 0};
+                for (int i = tid; i < N; i += THREADS)
+                    if (__ldcg(sites + i) >= 0) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) part[b] += __ldg(m.basecnt + i * 4 + b);
+                    }
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    int s = 0;
-                    for (int i = lane; i < N; i += 32)
-                        if (__ldcg(sites + i) >= 0) s += __ldg(m.basecnt + i * 4 + b);
-                    bsum[b] = __reduce_add_sync(FULL, s);
+                    const int s = __reduce_add_sync(FULL, part[b]);
+                    if (lane == 0 && s != 0) atomicAdd(&bsum[b], s);
                 }
+                team_sync<T>();
             }
+        } else {
+            team_sync<T>(); // the previous sweep's last round wrote sites / pw after its only barrier
         }
         bool changed = false;
-        for (int n = 0; n < N; ++n, ++v) {
-            const uint32_t *row = ring.wait(v);
-            const int len_n = __ldg(a.s.len + n);
-            const int W = len_n - k + 1;
-            if (phase == MPH_INIT) { // getPWMOfRandomStarts[WithBPV] |> createMotifIndex prob [position] (fs:876-877, fs:993-994)
-                random_loo_counts_impl<KP, GIBBS_P0_NB_CHAIN, false>(a, chain_uid, chain, n, WT.counts, lane, WT.lgcol);
-                double p;
-                int w;
-                if (!m.data_bg) {
-                    build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
-                    pick_argmax<KP>(WT, row, W, k, a.fast_ok, lane, p, w);
-                } else { // SiteSampler.getPWMOfRandomStarts: drifting background (fs:589-611), ranked like the SiteSampler's
-                    const bool given = a.ppm_given != nullptr;           // fs:1029: scored against the caller's PPM
-                    const bool fast = m.greedy_fast_ok && !given;
-                    int f0[4], cn[4];
-                    drift_tables<KP>(WT, WT.counts, false, 0, k, a, given, fast, n, lane, f0, cn);
-                    drift_pick<KP>(WT, row, W, k, a, fast, f0, cn, lane, p, w, -1, n);
-                }
-                if (lane == 0) {
-                    sites[n] = w;
-                    pw[n] = log2_ref(p);
-                }
-            } else {
-                const int site_n = __ldcg(sites + n);
-                const double pw_n = __ldcg(pw + n);
-                const bool has_own = site_n >= 0;
-                const uint64_t own = has_own ? kmer_shared<KP>(row, site_n) : 0;
-                const double *g_n = m.bg.g + (size_t)n * m.bg.wstride;
-                double gsum_n = 0.0, gmax_n = 0.0;
-                int cn[4] = {0, 0, 0, 0};
-                if (!m.data_bg) {
-                    build_tables<KP>(WT, S.total, has_own, own, k, a.wtab, lane);
-                    gsum_n = __ldg(m.bg.gsum + n);
-                    gmax_n = __ldg(m.bg.gmax + n);
-                } else {
-                    // background of this held-out sequence (fs:896-905): the OTHER sequences that have a site, outside
-                    // those sites (fused over the alphabet), plus every base of the held-out sequence
-                    for (int e = lane; e < 4 * k; e += 32) {
-                        int c = S.total[e];
-                        if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3)) c -= 1;
-                        WT.lgcol[e] = c;
-                    }
-                    __syncwarp();
-                    int F[4], fs = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        int s = 0;
-                        for (int j = lane; j < k; j += 32) s += WT.lgcol[j * 4 + b];
-                        cn[b] = __ldg(m.basecnt + n * 4 + b);
-                        F[b] = bsum[b] - (has_own ? cn[b] : 0) - __reduce_add_sync(FULL, s) + cn[b];
-                        fs += F[b];
-                    }
-                    const double den = __dadd_rn((double)fs, m.alpha_pc);
-                    double q[4];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) q[b] = __ddiv_rn(__dadd_rn((double)F[b], m.pc), den); // fs:119
-                    for (int e = lane; e < 8 * KP; e += 32) { // PWM = PPM / pcv (fs:286); dummy column of an odd k = 1.0
-                        const int b = e & 3;
-                        const double qb = b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3];
-                        WT.wcol[e] = (e >> 2) < k ? __ddiv_rn(__ldg(m.pvals + WT.lgcol[e]), qb) : 1.0;
-                    }
-                    // background-only probability of every window (fs:776), first maximum, and their sum in list order:
-                    // the same left-to-right product as a window score, over a table whose every column is q
-                    // (kept in the pair-table space, which is rebuilt after this loop when the greedy ranking pass runs)
-                    double *qtab = reinterpret_cast<double *>(WT.ptab);
-                    for (int e = lane; e < 8 * KP; e += 32) {
-                        const int b = e & 3;
-                        qtab[e] = (e >> 2) < k ? (b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3]) : 1.0;
-                    }
-                    __syncwarp();
-                    double bestg = 0.0;
-                    for (int w0 = 0; w0 < W; w0 += 32) {
-                        const int w = w0 + lane;
-                        if (w < W) {
-                            const double v = exact_window<KP>(row, w, k, qtab);
-                            gbuf[w] = v;
-                            bestg = fmax(bestg, v);
+        int n0 = 0;
+        int width = (phase == MPH_GREEDY) ? 1 : T; // greedy: speculation width adapts as in chain_kernel
+        unsigned round = 0;
+        while (n0 < N) {
+            const int n = n0 + warp;
+            const bool active = n < N && warp < width;
+            int flag = 0, site_n = -1, new_site = -1, W = 0;
+            double new_pw = 0.0;
+            bool has_own = false;
+            uint64_t own = 0, neu = 0;
+            int cn[4] = {0, 0, 0, 0};
+            if (active) {
+                const uint32_t *row = ring.wait(vbase + (uint32_t)n);
+                W = __ldg(a.s.len + n) - k + 1;
+                {
+                    site_n = __ldcg(sites + n);
+                    const double pw_n = __ldcg(pw + n);
+                    has_own = site_n >= 0;
+                    own = has_own ? kmer_shared<KP>(row, site_n) : 0;
+                    const double *g_n = m.bg.g + (size_t)n * m.bg.wstride;
+                    double gsum_n = 0.0, gmax_n = 0.0;
+                    if (!m.data_bg) {
+                        build_tables<KP>(WT, S.total, has_own, own, k, a.wtab, lane);
+                        gsum_n = __ldg(m.bg.gsum + n);
+                        gmax_n = __ldg(m.bg.gmax + n);
+                    } else {
+                        // background of this held-out sequence (fs:896-905): the OTHER sequences that have a site, outside
+                        // those sites (fused over the alphabet), plus every base of the held-out sequence
+                        for (int e = lane; e < 4 * k; e += 32) {
+                            int c = S.total[e];
+                            if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3)) c -= 1;
+                            WT.lgcol[e] = c;
                         }
-                    }
-                    __syncwarp();
-                    {
-                        const uint32_t hi = (uint32_t)__double2hiint(bestg), mh = __reduce_max_sync(FULL, hi);
-                        const uint32_t lo = (hi == mh) ? (uint32_t)__double2loint(bestg) : 0u, ml = __reduce_max_sync(FULL, lo);
-                        gmax_n = __hiloint2double((int)mh, (int)ml);
-                    }
-                    if (phase == MPH_STOCH) { // List.sum visits the background entries first, in window order (fs:748)
+                        __syncwarp();
+                        int F[4], fs = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            int s = 0;
+                            for (int j = lane; j < k; j += 32) s += WT.lgcol[j * 4 + b];
+                            cn[b] = __ldg(m.basecnt + n * 4 + b);
+                            F[b] = bsum[b] - (has_own ? cn[b] : 0) - __reduce_add_sync(FULL, s) + cn[b];
+                            fs += F[b];
+                        }
+                        const double den = __dadd_rn((double)fs, m.alpha_pc);
+                        double q[4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) q[b] = __ddiv_rn(__dadd_rn((double)F[b], m.pc), den); // fs:119
+                        for (int e = lane; e < 8 * KP; e += 32) { // PWM = PPM / pcv (fs:286); dummy column of an odd k = 1.0
+                            const int b = e & 3;
+                            const double qb = b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3];
+                            WT.wcol[e] = (e >> 2) < k ? __ddiv_rn(__ldg(m.pvals + WT.lgcol[e]), qb) : 1.0;
+                        }
+                        // background-only probability of every window (fs:776), first maximum, and their sum in list order:
+                        // the same left-to-right product as a window score, over a table whose every column is q
+                        // (kept in the pair-table space, which is rebuilt after this loop when the greedy ranking pass runs)
+                        double *qtab = reinterpret_cast<double *>(WT.ptab);
+                        for (int e = lane; e < 8 * KP; e += 32) {
+                            const int b = e & 3;
+                            qtab[e] = (e >> 2) < k ? (b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3]) : 1.0;
+                        }
+                        __syncwarp();
+                        double bestg = 0.0;
                         for (int w0 = 0; w0 < W; w0 += 32) {
-                            const double v = (w0 + lane < W) ? gbuf[w0 + lane] : 0.0;
-                            const int lim = min(32, W - w0);
-                            for (int j = 0; j < lim; ++j) gsum_n = __dadd_rn(gsum_n, __shfl_sync(FULL, v, j));
+                            const int w = w0 + lane;
+                            if (w < W) {
+                                const double v = exact_window<KP>(row, w, k, qtab);
+                                gbuf[w] = v;
+                                bestg = fmax(bestg, v);
+                            }
+                        }
+                        __syncwarp();
+                        {
+                            const uint32_t hi = (uint32_t)__double2hiint(bestg), mh = __reduce_max_sync(FULL, hi);
+                            const uint32_t lo = (hi == mh) ? (uint32_t)__double2loint(bestg) : 0u, ml = __reduce_max_sync(FULL, lo);
+                            gmax_n = __hiloint2double((int)mh, (int)ml);
+                        }
+                        if (phase == MPH_STOCH) { // List.sum visits the background entries first, in window order (fs:748)
+                            for (int w0 = 0; w0 < W; w0 += 32) {
+                                const double v = (w0 + lane < W) ? gbuf[w0 + lane] : 0.0;
+                                const int lim = min(32, W - w0);
+                                for (int j = 0; j < lim; ++j) gsum_n = __dadd_rn(gsum_n, __shfl_sync(FULL, v, j));
+                            }
+                        }
+                        g_n = gbuf;
+                    }
+                    double best_l;
+                    int best_w;
+                    int n_cand = -1;
+                    bool slow = false;
+                    if (phase == MPH_GREEDY && m.greedy_fast_ok) { // only the best candidate matters: rank, re-score, compare
+                        if (m.data_bg) fixed_point_tables<KP>(WT, lane);
+                        double pbest;
+                        if (pick_unique_argmax<KP>(WT, row, W, k, lane, pbest, best_w)) {
+                            best_l = log2_ref(pbest);
+                            n_cand = best_l > a.cutoff ? 1 : 0; // fs:735
                         }
                     }
-                    g_n = gbuf;
-                }
-                double best_l;
-                int best_w;
-                int n_cand = -1;
-                if (phase == MPH_GREEDY && m.greedy_fast_ok) { // only the best candidate matters: rank, re-score, compare
-                    if (m.data_bg) fixed_point_tables<KP>(WT, lane);
-                    double pbest;
-                    if (pick_unique_argmax<KP>(WT, row, W, k, lane, pbest, best_w)) {
-                        best_l = log2_ref(pbest);
-                        n_cand = best_l > a.cutoff ? 1 : 0; // fs:735
+                    if (n_cand < 0) {
+                        n_cand = motif_candidates<KP>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w);
+                        slow = true;
                     }
-                }
-                if (n_cand < 0) {
-                    n_cand = motif_candidates<KP>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w);
-                    st_slow += 1;
-                }
-                double new_pw;
-                int new_site;
-                bool take;
-                if (phase == MPH_STOCH) { // fs:828-853: one uniform per n, every n reads the input state
-                    const uint64_t d = (uint64_t)N * (uint64_t)(N - 1) + (uint64_t)n;
-                    double u;
-                    if (a.rng_mode == 0) {
-                        const uint64_t blk = d >> 2;
-                        const uint4 r = philox4x32_10(
-                            make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
-                            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-                        const uint32_t word = (d & 3) == 0 ? r.x : (d & 3) == 1 ? r.y : (d & 3) == 2 ? r.z : r.w;
-                        u = (double)word * (1.0 / 4294967296.0);
-                    } else {
-                        u = ((int64_t)d < a.uniforms_per_chain) ? __ldg(a.uniforms + (size_t)chain * a.uniforms_per_chain + d) : 0.0;
-                    }
-                    const bool ok = motif_roulette(g_n, gsum_n, W, cand_l, cand_w, n_cand, u, lane, new_pw, new_site,
-                                                   m.roulette_scan_ok != 0);
-                    if (!ok) {
-                        if (lane == 0) atomicExch(m.error, 1);
-                        new_pw = pw_n;
-                        new_site = site_n;
-                    }
-                    take = true;
-                } else { // fs:788-822: first maximum by PWMS over background entries ++ candidates
-                    if (n_cand > 0 && best_l > gmax_n) {
-                        new_pw = best_l;
-                        new_site = best_w;
-                    } else {
-                        new_pw = gmax_n;
-                        new_site = -1;
-                    }
-                    take = new_pw > pw_n; // fs:816
-                }
-                if (take) {
-                    if (phase == MPH_GREEDY && new_site != site_n) {
-                        changed = true;
-                        const uint64_t neu = new_site >= 0 ? kmer_shared<KP>(row, new_site) : 0;
-                        if (lane < k) { // in-place sweep: -old k-mer, +new k-mer
-                            if (has_own) S.total[lane * 4 + (int)((own >> (2 * lane)) & 3u)] -= 1;
-                            if (new_site >= 0) S.total[lane * 4 + (int)((neu >> (2 * lane)) & 3u)] += 1;
+                    bool take;
+                    if (phase == MPH_STOCH) { // fs:828-853: one uniform per n, every n reads the input state
+                        const uint64_t d = (uint64_t)N * (uint64_t)(N - 1) + (uint64_t)n;
+                        double u;
+                        if (a.rng_mode == 0) {
+                            const uint64_t blk = d >> 2;
+                            const uint4 r = philox4x32_10(
+                                make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                                make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                            const uint32_t word = (d & 3) == 0 ? r.x : (d & 3) == 1 ? r.y : (d & 3) == 2 ? r.z : r.w;
+                            u = (double)word * (1.0 / 4294967296.0);
+                        } else {
+                            u = ((int64_t)d < a.uniforms_per_chain) ? __ldg(a.uniforms + (size_t)chain * a.uniforms_per_chain + d) : 0.0;
                         }
-                        if (m.data_bg && has_own != (new_site >= 0)) { // the sequence gained or lost its site
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) bsum[b] += (new_site >= 0 ? cn[b] : -cn[b]);
+                        const bool ok = motif_roulette(g_n, gsum_n, W, cand_l, cand_w, n_cand, u, lane, new_pw, new_site,
+                                                       m.roulette_scan_ok != 0);
+                        if (!ok) {
+                            if (lane == 0) atomicExch(m.error, 1);
+                            new_pw = pw_n;
+                            new_site = site_n;
                         }
+                        take = true;
+                    } else { // fs:788-822: first maximum by PWMS over background entries ++ candidates
+                        if (n_cand > 0 && best_l > gmax_n) {
+                            new_pw = best_l;
+                            new_site = best_w;
+                        } else {
+                            new_pw = gmax_n;
+                            new_site = -1;
+                        }
+                        take = new_pw > pw_n; // fs:816
                     }
-                    if (lane == 0) {
+                    const bool moved = take && phase == MPH_GREEDY && new_site != site_n;
+                    if (moved && new_site >= 0) neu = kmer_shared<KP>(row, new_site); // rows are not read after the sync
+                    flag = (take ? 1 : 0) | (moved ? 2 : 0) | (slow ? 4 : 0);
+                }
+            }
+            int32_t *flags = S.flags + (round & 1) * T; // double-buffered: one team sync per round suffices
+            ++round;
+            if (lane == 0) flags[warp] = flag;
+            team_sync<T>();
+            // greedy only: warps after the first mover of the round saw stale counts
+            const unsigned movers = __ballot_sync(FULL, lane < T && (flags[lane < T ? lane : 0] & 2) != 0);
+            const int first_mover = movers ? __ffs(movers) - 1 : T; // (only greedy updates set the mover bit)
+            const int last_commit = min(first_mover, width - 1);
+            changed |= movers != 0;
+            if (active) {
+                if (warp <= last_commit) {
+                    st_updates += 1;
+                    st_windows += (unsigned long long)W;
+                    st_slow += (flag & 4) ? 1 : 0;
+                    if ((flag & 1) && lane == 0) {
                         sites[n] = new_site;
                         pw[n] = new_pw;
                     }
+                } else {
+                    st_spec += 1;
                 }
             }
-            st_updates += 1;
-            st_windows += (unsigned long long)W;
-            __syncwarp();
-            if (lane == 0) ring.fill(v + 1 + 4);
+            const int committed = min(last_commit + 1, N - n0);
+            if (warp == 0) ring.fill_span(vbase + (uint32_t)(n0 + R), n0 + R, committed, lane); // their rows are free
+            n0 += committed;
+            if (phase == MPH_GREEDY) {
+                if (first_mover < T) { // in-place sweep: later n see the new state (fs:795 reads acc): -old k-mer, +new k-mer
+                    if (warp == first_mover) {
+                        if (lane < k) {
+                            if (has_own) S.total[lane * 4 + (int)((own >> (2 * lane)) & 3u)] -= 1;
+                            if (new_site >= 0) S.total[lane * 4 + (int)((neu >> (2 * lane)) & 3u)] += 1;
+                        }
+                        if (m.data_bg && has_own != (new_site >= 0) && lane < 4) { // the sequence gained or lost its site
+                            const int d = lane == 0 ? cn[0] : lane == 1 ? cn[1] : lane == 2 ? cn[2] : cn[3];
+                            bsum[lane] += new_site >= 0 ? d : -d;
+                        }
+                    }
+                    team_sync<T>(); // counts updated before the next round builds its tables
+                    width = max(1, width >> 1);
+                } else {
+                    width = min(T, width * 2);
+                }
+            }
         }
+        vbase += (uint32_t)N;
         st_sweeps += 1;
         bool next = true;
         if (phase == MPH_GREEDY) {
@@ -522,17 +570,20 @@ __global__ void __launch_bounds__(32) motif_kernel(const MotifArgs m) {
             while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
         }
     }
-    if (lane == 0)
-        for (int i = 0; i < 4; ++i) ring.wait(v + (uint32_t)i);
-    __syncwarp();
-    for (int n = lane; n < N; n += 32) hv[n] = __ldcg(pw + n);
+    if (tid == 0) // the ring always has R rows in flight: let them land before the CTA exits
+        for (int i = 0; i < R; ++i) ring.wait(vbase + (uint32_t)i);
+    team_sync<T>();
+    for (int n = tid; n < N; n += THREADS) hv[n] = __ldcg(pw + n);
     if (lane == 0) {
-        double sum = 0.0;
-        for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(pw + n));
-        a.sums[chain] = sum;
         atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
         atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
         atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
+        atomicAdd(a.stats + ST_SPECULATED, st_spec);
+    }
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(pw + n));
+        a.sums[chain] = sum;
         atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
         atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
     }
