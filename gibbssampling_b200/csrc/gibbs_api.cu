@@ -160,6 +160,7 @@ struct gibbs_handle {
     int32_t opt_init_path = 0;         // gibbs_set_option(GIBBS_OPT_INIT_PATH)
     int32_t opt_exact_scans = 0;       // gibbs_set_option(GIBBS_OPT_EXACT_SCANS)
     int32_t opt_stage2_at = 2, opt_stage3_at = 1; // hand-over thresholds in chains per SM (GIBBS_OPT_STAGE2_AT / _STAGE3_AT)
+    int32_t opt_min_width = -1;        // GIBBS_OPT_MIN_WIDTH: -1 = automatic
     int32_t opt_cluster = 8;           // largest cluster the last hand-over stages may use: 0 (none), 4 or 8 (GIBBS_OPT_CLUSTER)
     int32_t cluster_cap[2] = {-1, -1}; // clusters of 4 / 8 CTAs the device holds at once (queried once per shape)
     int32_t cluster_cap_n = 0, cluster_cap_rw = 0, cluster_cap_k = 0;
@@ -415,6 +416,11 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
         ChainArgs b = a;
         b.pause_below = stages[st].pause_below;
         b.from_list = st > 0;
+        {   // chains that reach this stage per SM (at most): with an SM or more per chain, never narrow a speculative round
+            const int per_sm = st == 0 ? (a.n_chains + sms - 1) / sms : (stages[st - 1].pause_below + sms - 1) / sms;
+            b.min_width = h->opt_min_width >= 0 ? h->opt_min_width
+                          : stages[st].cluster ? stages[st].cluster * 16 : (per_sm <= 1 ? stages[st].team : 1);
+        }
         b.pending_in = st > 0 ? h->pending.p + (size_t)(st - 1) * a.n_chains : nullptr;
         b.pending_in_n = st > 0 ? h->ctl.p + st : nullptr;
         b.pending_out = st + 1 < n_stages ? h->pending.p + (size_t)st * a.n_chains : nullptr;
@@ -1292,6 +1298,10 @@ int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value) {
         return GIBBS_OK;
     case GIBBS_OPT_EXACT_SCANS:
         h->opt_exact_scans = value != 0;
+        return GIBBS_OK;
+    case GIBBS_OPT_MIN_WIDTH:
+        if (value < -1 || value > 128) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_MIN_WIDTH takes -1 (automatic) .. 128");
+        h->opt_min_width = value;
         return GIBBS_OK;
     case GIBBS_OPT_CLUSTER:
         if (value != 0 && value != 4 && value != 8) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_CLUSTER takes 0, 4 or 8");

@@ -63,7 +63,7 @@ __host__ __device__ constexpr int cl_delta_off() { return cl_flags_off<C>() + 2 
 template <int C>
 __host__ __device__ constexpr int cl_ctl_off() { return cl_delta_off<C>() + 2 * C * CL_T * 16; }
 template <int C>
-__host__ __device__ constexpr int cl_tables_off() { return (cl_ctl_off<C>() + 16 + 15) / 16 * 16; }
+__host__ __device__ constexpr int cl_tables_off() { return (cl_ctl_off<C>() + 16 + 63) / 64 * 64; }
 template <int C>
 __host__ __device__ inline size_t cluster_smem_bytes(int n, int row_words) {
     return (size_t)cl_tables_off<C>() + (size_t)CL_T * WARP_TABLE_BYTES + (size_t)CL_T * 2 * row_words * 4 + (size_t)n * 4 * sizeof(WEnt);
@@ -71,7 +71,7 @@ __host__ __device__ inline size_t cluster_smem_bytes(int n, int row_words) {
 
 template <int KP, int C>
 static __global__ void __launch_bounds__(32 * CL_T, 1) chain_cluster_kernel(const ChainArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int T = CL_T, THREADS = 32 * CL_T, GW = C * CL_T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t crank = cluster_ctarank();
@@ -95,6 +95,7 @@ static __global__ void __launch_bounds__(32 * CL_T, 1) chain_cluster_kernel(cons
         WT.lgcol = reinterpret_cast<int32_t *>(b + 2048);
         WT.counts = reinterpret_cast<int32_t *>(b + 2560);
     }
+    require_aligned_tables(WT);
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem_raw + cl_tables_off<C>() + T * WARP_TABLE_BYTES) + warp * 2 * row_words;
     WEnt *wtab_s = reinterpret_cast<WEnt *>(smem_raw + cl_tables_off<C>() + T * WARP_TABLE_BYTES + (size_t)T * 2 * row_words * 4);
 
@@ -144,7 +145,7 @@ static __global__ void __launch_bounds__(32 * CL_T, 1) chain_cluster_kernel(cons
         resumed = false;
         bool changed = false;
         int n0 = 0;
-        int width = (phase == PH_GREEDY) ? 1 : GW;
+        int width = (phase == PH_GREEDY) ? max(1, min(GW, a.min_width)) : GW;
         unsigned round = 0;
         int have = -1, have_slot = 0; // sequence whose row sits (or is arriving) in slot have_slot; the other slot is free
         // state of the sequence this warp will probably score next, prefetched into registers
@@ -267,7 +268,7 @@ static __global__ void __launch_bounds__(32 * CL_T, 1) chain_cluster_kernel(cons
                         }
                     }
                     __syncthreads(); // counts updated before the next round builds its tables
-                    width = max(1, width >> 1);
+                    width = max(max(1, min(GW, a.min_width)), width >> 1);
                 } else {
                     width = min(GW, width * 2);
                 }

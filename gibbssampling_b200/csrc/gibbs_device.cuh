@@ -88,6 +88,9 @@ struct ChainArgs {
     int32_t ss_stride;        // entries (int4) per sequence: max_len + 2
     // pause / resume at sweep boundaries: once few chains are still running they are continued by a
     // following launches with wider teams: 4 -> 8 -> 16 warps per chain (see launch_chain_kp)
+    // greedy sweeps: narrowest speculative round. 1 while many chains share an SM (discarded work costs the others issue
+    // slots); the team size once a chain has its SM(s) to itself -- idle warps are free, only latency counts there
+    int32_t min_width;
     int32_t *active;          // chains not finished yet
     int32_t pause_below;      // pause when *active <= pause_below (0 = never)
     int32_t from_list;        // 1 = this launch continues the chains listed in pending_in
@@ -168,6 +171,11 @@ __device__ __forceinline__ void team_sync() {
 // PTX wrappers: mbarrier + 1-D bulk async copy (TMA, SASS UBLKCP)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// the ranking pass ORs nibble offsets into the pair-table address: every per-warp table block must be 64-byte aligned
+__device__ __forceinline__ void require_aligned_tables(const WarpTables &t) {
+    if ((smem_u32(t.ptab) & 63u) != 0) __trap();
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -697,22 +705,42 @@ __device__ __noinline__ void scan_exact_masked(const uint32_t *row, const uint32
 // 4(e+p) of the chunk's aligned bit string, odd windows those at bit 4(e+p)+2, so CH/2 + KP - 1
 // nibble extractions per parity serve CH/2 windows x KP lookups. Returns the chunk maximum of
 // key = (sum << 8) | (255 - round), i.e. the low 8 bits identify the chunk among the lane's chunks.
+// The lookups are issued as ld.shared [reg + imm]: the register is (nibble * 4) | shared address of the warp's pair
+// table -- one shift and one LOP3 per nibble, which is why the per-warp tables are 64-byte aligned -- and the immediate
+// selects the column pair (64 B per table).
+template <int OFF>
+__device__ __forceinline__ int32_t lds_ptab(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int KP, int P>
+struct PairSum { // sum over column pairs P .. KP-1 of ptab[p][nibble e + p]
+    static __device__ __forceinline__ int32_t of(const uint32_t *ad, int e) {
+        return lds_ptab<P * 64>(ad[e + P]) + PairSum<KP, P + 1>::of(ad, e);
+    }
+};
+template <int KP>
+struct PairSum<KP, KP> {
+    static __device__ __forceinline__ int32_t of(const uint32_t *, int) { return 0; }
+};
+
 template <int KP, int CH, bool MASK>
-__device__ __forceinline__ int32_t score_chunk(const uint32_t *a, const uint32_t *b, const int32_t *ptab, int idx, int lim) {
+__device__ __forceinline__ int32_t score_chunk(const uint32_t *a, const uint32_t *b, uint32_t ptab_addr, int idx, int lim) {
     constexpr int NE = CH / 2 + KP - 1;
-    int nibE[NE], nibO[NE];
+    uint32_t adE[NE], adO[NE]; // (nibble << 2) | table address, even / odd windows
 #pragma unroll
     for (int t = 0; t < NE; ++t) {
-        nibE[t] = (a[t >> 3] >> (4 * (t & 7))) & 15;
-        nibO[t] = (b[t >> 3] >> (4 * (t & 7))) & 15;
+        const int j = t & 7;
+        const uint32_t xe = a[t >> 3], xo = b[t >> 3];
+        adE[t] = ((j == 0 ? (xe << 2) : (xe >> (4 * j - 2))) & 0x3cu) | ptab_addr;
+        adO[t] = ((j == 0 ? (xo << 2) : (xo >> (4 * j - 2))) & 0x3cu) | ptab_addr;
     }
     int32_t key[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
         const int e = i >> 1;
-        int32_t v = idx;
-#pragma unroll
-        for (int p = 0; p < KP; ++p) v += ptab[p * 16 + ((i & 1) ? nibO[e + p] : nibE[e + p])];
+        int32_t v = idx + ((i & 1) ? PairSum<KP, 0>::of(adO, e) : PairSum<KP, 0>::of(adE, e));
         if (MASK) v = (i < lim) ? v : INT32_MIN;
         key[i] = v;
     }
@@ -743,6 +771,7 @@ __device__ __forceinline__ void scan_fast(const uint32_t *row, int W, const int3
                                           int32_t &M2, int &S1) {
     using G = ScanGeom<KP, CH>;
     const int n_chunks = (W + CH - 1) / CH;
+    const uint32_t ptab_addr = smem_u32(ptab); // 64-byte aligned (checked once per kernel: tables_aligned)
     M1 = INT32_MIN;
     M2 = INT32_MIN;
     S1 = 0;
@@ -762,8 +791,8 @@ __device__ __forceinline__ void scan_fast(const uint32_t *row, int W, const int3
 #pragma unroll
             for (int i = 0; i < G::NWA; ++i) b[i] = __funnelshift_r(a[i], a[i + 1], 2);
             int32_t cm;
-            if (W >= CH) cm = score_chunk<KP, CH, false>(a, b, ptab, idx, CH); // warp-uniform branch
-            else cm = score_chunk<KP, CH, true>(a, b, ptab, idx, W);
+            if (W >= CH) cm = score_chunk<KP, CH, false>(a, b, ptab_addr, idx, CH); // warp-uniform branch
+            else cm = score_chunk<KP, CH, true>(a, b, ptab_addr, idx, W);
             if (cm > M1) {
                 M2 = max(M2, M1);
                 M1 = cm;

@@ -231,7 +231,7 @@ __host__ __device__ inline int init_smem_bytes(int row_words) {
 // DRIFT = the data-derived background (getPWMOfRandomStarts fs:589-611, getMotifsWithBestPWMSOfPPM fs:644-661)
 template <int KP, bool DRIFT = false>
 static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS) init_kernel(const ChainArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.s.n, k = a.k, row_words = a.s.row_words;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
@@ -244,6 +244,7 @@ static __global__ void __launch_bounds__(INIT_WARPS * 32, GIBBS_INIT_MIN_BLOCKS)
         WT.lgcol = reinterpret_cast<int32_t *>(b + 2048);
         WT.counts = reinterpret_cast<int32_t *>(b + 2560);
     }
+    require_aligned_tables(WT);
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem_raw + 64 + INIT_WARPS * 16 + INIT_WARPS * WARP_TABLE_BYTES) +
                      warp * 2 * row_words;
     if (tid < 16) lut[tid] = hist_lut_entry(tid);
@@ -326,14 +327,14 @@ constexpr int ISM_WARPS = GIBBS_ISM_WARPS;
 
 // per-warp tables sized for the k at hand: wcol 64 KP + ptab 64 KP + lgcol 32 KP + counts 32 KP bytes
 __host__ __device__ constexpr int ism_table_bytes(int kp) { return 192 * kp; }
-__host__ __device__ inline size_t init_smem_rows_bytes(int n, int row_words) { return (size_t)n * row_words * 4; }
+__host__ __device__ inline size_t init_smem_rows_bytes(int n, int row_words) { return ((size_t)n * row_words * 4 + 63) / 64 * 64; }
 __host__ __device__ inline size_t init_smem_total_bytes(int n, int row_words, int kp) {
     return init_smem_rows_bytes(n, row_words) + (size_t)ISM_WARPS * ism_table_bytes(kp);
 }
 
 template <int KP>
 static __global__ void __launch_bounds__(ISM_WARPS * 32, 1) init_smem_kernel(const ChainArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.s.n, k = a.k, row_words = a.s.row_words;
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem_raw);
@@ -345,6 +346,7 @@ static __global__ void __launch_bounds__(ISM_WARPS * 32, 1) init_smem_kernel(con
         WT.lgcol = reinterpret_cast<int32_t *>(b + 128 * KP);
         WT.counts = reinterpret_cast<int32_t *>(b + 160 * KP);
     }
+    require_aligned_tables(WT);
     {   // rows are multiples of 16 B
         const uint4 *src = reinterpret_cast<const uint4 *>(a.s.packed);
         uint4 *dst = reinterpret_cast<uint4 *>(rows);
@@ -403,7 +405,7 @@ static __global__ void __launch_bounds__(ISM_WARPS * 32, 1) init_smem_kernel(con
 // pays nothing for a phase that a grid-wide kernel normally runs (gibbs_api.cu, launch_random_starts).
 template <int KP, int T, bool MASKED = false, bool DRIFT = false, bool INIT_ONLY = false>
 static __global__ void __launch_bounds__(32 * T, (INIT_ONLY ? (T == 1 ? 8 : 4) : T == 1 ? 16 : T == 4 ? GIBBS_T4_MIN_BLOCKS : T == 8 ? GIBBS_T8_MIN_BLOCKS : GIBBS_T16_MIN_BLOCKS)) chain_kernel(const ChainArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -414,6 +416,7 @@ static __global__ void __launch_bounds__(32 * T, (INIT_ONLY ? (T == 1 ? 8 : 4) :
     }
     const TeamSmem S = carve_smem(smem_raw, T);
     const WarpTables WT = warp_tables(S, warp);
+    require_aligned_tables(WT);
 
     const int N = a.s.n, k = a.k;
     int32_t *sites = a.sites + (size_t)chain * N;
@@ -471,7 +474,7 @@ static __global__ void __launch_bounds__(32 * T, (INIT_ONLY ? (T == 1 ? 8 : 4) :
         // greedy sweeps: how many sequences a round attempts. Halved after a round that discarded work
         // (a site moved), doubled after a quiet round: early sweeps, where almost every update moves a
         // site, run nearly sequentially and waste no issue slots; late sweeps run T wide.
-        int width = (phase == PH_GREEDY) ? 1 : T;
+        int width = (phase == PH_GREEDY) ? max(1, min(T, a.min_width)) : T;
         unsigned round = 0;
         while (n0 < N) {
             if ((n0 >> 5) != cur_blk) { // entering a new block: fetch the one after it (not read this round)
@@ -577,7 +580,7 @@ static __global__ void __launch_bounds__(32 * T, (INIT_ONLY ? (T == 1 ? 8 : 4) :
                         }
                     }
                     team_sync<T>(); // counts updated before the next round builds its tables
-                    width = max(1, width >> 1);
+                    width = max(max(1, min(T, a.min_width)), width >> 1);
                 } else {
                     width = min(T, width * 2);
                 }
@@ -661,7 +664,7 @@ struct PrimArgs {
 
 template <int KP>
 static __global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
     if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
@@ -673,10 +676,11 @@ static __global__ void __launch_bounds__(32) loo_counts_kernel(const PrimArgs a)
 // mode 0: every window in float64 (raw product and log2); mode 1: argmax pick
 template <int KP>
 static __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int mode) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
     const WarpTables WT = warp_tables(S, 0);
+    require_aligned_tables(WT);
     RowRing<4> ring;
     ring.init(S, a.s, a.heldout, lane);
     if (lane < 16) S.lut[lane] = hist_lut_entry(lane);
@@ -710,7 +714,7 @@ static __global__ void __launch_bounds__(32) scan_kernel(const PrimArgs a, int m
 // counts of all N sites of one chain (PWM counts reported with the best chain)
 template <int KP>
 static __global__ void __launch_bounds__(32) all_counts_kernel(DeviceSeqs s, const int32_t *sites, int k, int32_t *counts_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
     if (lane < 16) S.lut[lane] = hist_lut_entry(lane);

@@ -311,7 +311,7 @@ constexpr int MOTIF_BSUM_OFFSET = 2144; // 4 ints in the slack of the team's fix
 
 template <int KP, int T>
 __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_BLOCKS : 2)) motif_kernel(const MotifArgs m) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
     const ChainArgs &a = m.c;
@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
     const int chain = blockIdx.x;
     const TeamSmem S = carve_smem(smem_raw, T);
     const WarpTables WT = warp_tables(S, warp);
+    require_aligned_tables(WT);
     int32_t *bsum = reinterpret_cast<int32_t *>(smem_raw + MOTIF_BSUM_OFFSET); // data background: base counts over the sequences that have a site
     const int N = a.s.n, k = a.k;
     int32_t *sites = a.sites + (size_t)chain * N;
@@ -603,7 +604,7 @@ struct RouletteArgs {
 
 template <int KP>
 __global__ void __launch_bounds__(32) roulette_kernel(const RouletteArgs r) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const PrimArgs &a = r.p;
     const int lane = threadIdx.x;
     const TeamSmem S = carve_smem(smem_raw, 1);
