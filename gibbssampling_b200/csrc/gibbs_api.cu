@@ -418,8 +418,8 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
         b.from_list = st > 0;
         {   // chains that reach this stage per SM (at most): with an SM or more per chain, never narrow a speculative round
             const int per_sm = st == 0 ? (a.n_chains + sms - 1) / sms : (stages[st - 1].pause_below + sms - 1) / sms;
-            b.min_width = h->opt_min_width >= 0 ? h->opt_min_width
-                          : stages[st].cluster ? stages[st].cluster * 16 : (per_sm <= 1 ? stages[st].team : 1);
+            b.min_width = stages[st].cluster ? stages[st].cluster * 16 : per_sm <= 1 ? stages[st].team
+                          : h->opt_min_width >= 1 ? h->opt_min_width : 1; // (GIBBS_OPT_MIN_WIDTH: the stages that share SMs)
         }
         b.pending_in = st > 0 ? h->pending.p + (size_t)(st - 1) * a.n_chains : nullptr;
         b.pending_in_n = st > 0 ? h->ctl.p + st : nullptr;

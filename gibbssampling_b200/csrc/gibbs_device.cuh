@@ -628,21 +628,35 @@ __device__ __noinline__ void build_tables_masked(const WarpTables &W, const int3
 // ------------------------------------------------------------------------------------------------
 // exact float64 window score: Array.fold (fun (pos, v) b -> pos + 1, v * pwm.[b, pos]) (0, 1.) (fs:290-293)
 // ------------------------------------------------------------------------------------------------
+template <int OFF>
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+// factor of column J: wcol[J][base J of the k-mer]; the address register is (base * 8) | table address (the table is
+// 32-byte aligned: one shift + one LOP3), the immediate selects the column (32 B each)
+template <int KP, int J>
+struct WindowProduct {
+    static __device__ __forceinline__ double upto(uint32_t lo, uint32_t hi, uint32_t wcol_addr, int k) {
+        const double prev = WindowProduct<KP, J - 1>::upto(lo, hi, wcol_addr, k);
+        constexpr int c = J - 1;                       // column of this factor
+        const uint32_t word = c < 16 ? lo : hi;
+        constexpr int sh = 2 * (c & 15);               // bit position of the base code inside its word
+        const uint32_t off = (sh >= 3 ? (word >> (sh - 3)) : (word << (3 - sh))) & 24u;
+        const double f = lds_f64<c * 32>(off | wcol_addr);
+        return c < k ? __dmul_rn(prev, f) : prev;      // ((1 * w0) * w1) * ... left to right (fs:291-292)
+    }
+};
+template <int KP>
+struct WindowProduct<KP, 0> {
+    static __device__ __forceinline__ double upto(uint32_t, uint32_t, uint32_t, int) { return 1.0; }
+};
+
 template <int KP>
 __device__ __forceinline__ double exact_window(const uint32_t *row, int w, int k, const double *wcol) {
     const uint64_t kmer = kmer_shared<KP>(row, w);
-    const uint64_t k8 = kmer << 3; // base code * 8 = byte offset inside a 32 B column (columns 0..29)
-    const char *base = reinterpret_cast<const char *>(wcol);
-    double f[2 * KP];
-#pragma unroll
-    for (int j = 0; j < 2 * KP; ++j) // dummy column (odd k) holds 1.0
-        f[j] = *reinterpret_cast<const double *>(
-            base + j * 32 + (j <= 29 ? ((uint32_t)(k8 >> (2 * j)) & 24u) : (((uint32_t)(kmer >> (2 * j)) << 3) & 24u)));
-    double p = 1.0;
-#pragma unroll
-    for (int j = 0; j < 2 * KP; ++j)
-        if (j < k) p = __dmul_rn(p, f[j]);
-    return p;
+    return WindowProduct<KP, 2 * KP>::upto((uint32_t)kmer, (uint32_t)(kmer >> 32), smem_u32(wcol), k);
 }
 
 __device__ __forceinline__ bool better(double ohv, int ow, double hv, int w) { return ohv > hv || (ohv == hv && ow < w); }

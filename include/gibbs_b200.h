@@ -136,8 +136,8 @@ int32_t gibbs_synchronize(gibbs_handle *h);
  *   GIBBS_OPT_EXACT_SCANS  1 = no ranking pass anywhere: every window in float64, sequential roulette walk
  *   GIBBS_OPT_STAGE2_AT / GIBBS_OPT_STAGE3_AT  straggler hand-over of the SiteSampler chain kernel: once this many chains
  *                          per SM (or fewer) are still running they continue with 8 / 16 warps per chain (defaults 2, 1)
- *   GIBBS_OPT_MIN_WIDTH    narrowest speculative round of the greedy sweeps (-1 = automatic: 1 while chains share an SM,
- *                          the whole team once a chain has an SM or a cluster to itself)
+ *   GIBBS_OPT_MIN_WIDTH    narrowest speculative round of the greedy sweeps while chains share an SM (default 1; once a
+ *                          chain has an SM or a cluster to itself its rounds always use the whole team)
  *   GIBBS_OPT_CLUSTER      largest thread-block cluster the last stages may give one chain: 8 (default), 4 or 0 (none)
  */
 #define GIBBS_OPT_INIT_PATH 1
