@@ -42,6 +42,9 @@ GIBBS_CHAIN_TU(launch_init_wide);       // gibbs_init_tu.cu: the grid-wide rando
 GIBBS_CHAIN_TU(launch_init_wide_drift);
 GIBBS_CHAIN_TU(launch_init_smem);
 #undef GIBBS_CHAIN_TU
+struct MotifArgs;
+cudaError_t launch_motif_t4(const MotifArgs &m, int grid, int smem, cudaStream_t stream); // gibbs_motif_tu.cu
+cudaError_t launch_motif_t1(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
 // gibbs_cluster_tu.cu: one chain on a cluster of 4 / 8 CTAs (capacity_out != null: only report how many clusters fit)
 cudaError_t launch_chain_cluster4(const ChainArgs &a, int n_clusters, cudaStream_t stream, int *capacity_out);
 cudaError_t launch_chain_cluster8(const ChainArgs &a, int n_clusters, cudaStream_t stream, int *capacity_out);
@@ -594,16 +597,7 @@ int32_t launch_motif_kp(gibbs_handle *h, MotifArgs m) {
     }
     const int team = motif_team(h);
     const int smem = team_smem_bytes(m.c.s.row_words, team);
-    if (team == 4) {
-        int32_t rc = set_smem(motif_kernel<KPV, 4>, smem);
-        if (rc) return rc;
-        motif_kernel<KPV, 4><<<m.c.n_chains, 128, smem, h->stream>>>(m);
-    } else {
-        int32_t rc = set_smem(motif_kernel<KPV, 1>, smem);
-        if (rc) return rc;
-        motif_kernel<KPV, 1><<<m.c.n_chains, 32, smem, h->stream>>>(m);
-    }
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(team == 4 ? launch_motif_t4(m, m.c.n_chains, smem, h->stream) : launch_motif_t1(m, m.c.n_chains, smem, h->stream));
     h->run_team = team;
     return GIBBS_OK;
 }

@@ -18,7 +18,7 @@ namespace gibbs {
 
 
 // one thread per sequence: A,C,G,T counts, and the number of symbols outside A,C,G,T (maskcnt may be null)
-__global__ void basecount_kernel(DeviceSeqs s, int32_t *basecnt, int32_t *maskcnt) {
+static __global__ void basecount_kernel(DeviceSeqs s, int32_t *basecnt, int32_t *maskcnt) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= s.n) return;
     const uint32_t *row = s.packed + (size_t)n * s.row_words;
@@ -39,7 +39,7 @@ __global__ void basecount_kernel(DeviceSeqs s, int32_t *basecnt, int32_t *maskcn
 
 // ss[n][t] = sum_{u < t} P_n[u] with P_n[u] = base counts (A,C,G,T; other symbols skipped) of the first u bases of
 // sequence n, t = 0 .. len + 1: the prefix-of-prefix table of scan_drifting_tables. One thread per sequence (run once).
-__global__ void prefix_kernel(DeviceSeqs s, int stride, int4 *ss) {
+static __global__ void prefix_kernel(DeviceSeqs s, int stride, int4 *ss) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= s.n) return;
     const uint32_t *row = s.packed + (size_t)n * s.row_words;
@@ -60,7 +60,7 @@ __global__ void prefix_kernel(DeviceSeqs s, int stride, int4 *ss) {
     }
 }
 
-__global__ void pvals_kernel(int n, double pc, double den, double *pvals) {
+static __global__ void pvals_kernel(int n, double pc, double den, double *pvals) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n) pvals[c] = __ddiv_rn(__dadd_rn((double)c, pc), den);
 }

@@ -43,7 +43,7 @@ struct MotifArgs {
 };
 
 // one thread per sequence
-__global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1, double q2, double q3, int wstride, double *g,
+static __global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1, double q2, double q3, int wstride, double *g,
                                 double *gsum, double *gmax, int32_t *gmax_i) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= s.n) return;
@@ -77,20 +77,39 @@ template <int KP>
 __device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint32_t *row, int W, int k, double cutoff,
                                                 double raw_gate, double *cand_l, int32_t *cand_w, int lane,
                                                 double &best_l, int &best_w) {
+    // pass 1: every window's float64 product; the windows above a cheap gate just below 2^cutOff are compacted (in
+    // window order) so that the logarithms -- ~150 instructions each, executed by the whole warp whenever one lane
+    // needs one -- are taken over a dense list instead of over all W windows
+    int gated = 0;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+        const int w = w0 + lane;
+        const double s = w < W ? exact_window<KP>(row, w, k, T.wcol) : 0.0;
+        const bool g = w < W && s > raw_gate;
+        const unsigned m = __ballot_sync(FULL, g);
+        if (g) {
+            const int at = gated + __popc(m & ((1u << lane) - 1u));
+            cand_l[at] = s;
+            cand_w[at] = w;
+        }
+        gated += __popc(m);
+    }
+    __syncwarp();
+    // pass 2: the decision itself is made on the log (fs:735); survivors are compacted in place (a block writes only
+    // below what it has read)
     int count = 0;
     double bl = -INFINITY;
     int bw = INT32_MAX;
-    for (int w0 = 0; w0 < W; w0 += 32) {
-        const int w = w0 + lane;
-        bool is_c = false;
+    for (int i0 = 0; i0 < gated; i0 += 32) {
+        const int i = i0 + lane;
         double l = 0.0;
-        if (w < W) {
-            const double s = exact_window<KP>(row, w, k, T.wcol);
-            if (s > raw_gate) { // cheap gate just below 2^cutOff; the decision itself is made on the log
-                l = log2_ref(s);
-                is_c = l > cutoff;
-            }
+        int w = 0;
+        bool is_c = false;
+        if (i < gated) {
+            l = log2_ref(cand_l[i]);
+            w = cand_w[i];
+            is_c = l > cutoff;
         }
+        __syncwarp();
         const unsigned m = __ballot_sync(FULL, is_c);
         if (is_c) {
             const int at = count + __popc(m & ((1u << lane) - 1u));
@@ -113,7 +132,7 @@ __device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint3
 // rouletteWheelSelection (fs:746-754) over [W background entries] ++ [candidates]: exact sequential
 // float64 semantics (sum from 0.0 in list order, weights PWMS/sum, inclusive bounds on both sides).
 // Returns false when the pick ran past the list (the reference throws, fs:753).
-__device__ __noinline__ bool motif_roulette_exact(const double *g, double gsum, int W, const double *cand_l,
+static __device__ __noinline__ bool motif_roulette_exact(const double *g, double gsum, int W, const double *cand_l,
                                                   const int32_t *cand_w, int n_cand, double pick, int lane, double &pwms_out,
                                                   int &site_out) {
     double sum = gsum; // the background entries come first in the list; gsum was accumulated in that order
@@ -305,7 +324,7 @@ __device__ __forceinline__ void fixed_point_tables(const WarpTables &T, int lane
 //     order up to and including the first warp whose accepted update changes the sites (moves, drops or gains a site).
 // Per warp: candidate scratch (and, data-derived background, the background window products) in global memory.
 #ifndef GIBBS_MOTIF_T4_BLOCKS
-#define GIBBS_MOTIF_T4_BLOCKS 5
+#define GIBBS_MOTIF_T4_BLOCKS 7 // 72 registers: all 1024 chains of a C2 step resident at once (5 blocks / 96 registers: 1.4 waves)
 #endif
 constexpr int MOTIF_BSUM_OFFSET = 2144; // 4 ints in the slack of the team's fixed shared memory (TEAM_FIXED_BYTES = 2176)
 
@@ -603,7 +622,7 @@ struct RouletteArgs {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(32) roulette_kernel(const RouletteArgs r) {
+static __global__ void __launch_bounds__(32) roulette_kernel(const RouletteArgs r) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const PrimArgs &a = r.p;
     const int lane = threadIdx.x;

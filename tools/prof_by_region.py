@@ -11,7 +11,7 @@ def regions(path):
             m2 = re.search(r'(\w+)\s*\(', l) or re.search(r'struct\s+(\w+)', l)
             if m2 and not l.startswith('template'): out.append((i, m2.group(1)))
     return out
-reg = {f: regions('gibbssampling_b200/csrc/' + f) for f in ('gibbs_device.cuh', 'gibbs_kernels.cuh', 'gibbs_drift_dev.cuh')}
+reg = {f: regions('gibbssampling_b200/csrc/' + f) for f in ('gibbs_device.cuh', 'gibbs_kernels.cuh', 'gibbs_drift_dev.cuh', 'gibbs_motif.cuh', 'gibbs_cluster.cuh')}
 def region_of(f, l):
     if f not in reg: return f
     name = '?'
