@@ -588,27 +588,34 @@ __device__ __forceinline__ void site_counts(const DeviceSeqs &s, const int32_t *
 template <int KP, bool MASKED, bool WSMEM = false>
 __device__ __forceinline__ void build_tables_impl(const WarpTables &W, const int32_t *counts, bool has_own, uint64_t own, int k,
                                                   const WEnt *__restrict__ wtab, int lane, uint64_t own_mask) {
+    constexpr int NE = (8 * KP + 31) / 32;  // passes over the (column, base) entries: entry e = lane + 32 i
+    constexpr int NP = (16 * KP + 31) / 32; // passes over the pair-table entries
+    int32_t lg[NE];
 #pragma unroll
-    for (int e = lane; e < 8 * KP; e += 32) {
+    for (int i = 0; i < NE; ++i) {
+        const int e = lane + 32 * i;
         const int j = e >> 2, b = e & 3;
         double w = 1.0;
-        int32_t lg = 0;
-        if (j < k) {
+        lg[i] = 0;
+        if (e < 8 * KP && j < k) {
             int c = counts[e];
             if (has_own && (int)((own >> (2 * j)) & 3u) == b && !(MASKED && ((own_mask >> (2 * j)) & 1u))) c -= 1; // (a masked own base was never counted)
             const int4 *ent = reinterpret_cast<const int4 *>(wtab + (size_t)c * 4 + b);
             const int4 raw = WSMEM ? *ent : __ldg(ent);
             w = __hiloint2double(raw.y, raw.x);
-            lg = raw.z;
+            lg[i] = raw.z;
         }
-        W.wcol[e] = w;
-        W.lgcol[e] = lg;
+        if (e < 8 * KP) W.wcol[e] = w;
     }
-    __syncwarp();
+    // pair table straight from the registers: entry (p, nib) = lg(column 2p, base nib & 3) + lg(column 2p + 1, base nib >> 2).
+    // Pass t, lane l holds p = 2 t + (l >> 4), nib = l & 15; both addends sit in register lg[t >> 1] of the lanes
+    // 16 (t & 1) + 8 (l >> 4) + {nib & 3, 4 + (nib >> 2)}.
+    const int s0 = 8 * (lane >> 4) + (lane & 3), s1 = 8 * (lane >> 4) + 4 + ((lane >> 2) & 3);
 #pragma unroll
-    for (int idx = lane; idx < 16 * KP; idx += 32) {
-        const int p = idx >> 4, nib = idx & 15;
-        W.ptab[idx] = W.lgcol[(2 * p) * 4 + (nib & 3)] + W.lgcol[(2 * p + 1) * 4 + (nib >> 2)];
+    for (int t = 0; t < NP; ++t) {
+        const int32_t v = __shfl_sync(FULL, lg[t >> 1], s0 + 16 * (t & 1)) + __shfl_sync(FULL, lg[t >> 1], s1 + 16 * (t & 1));
+        const int idx = lane + 32 * t;
+        if (idx < 16 * KP) W.ptab[idx] = v;
     }
     __syncwarp();
 }
