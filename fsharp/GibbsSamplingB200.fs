@@ -28,7 +28,7 @@ module Native =
         val mutable maxSweeps     : int
         val mutable phaseMask     : int
         val mutable background    : int   // 0 = fixed pcv (WithBPV), 1 = data-derived (fs:697)
-        val mutable reserved      : int
+        val mutable motif_amount  : int
 
     [<Struct; StructLayout(LayoutKind.Sequential)>]
     type GibbsRunStats =
@@ -41,7 +41,7 @@ module Native =
         val mutable kernelLaunches: int
         val mutable fastPath      : int
         val mutable teamWarps     : int
-        val mutable reserved      : int
+        val mutable motif_amount  : int
         val mutable kernelMs      : float
 
     [<Literal>]

@@ -1,9 +1,9 @@
 """MotifSampler -- the reference module's functions (fs:709-1038) behind the CUDA library.
 
-`MotifIndex` = {PWMS: float; Positions: int list} (fs:712-716). Only motifAmount = 1 is in scope
-(SURVEY.md section 2, row 8): combinations of m >= 2 windows are an exponential enumeration, not
-data-parallel window scoring. Both the fixed-background (`...ByPCV` / `...WithPCV`) family and the
-data-derived-background family (fs:885-1038) run on the GPU.
+`MotifIndex` = {PWMS: float; Positions: int list} (fs:712-716). motifAmount = 1 (one site per sequence or none) and
+motifAmount = 2 (up to two non-overlapping sites, fs:727-742 -- the reference script's second live call, fsx:407) are
+built; three and more sites per sequence raise GibbsUnsupportedError. Both the fixed-background (`...ByPCV` /
+`...WithPCV`) family and the data-derived-background family (fs:885-1038) run on the GPU.
 """
 from __future__ import annotations
 
@@ -29,35 +29,43 @@ def createMotifIndex(pwms: float, pos) -> MotifIndex:
     return MotifIndex(float(pwms), tuple(int(p) for p in pos))
 
 
-def _check_m(motifAmount: int) -> None:
-    if int(motifAmount) != 1:
+def _check_m(motifAmount: int) -> int:
+    m = int(motifAmount)
+    if m not in (1, 2):
         raise _abi.GibbsUnsupportedError(
             _abi.GIBBS_ERR_UNSUPPORTED,
-            f"motifAmount = {motifAmount}: only one site per sequence is built; combinations of m >= 2 windows "
-            "(calculatePWMsForSegmentCombinations, fs:727-742) are an exponential enumeration, out of scope")
+            f"motifAmount = {motifAmount}: one and two sites per sequence are built "
+            "(calculatePWMsForSegmentCombinations, fs:727-742); three and more are not")
+    return m
 
 
 def _to_motif_array(scores: np.ndarray, sites: np.ndarray) -> list:
-    return [MotifIndex(float(s), (int(p),) if p >= 0 else ()) for s, p in zip(scores, sites)]
+    """scores [n]; sites [n] (one position, -1 = none) or [n, m] Positions lists (newest first, -1 = absent)."""
+    sites = np.asarray(sites)
+    if sites.ndim == 1:
+        return [MotifIndex(float(s), (int(p),) if p >= 0 else ()) for s, p in zip(scores, sites)]
+    return [MotifIndex(float(s), tuple(int(p) for p in row if p >= 0)) for s, row in zip(scores, sites)]
 
 
-def _split_motif_state(motifMem) -> tuple[np.ndarray, np.ndarray]:
+def _split_motif_state(motifMem, m: int = 1) -> tuple[np.ndarray, np.ndarray]:
+    """(PWMS [n], Positions [n, m] newest first / -1 = absent)"""
     if motifMem is None:
         raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "motifMem is null (ArgumentNullException)")
-    scores = np.array([float(m.PWMS) for m in motifMem], dtype=np.float64)
-    sites = np.empty(len(motifMem), dtype=np.int32)
-    for i, m in enumerate(motifMem):
-        if len(m.Positions) > 1:
-            _check_m(len(m.Positions))
-        sites[i] = m.Positions[0] if m.Positions else -1
-    return scores, sites
+    scores = np.array([float(x.PWMS) for x in motifMem], dtype=np.float64)
+    pos = np.full((len(motifMem), m), -1, dtype=np.int32)
+    for i, x in enumerate(motifMem):
+        if len(x.Positions) > m:
+            raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, f"a MotifIndex holds {len(x.Positions)} positions, motifAmount = {m}")
+        pos[i, :len(x.Positions)] = x.Positions
+    return scores, pos
 
 
 def _run(phase_mask: int, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, *, start=None,
          n_chains: int = 1, seed: int = 0, chain: int = 0, uniforms=None, engine: Optional[GibbsEngine] = None,
-         max_sweeps: int = 0, ppM=None, best_of: Optional[int] = None):
-    """pcv given -> the PCV family (fixed background); pcv None -> the data-derived family (fs:885-1038)."""
-    _check_m(motifAmount)
+         max_sweeps: int = 0, ppM=None, best_of: Optional[int] = None) -> list:
+    """pcv given -> the PCV family (fixed background); pcv None -> the data-derived family (fs:885-1038).
+    Returns the MotifIndex[] of chain 0, or of the restart loop's winner when best_of (numberOfRepetitions) is given."""
+    m = _check_m(motifAmount)
     if pcv is None:
         _bg_of(alphabet, ProbabilityCompositeVector.ofACGT(1, 1, 1, 1))   # only checks A,C,G,T are in the alphabet
         bg, background = [0.25] * 4, _abi.GIBBS_BG_DATA
@@ -66,18 +74,22 @@ def _run(phase_mask: int, motifAmount, motifLength, pseudoCount, cutOff, alphabe
     eng, own = _engine_for(sources, engine)
     try:
         params = make_params(motifLength, pseudoCount, len(alphabet), bg, cutoff=cutOff, background=background,
-                             sampler=_abi.GIBBS_MOTIF_SAMPLER, phase_mask=phase_mask, max_sweeps=max_sweeps)
+                             sampler=_abi.GIBBS_MOTIF_SAMPLER, phase_mask=phase_mask, max_sweeps=max_sweeps, motif_amount=m)
         if start is not None:
-            scores, sites = _split_motif_state(start)
-            eng.set_start_state(np.tile(sites, (n_chains, 1)), np.tile(scores, (n_chains, 1)))
+            scores, pos = _split_motif_state(start, m)
+            eng.set_start_motif_state(np.tile(pos, (n_chains, 1, 1)), np.tile(scores, (n_chains, 1)))
         u = None if uniforms is None else np.asarray(uniforms, dtype=np.float64).reshape(n_chains, -1)
         if ppM is not None:
             eng.set_start_ppm(ppM, motifLength)
         try:
-            if best_of is None:
-                return eng.run(params, n_chains, chain_id_base=chain, seed=seed, uniforms=u, want_counts=False)
             eng.run_device(params, n_chains, chain_id_base=chain, seed=seed, uniforms=u)
-            return eng.fetch_best(best_of)   # the restart loop (fs:857-881) runs on the GPU; only the winner comes back
+            if best_of is None:
+                res = eng.fetch(want_counts=False)
+                return _to_motif_array(res.scores[0], res.sites[0] if m == 1 else eng.fetch_positions(m)[0])
+            best = eng.fetch_best(best_of)   # the restart loop (fs:857-881) runs on the GPU; only the winner comes back
+            if m == 1 or best.restart < 0:
+                return _to_motif_array(best.scores, best.sites)
+            return _to_motif_array(best.scores, eng.fetch_best_positions(m))
         finally:
             if ppM is not None:
                 eng.set_start_ppm(None)
@@ -104,24 +116,21 @@ def rouletteWheelSelectionOfSites(motifLength, pseudoCount, cutOff, alphabet, so
 def findBestMotifPositionsWithStartPositionsByPCV(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv,
                                                   motifMem, **kw) -> list:
     """fs:828-853: the synchronous stochastic sweep (one roulette pick per sequence)."""
-    res = _run(_abi.PHASE_STOCHASTIC, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv,
-               start=motifMem, **kw)
-    return _to_motif_array(res.scores[0], res.sites[0])
+    return _run(_abi.PHASE_STOCHASTIC, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv,
+                start=motifMem, **kw)
 
 
 def findBestMotifPositionsWithStartPositionByPCV(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv,
                                                  motifMem, **kw) -> list:
     """fs:788-822: greedy in-place sweeps until the positions stop changing."""
-    res = _run(_abi.PHASE_MOTIF_GREEDY, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv,
-               start=motifMem, **kw)
-    return _to_motif_array(res.scores[0], res.sites[0])
+    return _run(_abi.PHASE_MOTIF_GREEDY, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv,
+                start=motifMem, **kw)
 
 
 def doMotifSamplingWithPCV(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, **kw) -> list:
     """One restart of fs:876-879: random starts |> stochastic sweep |> greedy sweeps (the reference inlines
     this pipeline in findBestInormationContentContainingMotifsWithPCV; there is no separate `do` function)."""
-    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, **kw)
-    return _to_motif_array(res.scores[0], res.sites[0])
+    return _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, **kw)
 
 
 def replay_motif_restart_loop(numberOfRepetitions: int, scores: np.ndarray, sites: np.ndarray, sums: np.ndarray) -> list:
@@ -163,52 +172,46 @@ def findBestInormationContentContainingMotifsWithPCV(numberOfRepetitions, motifA
                                                      max_sweeps: int = 0) -> list:
     """fs:856-881: restarts run as parallel chains, the promote-or-restart loop is replayed over their results."""
     n_restarts = max(int(numberOfRepetitions) + 1, 1)
-    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, n_chains=n_restarts,
+    return _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, pcv, n_chains=n_restarts,
                seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps,
                best_of=int(numberOfRepetitions))
-    return _to_motif_array(res.scores, res.sites)
 
 
 # ---- data-derived background (fs:885-1038): one background per held-out sequence (fs:896-905) -------------
 def findBestMotifIndicesByWithStartPositions(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, motifMem,
                                              **kw) -> list:
     """fs:935-970: the synchronous stochastic sweep."""
-    res = _run(_abi.PHASE_STOCHASTIC, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None,
-               start=motifMem, **kw)
-    return _to_motif_array(res.scores[0], res.sites[0])
+    return _run(_abi.PHASE_STOCHASTIC, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None,
+                start=motifMem, **kw)
 
 
 def findBestMotifIndicesWithStartPositions(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, motifMem,
                                            **kw) -> list:
     """fs:885-929: greedy in-place sweeps."""
-    res = _run(_abi.PHASE_MOTIF_GREEDY, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None,
-               start=motifMem, **kw)
-    return _to_motif_array(res.scores[0], res.sites[0])
+    return _run(_abi.PHASE_MOTIF_GREEDY, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None,
+                start=motifMem, **kw)
 
 
 def doMotifSampling(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, **kw) -> list:
     """fs:1034-1038."""
-    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, **kw)
-    return _to_motif_array(res.scores[0], res.sites[0])
+    return _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, **kw)
 
 
 def getMotifsWithBestInformationContents(numberOfRepetitions, motifAmount, motifLength, pseudoCount, cutOff, alphabet,
                                          sources, *, seed: int = 0, chain: int = 0, uniforms=None,
                                          engine: Optional[GibbsEngine] = None, max_sweeps: int = 0) -> list:
-    """fs:973-998 -- the reference script's second live call (fsx:407; there with motifAmount = 2, out of scope)."""
+    """fs:973-998 -- the reference script's second live call (fsx:407: reps 1, motifAmount 2, k 6, pc 1e-4, cutOff 1.0)."""
     n_restarts = max(int(numberOfRepetitions) + 1, 1)
-    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
+    return _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
                seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps,
                best_of=int(numberOfRepetitions))
-    return _to_motif_array(res.scores, res.sites)
 
 
 def doMotifSamplingWithPPM(motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, **kw) -> list:
     """fs:1028-1032: SiteSampler.getMotifsWithBestPWMSOfPPM as the start, then the data-derived sweeps."""
     if ppM is None:
         raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "ppM is null (ArgumentNullException)")
-    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, ppM=ppM, **kw)
-    return _to_motif_array(res.scores[0], res.sites[0])
+    return _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, ppM=ppM, **kw)
 
 
 def getBestPWMSsOfPPM(numberOfRepetitions, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, ppM, *,
@@ -218,7 +221,6 @@ def getBestPWMSsOfPPM(numberOfRepetitions, motifAmount, motifLength, pseudoCount
     if ppM is None:
         raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "ppM is null (ArgumentNullException)")
     n_restarts = max(int(numberOfRepetitions) + 1, 1)
-    res = _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
+    return _run(0, motifAmount, motifLength, pseudoCount, cutOff, alphabet, sources, None, n_chains=n_restarts,
                seed=seed, chain=chain, uniforms=uniforms, engine=engine, max_sweeps=max_sweeps, ppM=ppM,
                best_of=int(numberOfRepetitions))
-    return _to_motif_array(res.scores, res.sites)

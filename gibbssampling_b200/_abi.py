@@ -36,7 +36,8 @@ EXPORTS = [
     "gibbs_loo_counts", "gibbs_window_scores", "gibbs_pick_argmax", "gibbs_pick_roulette",
     "gibbs_set_start_ppm", "gibbs_set_start_state", "gibbs_run_device", "gibbs_fetch", "gibbs_run", "gibbs_device_results",
     "gibbs_host_alloc", "gibbs_host_free", "gibbs_measure_smem_bandwidth",
-    "gibbs_set_option", "gibbs_fetch_best",
+    "gibbs_set_option", "gibbs_fetch_best", "gibbs_fetch_positions", "gibbs_fetch_best_positions",
+    "gibbs_set_start_motif_state",
     "gibbs_multi_create", "gibbs_multi_destroy", "gibbs_multi_num_devices", "gibbs_multi_handle",
     "gibbs_multi_run_device", "gibbs_multi_fetch_best",
 ]
@@ -99,7 +100,7 @@ class Params(C.Structure):
         ("max_sweeps", C.c_int32),
         ("phase_mask", C.c_int32),
         ("background", C.c_int32),
-        ("reserved", C.c_int32),
+        ("motif_amount", C.c_int32),
     ]
 
 
@@ -164,6 +165,9 @@ def load() -> C.CDLL:
     lib.gibbs_measure_smem_bandwidth.argtypes = [i32, i32, P(f64), P(f64)]
     lib.gibbs_set_option.argtypes = [vp, i32, i32]
     lib.gibbs_fetch_best.argtypes = [vp, i32, P(i32), P(f64), P(i32), P(f64), P(i32), P(i32), P(RunStats)]
+    lib.gibbs_fetch_positions.argtypes = [vp, i32, P(i32)]
+    lib.gibbs_fetch_best_positions.argtypes = [vp, i32, P(i32)]
+    lib.gibbs_set_start_motif_state.argtypes = [vp, i32, i32, P(i32), P(f64)]
     lib.gibbs_multi_create.argtypes = [P(C.c_uint8), P(i64), i32, P(i32), i32, P(vp)]
     lib.gibbs_multi_destroy.argtypes = [vp]
     lib.gibbs_multi_num_devices.argtypes = [vp]

@@ -3,6 +3,7 @@
 The library is several translation units compiled in parallel and linked by nvcc:
   gibbs_api.cu        the extern "C" boundary, setup / primitive / init / MotifSampler kernels
   gibbs_motif_tu.cu   the MotifSampler kernel, one team size per unit
+  gibbs_motif2_tu.cu  the MotifSampler with motifAmount = 2
   gibbs_cluster_tu.cu one chain on a thread-block cluster of 4 / 8 CTAs (the last hand-over stages), one size per unit
   gibbs_init_tu.cu    the grid-wide random-start kernels, one kind per unit (same reason as the chain units)
   gibbs_chain_tu.cu   compiled once per GROUP of chain_kernel instantiations (warps per chain x masked symbols x
@@ -25,8 +26,9 @@ CHAIN_SOURCE = os.path.join(CSRC, "gibbs_chain_tu.cu")
 INIT_SOURCE = os.path.join(CSRC, "gibbs_init_tu.cu")
 CLUSTER_SOURCE = os.path.join(CSRC, "gibbs_cluster_tu.cu")
 MOTIF_SOURCE = os.path.join(CSRC, "gibbs_motif_tu.cu")
-DEPS = [API_SOURCE, CHAIN_SOURCE, INIT_SOURCE, CLUSTER_SOURCE, MOTIF_SOURCE] + [os.path.join(CSRC, f) for f in (
-    "gibbs_device.cuh", "gibbs_kernels.cuh", "gibbs_motif.cuh", "gibbs_drift.cuh", "gibbs_drift_dev.cuh", "gibbs_cluster.cuh",
+MOTIF2_SOURCE = os.path.join(CSRC, "gibbs_motif2_tu.cu")
+DEPS = [API_SOURCE, CHAIN_SOURCE, INIT_SOURCE, CLUSTER_SOURCE, MOTIF_SOURCE, MOTIF2_SOURCE] + [os.path.join(CSRC, f) for f in (
+    "gibbs_device.cuh", "gibbs_kernels.cuh", "gibbs_motif.cuh", "gibbs_drift.cuh", "gibbs_drift_dev.cuh", "gibbs_cluster.cuh", "gibbs_motif2.cuh",
 )] + [os.path.join(ROOT, "include", "gibbs_b200.h"), os.path.abspath(__file__)]
 
 # (entry point declared in gibbs_api.cu, warps per chain, masked symbols, drifting background)
@@ -92,6 +94,8 @@ def _jobs(nvcc: str, verbose: bool) -> list[tuple[str, list[str]]]:
     for t in (4, 1):
         obj = os.path.join(OBJ_DIR, f"launch_motif_t{t}.o")
         jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [f"-DGIBBS_MOTIF_TU_T={t}", "-c", "-o", obj, MOTIF_SOURCE]))
+    obj = os.path.join(OBJ_DIR, "launch_motif2.o")
+    jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + ["-c", "-o", obj, MOTIF2_SOURCE]))
     for c in (4, 8):
         obj = os.path.join(OBJ_DIR, f"launch_chain_cluster{c}.o")
         jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [f"-DGIBBS_CLUSTER_C={c}", "-c", "-o", obj, CLUSTER_SOURCE]))

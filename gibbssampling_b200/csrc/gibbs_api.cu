@@ -7,6 +7,7 @@
 #include "../../include/gibbs_b200.h"
 #include "gibbs_kernels.cuh"
 #include "gibbs_motif.cuh"
+#include "gibbs_motif2.cuh"
 #include "gibbs_drift.cuh"
 
 #include <cmath>
@@ -42,9 +43,10 @@ GIBBS_CHAIN_TU(launch_init_wide);       // gibbs_init_tu.cu: the grid-wide rando
 GIBBS_CHAIN_TU(launch_init_wide_drift);
 GIBBS_CHAIN_TU(launch_init_smem);
 #undef GIBBS_CHAIN_TU
-struct MotifArgs;
 cudaError_t launch_motif_t4(const MotifArgs &m, int grid, int smem, cudaStream_t stream); // gibbs_motif_tu.cu
 cudaError_t launch_motif_t1(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
+cudaError_t launch_motif2(const Motif2Args &q, int grid, int smem, cudaStream_t stream); // gibbs_motif2_tu.cu
+cudaError_t launch_motif2_seed(const int32_t *sites, long long cells, int32_t *pos2, cudaStream_t stream);
 // gibbs_cluster_tu.cu: one chain on a cluster of 4 / 8 CTAs (capacity_out != null: only report how many clusters fit)
 cudaError_t launch_chain_cluster4(const ChainArgs &a, int n_clusters, cudaStream_t stream, int *capacity_out);
 cudaError_t launch_chain_cluster8(const ChainArgs &a, int n_clusters, cudaStream_t stream, int *capacity_out);
@@ -168,6 +170,12 @@ struct gibbs_handle {
     int32_t cluster_cap[2] = {-1, -1}; // clusters of 4 / 8 CTAs the device holds at once (queried once per shape)
     int32_t cluster_cap_n = 0, cluster_cap_rw = 0, cluster_cap_k = 0;
     int32_t run_stages = 0;            // launches of the chain kernel family in the last run
+    int32_t wt_span = 0, drift_span = 0; // counts the W / PPM value tables cover: n (one site per sequence) or 2 n
+    DevBuf<int32_t> pos2;              // motifAmount = 2: Positions [chains][n][2], newest first
+    DevBuf<double> sc2;                // motifAmount = 2: window products of the current held-out sequence, per chain
+    int32_t run_m = 1;                 // motifAmount of the last run
+    int32_t start_m = 0;               // gibbs_set_start_motif_state staged Positions lists for this many sites (0 = none)
+    bool best_valid = false;           // win_sites holds the winner of a gibbs_fetch_best on the last run
     int32_t run_init_path = 0;         // where the random starts of the last run ran (GIBBS_INIT_*)
     DevBuf<int32_t> win_sites;         // gibbs_fetch_best: the winner's rows + [n] restart index
     DevBuf<double> win_scores;         // [n] scores + [n] sum
@@ -204,17 +212,19 @@ int32_t check_params(const gibbs_handle *h, const gibbs_params *p) {
 }
 
 // (re)build W(c, b) for c = 0..n-1 when the parameters it depends on changed
-int32_t ensure_wtab(gibbs_handle *h, const gibbs_params *p, int *launches) {
-    bool same = h->wtab_valid && h->wt_pc == p->pseudocount && h->wt_alen == p->alphabet_size;
+// span = how many counts the table covers: n, or 2 n when a sequence may contribute two sites (motifAmount = 2)
+int32_t ensure_wtab(gibbs_handle *h, const gibbs_params *p, int *launches, int span_mult = 1) {
+    const int span = h->n * span_mult;
+    bool same = h->wtab_valid && h->wt_pc == p->pseudocount && h->wt_alen == p->alphabet_size && h->wt_span >= span;
     for (int b = 0; b < 4 && same; ++b) same = h->wt_bg[b] == p->bg[b];
     if (same) return GIBBS_OK;
-    CUDA_TRY(h->wtab.reserve((size_t)h->n * 4));
+    CUDA_TRY(h->wtab.reserve((size_t)span * 4));
     const int init[3] = {INT32_MAX, INT32_MIN, 0};
     CUDA_TRY(cudaMemcpyAsync(h->flags.p + 1, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
     // normalizePPM: sum = float sourceCount + float alphabet.Length * pseudoCount (fs:257)
     const double den = (double)(h->n - 1) + ((double)p->alphabet_size * p->pseudocount);
-    const int total = h->n * 4;
-    wtab_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(h->n, p->pseudocount, den, p->bg[0], p->bg[1], p->bg[2],
+    const int total = span * 4;
+    wtab_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(span, p->pseudocount, den, p->bg[0], p->bg[1], p->bg[2],
                                                            p->bg[3], h->wtab.p, h->flags.p + 1);
     CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;
@@ -226,6 +236,7 @@ int32_t ensure_wtab(gibbs_handle *h, const gibbs_params *p, int *launches) {
     h->wt_abnormal = out[2];
     h->wt_pc = p->pseudocount;
     h->wt_alen = p->alphabet_size;
+    h->wt_span = span;
     memcpy(h->wt_bg, p->bg, sizeof h->wt_bg);
     h->wtab_valid = true;
     return GIBBS_OK;
@@ -327,6 +338,15 @@ int32_t launch_random_starts(gibbs_handle *h, ChainArgs &a, bool drift) {
         h->run_extra_launches += 1;
     }
     return GIBBS_OK;
+}
+
+int32_t launch_random_starts_any(gibbs_handle *h, ChainArgs &a, bool drift) {
+    switch ((a.k + 1) / 2) {
+#define X(KPV) case KPV: return launch_random_starts<KPV>(h, a, drift);
+        KP_CASES(X)
+#undef X
+    default: return fail(GIBBS_ERR_ARG, "unsupported k");
+    }
 }
 
 template <int KPV>
@@ -529,12 +549,13 @@ int32_t ensure_bgtab(gibbs_handle *h, const gibbs_params *p, int *launches) {
     return GIBBS_OK;
 }
 
-int32_t ensure_drift(gibbs_handle *h, const gibbs_params *p, int *launches) {
-    if (h->drift_valid && h->drift_pc == p->pseudocount && h->drift_alen == p->alphabet_size) return GIBBS_OK;
-    CUDA_TRY(h->pvals.reserve((size_t)h->n));
+int32_t ensure_drift(gibbs_handle *h, const gibbs_params *p, int *launches, int span_mult = 1) {
+    const int span = h->n * span_mult;
+    if (h->drift_valid && h->drift_pc == p->pseudocount && h->drift_alen == p->alphabet_size && h->drift_span >= span) return GIBBS_OK;
+    CUDA_TRY(h->pvals.reserve((size_t)span));
     CUDA_TRY(h->basecnt.reserve((size_t)h->n * 4));
     const double den = (double)(h->n - 1) + ((double)p->alphabet_size * p->pseudocount); // fs:257
-    pvals_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->n, p->pseudocount, den, h->pvals.p);
+    pvals_kernel<<<(span + 255) / 256, 256, 0, h->stream>>>(span, p->pseudocount, den, h->pvals.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(h->maskcnt.reserve((size_t)h->n));
     basecount_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(dev_seqs(h), h->basecnt.p, h->maskcnt.p);
@@ -566,6 +587,7 @@ int32_t ensure_drift(gibbs_handle *h, const gibbs_params *p, int *launches) {
     }
     h->drift_pc = p->pseudocount;
     h->drift_alen = p->alphabet_size;
+    h->drift_span = span;
     h->drift_valid = true;
     return GIBBS_OK;
 }
@@ -791,6 +813,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     h->cand_l.release(); h->cand_w.release(); h->err_flag.release();
     h->pvals.release(); h->basecnt.release(); h->maskcnt.release(); h->ss.release(); h->gbuf.release(); h->start_ppm.release();
     h->ctl.release(); h->resume.release(); h->pending.release();
+    h->win_sites.release(); h->win_scores.release(); h->pos2.release(); h->sc2.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -958,6 +981,11 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     if (p->sampler != GIBBS_SITE_SAMPLER && p->sampler != GIBBS_MOTIF_SAMPLER) return fail(GIBBS_ERR_ARG, "unknown sampler %d", p->sampler);
     if (rng_mode != GIBBS_RNG_PHILOX && rng_mode != GIBBS_RNG_INJECTED) return fail(GIBBS_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (rng_mode == GIBBS_RNG_INJECTED && (!uniforms || uniforms_per_chain < 0)) return fail(GIBBS_ERR_ARG, "injected uniforms missing");
+    const int m_amount = p->motif_amount <= 1 ? 1 : p->motif_amount;
+    if (p->sampler == GIBBS_SITE_SAMPLER && m_amount != 1) return fail(GIBBS_ERR_ARG, "motif_amount belongs to the MotifSampler");
+    if (m_amount > 2)
+        return fail(GIBBS_ERR_UNSUPPORTED, "motifAmount = %d: combinations of one and two windows are built (fs:727-742); three and "
+                                           "more sites per sequence are not", m_amount);
     if (h->n_masked > 0 && p->sampler != GIBBS_SITE_SAMPLER)
         return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler only (the MotifSampler needs "
                                            "ACGT-only sequences)");
@@ -965,8 +993,8 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     if (rc) return rc;
     h->run_done = false;
     int launches = 0;
-    if (p->background == GIBBS_BG_FIXED) rc = ensure_wtab(h, p, &launches);
-    else rc = ensure_drift(h, p, &launches);
+    if (p->background == GIBBS_BG_FIXED) rc = ensure_wtab(h, p, &launches, m_amount);
+    else rc = ensure_drift(h, p, &launches, m_amount);
     if (rc) return rc;
     const size_t cells = (size_t)n_chains * h->n;
     CUDA_TRY(h->sites.reserve(cells));
@@ -994,7 +1022,10 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         a.phase_mask = p->phase_mask ? p->phase_mask : motif_phases;
         if (a.phase_mask & ~motif_phases) return fail(GIBBS_ERR_ARG, "phase_mask 0x%x has phases that are not MotifSampler phases", a.phase_mask);
     }
+    const int start_m = h->start_m;
+    h->start_m = 0;
     if (!(a.phase_mask & GIBBS_PHASE_INIT)) {
+        if (start_m > m_amount) return fail(GIBBS_ERR_ARG, "the start state holds Positions lists of %d sites, motif_amount = %d", start_m, m_amount);
         if (h->start_chains != n_chains)
             return fail(GIBBS_ERR_ARG, "phase_mask without GIBBS_PHASE_INIT needs gibbs_set_start_state for %d chains", n_chains);
         if (h->start_max_excess > -p->k) // getSegment -> Array.take on a start position that leaves its sequence (fs:149-153)
@@ -1086,9 +1117,29 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             m.roulette_scan_ok = 0;
         }
         m.c.drift_fast_ok = m.data_bg ? m.greedy_fast_ok : 0; // what the grid-wide random starts (init_kernel<.., DRIFT>) read
+        if (m_amount == 2) { // up to two sites per sequence: Positions lists beside the one-site state
+            CUDA_TRY(h->pos2.reserve(cells * 2));
+            CUDA_TRY(h->sc2.reserve((size_t)n_chains * h->bg_wstride));
+            if (!(a.phase_mask & GIBBS_PHASE_INIT) && start_m < 2) // one-site start state: Positions = [site]
+                CUDA_TRY(launch_motif2_seed(h->sites.p, (long long)cells, h->pos2.p, h->stream));
+        }
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        rc = launch_motif(h, m);
-        if (rc) return rc;
+        if (m_amount == 2) {
+            h->run_extra_launches = 0;
+            const int before = m.c.phase_mask;
+            rc = launch_random_starts_any(h, m.c, m.data_bg != 0);
+            if (rc) return rc;
+            m.init_done = (before & GIBBS_PHASE_INIT) && !(m.c.phase_mask & GIBBS_PHASE_INIT);
+            Motif2Args q{};
+            q.m = m;
+            q.pos2 = h->pos2.p;
+            q.sc = h->sc2.p;
+            CUDA_TRY(launch_motif2(q, n_chains, team_smem_bytes(h->row_words, 1), h->stream));
+            h->run_team = 1;
+        } else {
+            rc = launch_motif(h, m);
+            if (rc) return rc;
+        }
         launches += h->run_extra_launches;
     } else if (p->background == GIBBS_BG_DATA) {
         // teams of warps, speculative rounds and the hand-over of chain_kernel, with the drifting-background scan
@@ -1120,6 +1171,8 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         launches += h->run_extra_launches;
     }
     h->run_sampler = p->sampler;
+    h->run_m = p->sampler == GIBBS_MOTIF_SAMPLER ? m_amount : 1;
+    h->best_valid = false;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     ++launches;
     best_chain_kernel<<<1, 256, 0, h->stream>>>(h->sums.p, n_chains, h->best.p);
@@ -1172,7 +1225,63 @@ int32_t gibbs_set_start_state(gibbs_handle *h, int32_t n_chains, const int32_t *
     CUDA_TRY(cudaMemsetAsync(h->hv.p, 0xFF, cells * sizeof(double), h->stream)); // all-ones = NaN marker
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->start_chains = n_chains;
+    h->start_m = 0; // (gibbs_set_start_motif_state raises it after staging the Positions lists)
     h->run_done = false;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_set_start_motif_state(gibbs_handle *h, int32_t n_chains, int32_t m, const int32_t *positions, const double *pwms) {
+    if (!h || !positions || !pwms) return fail(GIBBS_ERR_ARG, "null argument (ArgumentNullException)");
+    if (m < 1 || m > 2) return fail(GIBBS_ERR_UNSUPPORTED, "Positions lists of %d sites: one and two are built", m);
+    if (h->n < 1 || n_chains < 1) return fail(GIBBS_ERR_ARG, "nothing to set");
+    const size_t cells = (size_t)n_chains * h->n;
+    std::vector<int32_t> newest;
+    try {
+        newest.resize(cells);
+    } catch (...) {
+        return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+    }
+    for (size_t c = 0; c < cells; ++c) newest[c] = positions[c * m];
+    int32_t rc = gibbs_set_start_state(h, n_chains, newest.data(), pwms); // validates the newest positions, stages scores
+    if (rc) return rc;
+    if (m == 2) {
+        int32_t excess = h->start_max_excess;
+        const int32_t *second = positions;
+        for (size_t c = 0; c < cells; ++c) {
+            const int32_t p0 = second[2 * c], p1 = second[2 * c + 1], l = h->len_host[c % (size_t)h->n];
+            if (p1 < -1 || p1 >= l || (p0 < 0 && p1 >= 0)) return fail(GIBBS_ERR_ARG, "bad Positions list (second position %d)", p1);
+            if (p1 >= 0 && p1 - l > excess) excess = p1 - l;
+        }
+        h->start_max_excess = excess;
+        CUDA_TRY(h->pos2.reserve(cells * 2));
+        CUDA_TRY(cudaMemcpyAsync(h->pos2.p, positions, cells * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->start_m = m;
+    return GIBBS_OK;
+}
+
+int32_t gibbs_fetch_positions(gibbs_handle *h, int32_t m, int32_t *positions_out) {
+    if (!h || !positions_out) return fail(GIBBS_ERR_ARG, "null argument");
+    if (!h->run_done) return fail(GIBBS_ERR_ARG, "gibbs_fetch_positions without a preceding gibbs_run_device");
+    if (m != h->run_m) return fail(GIBBS_ERR_ARG, "the last run had motif_amount = %d", h->run_m);
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    const size_t cells = (size_t)h->run_chains * h->n;
+    const int32_t *src = m == 2 ? h->pos2.p : h->sites.p;
+    CUDA_TRY(cudaMemcpyAsync(positions_out, src, cells * m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GIBBS_OK;
+}
+
+int32_t gibbs_fetch_best_positions(gibbs_handle *h, int32_t m, int32_t *positions_out) {
+    if (!h || !positions_out) return fail(GIBBS_ERR_ARG, "null argument");
+    if (!h->run_done || !h->best_valid) return fail(GIBBS_ERR_ARG, "gibbs_fetch_best_positions without a preceding gibbs_fetch_best");
+    if (m != h->run_m) return fail(GIBBS_ERR_ARG, "the last run had motif_amount = %d", h->run_m);
+    int32_t rc = set_device(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(positions_out, h->win_sites.p, (size_t)h->n * m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return GIBBS_OK;
 }
 
@@ -1229,26 +1338,57 @@ int32_t gibbs_fetch_best(gibbs_handle *h, int32_t repetitions, int32_t *sites_ou
     if (repetitions < 0) repetitions = 0;
     int32_t rc = set_device(h);
     if (rc) return rc;
-    const int32_t N = h->n;
-    CUDA_TRY(h->win_sites.reserve((size_t)N + 1));
+    const int32_t N = h->n, M = h->run_m, NS = N * M; // NS site entries per restart (Positions lists for motifAmount = 2)
+    CUDA_TRY(h->win_sites.reserve((size_t)NS + 1 + 2 * (size_t)N));
     CUDA_TRY(h->win_scores.reserve((size_t)N + 1));
-    restart_select_kernel<<<1, 32, 0, h->stream>>>(h->sums.p, h->sites.p, h->scores.p, h->run_chains, N, repetitions,
-                                                  h->run_sampler == GIBBS_MOTIF_SAMPLER ? 1 : 0, h->win_sites.p + N,
+    restart_select_kernel<<<1, 32, 0, h->stream>>>(h->sums.p, M == 2 ? h->pos2.p : h->sites.p, h->scores.p, h->run_chains, N, NS,
+                                                  repetitions, h->run_sampler == GIBBS_MOTIF_SAMPLER ? 1 : 0, h->win_sites.p + NS,
                                                   h->win_sites.p, h->win_scores.p, h->win_scores.p + N);
     CUDA_TRY(cudaGetLastError());
     int extra_launches = 1;
     // the winner is at a fixed device address: everything is queued before the one synchronisation
     int32_t best = -1;
     double sum = 0.0;
-    CUDA_TRY(cudaMemcpyAsync(&best, h->win_sites.p + N, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int32_t> pairs; // motifAmount = 2: the Positions lists; sites_out gets the newest position of each
+    CUDA_TRY(cudaMemcpyAsync(&best, h->win_sites.p + NS, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(&sum, h->win_scores.p + N, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (sites_out) CUDA_TRY(cudaMemcpyAsync(sites_out, h->win_sites.p, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (sites_out) {
+        if (M == 1) {
+            CUDA_TRY(cudaMemcpyAsync(sites_out, h->win_sites.p, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            try {
+                pairs.resize((size_t)NS);
+            } catch (...) {
+                return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+            }
+            CUDA_TRY(cudaMemcpyAsync(pairs.data(), h->win_sites.p, (size_t)NS * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
     if (scores_out) CUDA_TRY(cudaMemcpyAsync(scores_out, h->win_scores.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int32_t> counts2;
     if (counts_out) { // PWM counts of the winner's sites (all zero when the initial value survived)
-        rc = launch_all_counts(h, dev_seqs(h), h->win_sites.p, h->run_k, h->best.p + 1);
-        if (rc) return rc;
-        ++extra_launches;
-        CUDA_TRY(cudaMemcpyAsync(counts_out, h->best.p + 1, (size_t)h->run_k * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (M == 1) {
+            rc = launch_all_counts(h, dev_seqs(h), h->win_sites.p, h->run_k, h->best.p + 1);
+            if (rc) return rc;
+            ++extra_launches;
+            CUDA_TRY(cudaMemcpyAsync(counts_out, h->best.p + 1, (size_t)h->run_k * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        } else { // both elements of every Positions pair
+            try {
+                counts2.assign((size_t)h->run_k * 4 * 2, 0);
+            } catch (...) {
+                return fail(GIBBS_ERR_NOMEM, "host allocation failed");
+            }
+            for (int which = 0; which < 2; ++which) {
+                int32_t *tmp = h->win_sites.p + NS + 1 + (size_t)which * N;
+                pair_element_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(h->win_sites.p, N, which, tmp);
+                CUDA_TRY(cudaGetLastError());
+                rc = launch_all_counts(h, dev_seqs(h), tmp, h->run_k, h->best.p + 1);
+                if (rc) return rc;
+                extra_launches += 2;
+                CUDA_TRY(cudaMemcpyAsync(counts2.data() + (size_t)which * h->run_k * 4, h->best.p + 1, (size_t)h->run_k * 4 * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
     }
     unsigned long long st[ST_NSLOTS];
     CUDA_TRY(cudaMemcpyAsync(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
@@ -1257,6 +1397,11 @@ int32_t gibbs_fetch_best(gibbs_handle *h, int32_t repetitions, int32_t *sites_ou
         CUDA_TRY(cudaMemcpyAsync(&roulette_error, h->err_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (roulette_error) return fail(GIBBS_ERR_ROULETTE, "a roulette pick lay beyond the accumulated mass (ArgumentException, fs:753)");
+    h->best_valid = true;
+    if (sites_out && M == 2)
+        for (int32_t i = 0; i < N; ++i) sites_out[i] = pairs[(size_t)2 * i];
+    if (counts_out && M == 2)
+        for (int32_t e = 0; e < h->run_k * 4; ++e) counts_out[e] = counts2[(size_t)e] + counts2[(size_t)h->run_k * 4 + e];
     if (best < 0) { // loop 0 [||] [|(0., 0)|] returned its initial value (quirk A.6-8)
         if (sites_out) sites_out[0] = h->run_sampler == GIBBS_MOTIF_SAMPLER ? -1 : 0;
         if (scores_out) scores_out[0] = 0.0;
@@ -1418,6 +1563,7 @@ int32_t gibbs_multi_fetch_best(gibbs_multi *m, int32_t repetitions, int32_t *sit
     if (!m->run_done) return fail(GIBBS_ERR_ARG, "gibbs_multi_fetch_best without a preceding gibbs_multi_run_device");
     if (repetitions < 0) repetitions = 0;
     const int32_t N = m->dev[0]->n, R = m->run_chains;
+    if (m->dev[0]->run_m != 1) return fail(GIBBS_ERR_UNSUPPORTED, "the multi-device calls return one site per sequence (motif_amount = 1)");
     try {
         m->sums.assign((size_t)R, 0.0);
     } catch (...) {

@@ -772,8 +772,9 @@ static __global__ void __launch_bounds__(256) best_chain_kernel(const double *su
 // out[0] = index of the returned restart, -1 = the initial value survived (the caller returns [|(0., 0)|]);
 // the winner's rows are copied to win_sites / win_scores so that one fixed-address copy brings them to the host.
 // motif = the MotifIndex flavour of the initial value: {PWMS 0.; Positions []} (site -1) instead of (0., 0).
+// NS = site entries per restart: N, or 2 N for Positions lists of up to two sites (motifAmount = 2).
 static __global__ void __launch_bounds__(32) restart_select_kernel(const double *sums, const int32_t *sites, const double *scores,
-                                                                   int n_chains, int N, int reps, int motif, int32_t *out,
+                                                                   int n_chains, int N, int NS, int reps, int motif, int32_t *out,
                                                                    int32_t *win_sites, double *win_scores, double *win_sum) {
     const int lane = threadIdx.x;
     int best = -1;
@@ -801,12 +802,11 @@ static __global__ void __launch_bounds__(32) restart_select_kernel(const double 
         if (s_j == bsum) {                // acc = best? structural equality of the two arrays (F# (=): NaN <> NaN)
             bool same;
             if (best < 0) {
-                same = N == 1 && scores[(size_t)r_j * N] == 0.0 && sites[(size_t)r_j * N] == (motif ? -1 : 0);
+                same = N == 1 && scores[(size_t)r_j * N] == 0.0 && sites[(size_t)r_j * NS] == (motif ? -1 : 0);
             } else {
                 bool diff = false;
-                for (int i = lane; i < N; i += 32)
-                    diff |= sites[(size_t)r_j * N + i] != sites[(size_t)best * N + i] ||
-                            !(scores[(size_t)r_j * N + i] == scores[(size_t)best * N + i]);
+                for (int i = lane; i < N; i += 32) diff |= !(scores[(size_t)r_j * N + i] == scores[(size_t)best * N + i]);
+                for (int i = lane; i < NS; i += 32) diff |= sites[(size_t)r_j * NS + i] != sites[(size_t)best * NS + i];
                 same = !__any_sync(FULL, diff);
             }
             if (same) break;
@@ -825,10 +825,15 @@ static __global__ void __launch_bounds__(32) restart_select_kernel(const double 
         out[0] = best;
         *win_sum = best < 0 ? 0.0 : sums[best];
     }
-    for (int i = lane; i < N; i += 32) { // (no winner: -1 = no site, so that the PWM counts of the result are all zero)
-        win_sites[i] = best >= 0 ? sites[(size_t)best * N + i] : -1;
-        win_scores[i] = best >= 0 ? scores[(size_t)best * N + i] : 0.0;
-    }
+    // (no winner: -1 = no site, so that the PWM counts of the result are all zero)
+    for (int i = lane; i < NS; i += 32) win_sites[i] = best >= 0 ? sites[(size_t)best * NS + i] : -1;
+    for (int i = lane; i < N; i += 32) win_scores[i] = best >= 0 ? scores[(size_t)best * N + i] : 0.0;
+}
+
+// element `which` of every Positions pair: the site arrays the one-site kernels take
+static __global__ void pair_element_kernel(const int32_t *pos2, int n, int which, int32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pos2[2 * i + which];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -86,7 +86,7 @@ class RunResult:
 
 def make_params(k: int, pseudocount: float, alphabet_size: int, bg: Sequence[float], *, cutoff: float = 0.0,
                 sampler: int = _abi.GIBBS_SITE_SAMPLER, phase_shifts: bool = True, max_sweeps: int = 0,
-                phase_mask: int = 0, background: int = _abi.GIBBS_BG_FIXED) -> Params:
+                phase_mask: int = 0, background: int = _abi.GIBBS_BG_FIXED, motif_amount: int = 1) -> Params:
     p = Params()
     p.k = int(k)
     p.alphabet_size = int(alphabet_size)
@@ -99,7 +99,7 @@ def make_params(k: int, pseudocount: float, alphabet_size: int, bg: Sequence[flo
     p.max_sweeps = int(max_sweeps)
     p.phase_mask = int(phase_mask)
     p.background = int(background)
-    p.reserved = 0
+    p.motif_amount = int(motif_amount)
     return p
 
 
@@ -256,6 +256,31 @@ class GibbsEngine:
             raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "start state must be [n_chains, n_seqs]")
         _abi.check(self._lib.gibbs_set_start_state(self._h, C.c_int32(s.shape[0]), _ptr(s, C.c_int32),
                                                    _ptr(v, C.c_double)))
+
+    def set_start_motif_state(self, positions, pwms) -> None:
+        """motifMem : MotifIndex[] with up to m positions per sequence: positions [n_chains, n_seqs, m] (newest first,
+        -1 = absent), pwms [n_chains, n_seqs]."""
+        pos = np.ascontiguousarray(positions, dtype=np.int32)
+        v = np.ascontiguousarray(pwms, dtype=np.float64)
+        if pos.ndim == 2:
+            pos, v = pos.reshape(1, *pos.shape), v.reshape(1, -1)
+        if pos.ndim != 3 or pos.shape[:2] != v.shape or pos.shape[1] != self.n:
+            raise _abi.GibbsArgumentError(_abi.GIBBS_ERR_ARG, "start state must be [n_chains, n_seqs, m]")
+        _abi.check(self._lib.gibbs_set_start_motif_state(self._h, C.c_int32(pos.shape[0]), C.c_int32(pos.shape[2]),
+                                                         _ptr(pos, C.c_int32), _ptr(v, C.c_double)))
+
+    def fetch_positions(self, m: int) -> np.ndarray:
+        """MotifIndex.Positions of every sequence of every chain of the last run: int32 [chains, n, m], newest first."""
+        n_chains, _ = self._last
+        out = np.zeros((n_chains, self.n, m), dtype=np.int32)
+        _abi.check(self._lib.gibbs_fetch_positions(self._h, C.c_int32(m), _ptr(out, C.c_int32)))
+        return out
+
+    def fetch_best_positions(self, m: int) -> np.ndarray:
+        """Positions lists of the array the last fetch_best returned: int32 [n, m]."""
+        out = np.zeros((self.n, m), dtype=np.int32)
+        _abi.check(self._lib.gibbs_fetch_best_positions(self._h, C.c_int32(m), _ptr(out, C.c_int32)))
+        return out
 
     def _pinned(self, name: str, shape: tuple, dtype) -> np.ndarray:
         """Page-locked result buffer owned by this engine, grown on demand and reused by later fetches."""

@@ -73,7 +73,8 @@ typedef struct gibbs_params {
                            /* run in pipeline order from the state given to gibbs_set_start_state    */
     int32_t background;    /* GIBBS_BG_FIXED: bg[] (WithBPV family) | GIBBS_BG_DATA: derived from the */
                            /* sequences like doSiteSampling does (fs:697; per-window counts, fs:470)  */
-    int32_t reserved;
+    int32_t motif_amount;  /* MotifSampler motifAmount: sites per sequence, 0 / 1 = one, 2 = up to two (fs:727-742);  */
+                           /* three and more are GIBBS_ERR_UNSUPPORTED                                */
 } gibbs_params;
 
 #define GIBBS_BG_FIXED 0
@@ -243,6 +244,18 @@ int32_t gibbs_run(gibbs_handle *h, const gibbs_params *p, int32_t n_chains, int6
                   int64_t uniforms_per_chain, int32_t *sites_out, double *scores_out,
                   double *sums_out, int32_t *best_chain_out, int32_t *counts_out,
                   gibbs_run_stats *stats_out);
+/*
+ * MotifIndex.Positions for motif_amount = m (fs:712-716): int32 [n_chains][n_seqs][m], newest position first -- the cons
+ * order of fs:736, e.g. [306; 7] -- and -1 for an absent entry. sites_out of gibbs_fetch / gibbs_fetch_best holds the
+ * first element of each list. gibbs_fetch_best_positions: the lists of the array the last gibbs_fetch_best returned,
+ * int32 [n_seqs][m].
+ */
+int32_t gibbs_fetch_positions(gibbs_handle *h, int32_t m, int32_t *positions_out);
+int32_t gibbs_fetch_best_positions(gibbs_handle *h, int32_t m, int32_t *positions_out);
+/* gibbs_set_start_state for MotifIndex[] start states whose Positions hold up to m sites: positions int32
+ * [n_chains][n_seqs][m] (newest first, -1 = absent), pwms double [n_chains][n_seqs] */
+int32_t gibbs_set_start_motif_state(gibbs_handle *h, int32_t n_chains, int32_t m, const int32_t *positions,
+                                    const double *pwms);
 /* device pointers of the last run, for zero-copy collectives in the host layer (may be NULL) */
 int32_t gibbs_device_results(gibbs_handle *h, void **sites_dev, void **scores_dev, void **sums_dev);
 

@@ -129,12 +129,12 @@ def test_motif_restart_loop_and_scope():
         want, _ = O.best_motif_information_content(0, reps, S, 1, k, pc, cutoff, rng, pcv=O.pcv_from_acgt(bg))
         assert [list(m.Positions) for m in got] == [p for _, p in want]
         np.testing.assert_allclose([m.PWMS for m in got], [v for v, _ in want], rtol=RTOL)
-    with pytest.raises(_abi.GibbsUnsupportedError):
-        MotifSampler.doMotifSamplingWithPCV(2, k, pc, cutoff, DNA, seqs, pcv)
+    with pytest.raises(_abi.GibbsUnsupportedError):    # one and two sites per sequence are built (test_gpu_motif2.py), not three
+        MotifSampler.doMotifSamplingWithPCV(3, k, pc, cutoff, DNA, seqs, pcv)
     with pytest.raises(_abi.GibbsArgumentError):       # null PPM = ArgumentNullException; the family itself is built
         MotifSampler.doMotifSamplingWithPPM(1, k, pc, cutoff, DNA, seqs, None)
     with pytest.raises(_abi.GibbsUnsupportedError):
-        MotifSampler.doMotifSamplingWithPPM(2, k, pc, cutoff, DNA, seqs, np.full((k, 4), 0.25))
+        MotifSampler.doMotifSamplingWithPPM(3, k, pc, cutoff, DNA, seqs, np.full((k, 4), 0.25))
 
 
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: f"n{c[0]}_L{c[1]}_k{c[3]}_cut{c[5]}")

@@ -141,7 +141,7 @@ def test_unbuilt_reference_entry_points_say_so():
         SiteSampler.doSiteSamplingWithBPV(6, 1e-4, list("AT"), ["ACGTACGT"], ProbabilityCompositeVector())
     assert MotifSampler.createMotifIndex(1.5, [3]) == MotifSampler.MotifIndex(1.5, (3,))
     with pytest.raises(_abi.GibbsUnsupportedError):
-        MotifSampler.doMotifSamplingWithPCV(2, 6, 1e-4, 1.0, DNA, ["ACGTACGT"], ProbabilityCompositeVector.ofACGT(.25, .25, .25, .25))
+        MotifSampler.doMotifSamplingWithPCV(3, 6, 1e-4, 1.0, DNA, ["ACGTACGT"], ProbabilityCompositeVector.ofACGT(.25, .25, .25, .25))
 
 
 # ---------------------------------------------------------------------------------------------
