@@ -110,6 +110,9 @@ struct gibbs_handle {
     DevBuf<uint32_t> packed;
     DevBuf<uint32_t> mask;     // same geometry as packed: 0b11 at symbols outside A,C,G,T
     DevBuf<int32_t> rowflag;   // [n] sequence holds such a symbol
+    DevBuf<uint64_t> wide;     // gather copy of the packed rows (DeviceSeqs::wide), built on first use
+    bool wide_valid = false;
+    int32_t wide_words = 0;
     DevBuf<int32_t> len;
     DevBuf<int> flags;    // [1..3] wtab range
     DevBuf<int> symflags; // pack_kernel: [0] 1 + byte outside '*'..'Z', [1] symbols outside A,C,G,T, [2] Gap seen
@@ -314,6 +317,21 @@ int32_t launch_random_starts(gibbs_handle *h, ChainArgs &a, bool drift) {
         a.phase_mask &= ~GIBBS_PHASE_INIT; // the chain kernel continues from the state just written
         h->run_extra_launches += 1;
     } else if (init_path == GIBBS_INIT_WIDE) {
+        if (!h->wide_valid && a.k <= 25 && !masked) { // the gather copy: 8 bytes per 8 bases, built once per upload
+            const int ww = h->max_len / 8 + 1;
+            const size_t words = (size_t)h->n * ww;
+            if (words * 8 <= ((size_t)8 << 30) && h->wide.reserve(words) == cudaSuccess) {
+                wide_kernel<<<(unsigned)((words + 255) / 256), 256, 0, h->stream>>>(h->packed.p, h->n, h->row_words, ww, h->wide.p);
+                CUDA_TRY(cudaGetLastError());
+                h->wide_words = ww;
+                h->wide_valid = true;
+                h->run_extra_launches += 1;
+                a.s.wide = h->wide.p;
+                a.s.wide_words = ww;
+            } else {
+                cudaGetLastError(); // not enough memory: the packed rows serve
+            }
+        }
         const int smem = init_smem_bytes(a.s.row_words);
         const long long items = (long long)a.n_chains * a.s.n;
         long long grid = (items + INIT_WARPS - 1) / INIT_WARPS;
@@ -661,6 +679,8 @@ DeviceSeqs dev_seqs(const gibbs_handle *h) {
     s.uniform_len = h->min_len == h->max_len ? h->max_len : 0;
     s.mask = h->n_masked > 0 ? h->mask.p : nullptr;
     s.rowflag = h->n_masked > 0 ? h->rowflag.p : nullptr;
+    s.wide = h->wide_valid ? h->wide.p : nullptr;
+    s.wide_words = h->wide_words;
     return s;
 }
 
@@ -682,7 +702,7 @@ int32_t upload(gibbs_handle *h, const uint8_t *seqs, const int64_t *offsets, int
     h->n = 0;
     h->start_chains = 0;
     h->run_done = false;
-    h->wtab_valid = h->bg_valid = h->drift_valid = h->ss_valid = false;
+    h->wtab_valid = h->bg_valid = h->drift_valid = h->ss_valid = h->wide_valid = false;
     const int64_t total = offsets[n_seqs] - offsets[0];
     const int row_words = (int)(((max_len + 15) / 16 + 4 + 3) / 4 * 4);
     if (team_smem_bytes(row_words, 1) > 200 * 1024) return fail(GIBBS_ERR_ARG, "sequence too long for shared-memory staging");
@@ -805,7 +825,7 @@ int32_t gibbs_destroy(gibbs_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->ascii.release(); h->off.release(); h->packed.release(); h->len.release(); h->flags.release();
-    h->mask.release(); h->rowflag.release(); h->symflags.release();
+    h->mask.release(); h->rowflag.release(); h->symflags.release(); h->wide.release();
     h->wtab.release(); h->prim_sites.release(); h->prim_i32.release(); h->prim_f64.release();
     h->sites.release(); h->hv.release(); h->scores.release(); h->sums.release(); h->uniforms.release();
     h->stats.release(); h->best.release();

@@ -49,6 +49,11 @@ struct DeviceSeqs {
     // (their 2-bit code is 0); rowflag[i] != 0 iff sequence i holds at least one.
     const uint32_t *mask;
     const int32_t *rowflag;
+    // Gather copy for the random starts of sets that do not fit shared memory: wide[i][m] = the 32 bases from base 8 m of
+    // sequence i as one 64-bit word (windows overlap: 4x the packed size). A k-mer of k <= 25 at ANY position is one aligned
+    // 8-byte load -- one L1 sector request per draw instead of the two or three 4-byte requests of the packed rows.
+    const uint64_t *wide;
+    int32_t wide_words;     // words per sequence: max_len / 8 + 1
 };
 
 struct ChainArgs {
@@ -540,6 +545,12 @@ __device__ __forceinline__ typename KmerCounter<KP>::Word gather_kmer(const uint
     } else {
         return lo;
     }
+}
+// the same from the gather copy (DeviceSeqs::wide), k <= 25: one 8-byte load
+template <int KP>
+__device__ __forceinline__ typename KmerCounter<KP>::Word gather_kmer_wide(const uint64_t *__restrict__ wide, int wide_words, int i, int pos) {
+    const uint64_t v = __ldg(wide + (size_t)i * wide_words + (pos >> 3)) >> (2 * (pos & 7));
+    return (typename KmerCounter<KP>::Word)v;
 }
 
 // counts over the sites of all sequences except `exclude` (sites < 0 = no site), positions shifted

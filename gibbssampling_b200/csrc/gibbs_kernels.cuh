@@ -61,6 +61,19 @@ static __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const int6
     }
 }
 
+// gather copy of the packed rows: wide[i][m] = 64 bits from bit 16 m of row i (see DeviceSeqs::wide). One thread per word.
+static __global__ void wide_kernel(const uint32_t *__restrict__ packed, int n, int row_words, int wide_words, uint64_t *__restrict__ wide) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * wide_words) return;
+    const int i = (int)(t / wide_words), m = (int)(t % wide_words);
+    const uint32_t *row = packed + (size_t)i * row_words;
+    const int w = m >> 1; // 16 m bits = word m / 2 (+ 16 bits for odd m); rows end in >= 4 zero words
+    uint32_t a = row[w], b = w + 1 < row_words ? row[w + 1] : 0u, c = w + 2 < row_words ? row[w + 2] : 0u;
+    uint64_t v = ((uint64_t)b << 32) | a;
+    if (m & 1) v = (v >> 16) | ((uint64_t)c << 48);
+    wide[t] = v;
+}
+
 // W(c, b) = ((c + pc) / den) / q[b]   (normalizePPM fs:260, createPositionWeightMatrix fs:286)
 // plus its fixed-point log2. range[0] = min lg, range[1] = max lg, range[2] = any non-normal W.
 static __global__ void wtab_kernel(int n, double pc, double den, double q0, double q1, double q2, double q3, WEnt *wtab,
@@ -123,7 +136,8 @@ static __global__ void wtab_kernel(int n, double pc, double den, double q0, doub
 // The base counts are kept bit-sliced in registers (KmerCounter): no lookup table.
 // UNI = every sequence has the same length (no length load per draw); PHILOX = the counter-based stream (else the
 // injected doubles): warp-uniform properties of the run, hoisted out of the draw loop as template parameters.
-template <int KP, int NB, bool MASKED, bool SROWS, bool UNI, bool PHILOX>
+// WIDE = gather from the 64-bit copy (DeviceSeqs::wide) instead of the packed rows in global memory.
+template <int KP, int NB, bool MASKED, bool SROWS, bool UNI, bool PHILOX, bool WIDE = false>
 __device__ __forceinline__ void random_draw_loop(const ChainArgs &a, uint64_t chain_uid, int chain_local, int n, int32_t *counts,
                                                  int lane, int32_t *fix, const uint32_t *base_rows) {
     using Word = typename KmerCounter<KP>::Word;
@@ -171,7 +185,7 @@ __device__ __forceinline__ void random_draw_loop(const ChainArgs &a, uint64_t ch
                         pos = (int)(u * (double)range);           // rnd.Next(0, L-k+1), fs:145
                         pos = min(max(pos, 0), (int)range - 1);   // memory safety for u outside [0,1)
                     }
-                    const Word km = gather_kmer<KP, SROWS>(base_rows, row_words, i, pos);
+                    const Word km = WIDE ? gather_kmer_wide<KP>(a.s.wide, a.s.wide_words, i, pos) : gather_kmer<KP, SROWS>(base_rows, row_words, i, pos);
                     kmer[q][x] = ok ? km : (Word)0; // code 0 in every column: counted nowhere
                     if (MASKED && ok && __ldg(a.s.rowflag + i) != 0) hist_fix(a.s.mask, row_words, i, pos, k, fix);
                 }
@@ -197,7 +211,16 @@ __device__ __forceinline__ void random_loo_counts_impl(const ChainArgs &a, uint6
         return;
     }
     const uint32_t *const base_rows = SROWS ? rows : a.s.packed;
-    if (a.rng_mode != 0) random_draw_loop<KP, 1, MASKED, SROWS, false, false>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
+    bool done = false;
+    if constexpr (!SROWS && KP <= 13) { // the 64-bit gather copy holds every k-mer of k <= 25 in one aligned word
+        if (a.rng_mode == 0 && a.s.wide != nullptr && k <= 25) {
+            if (a.s.uniform_len > 0) random_draw_loop<KP, NB, MASKED, false, true, true, true>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
+            else random_draw_loop<KP, NB, MASKED, false, false, true, true>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
+            done = true;
+        }
+    }
+    if (done) {
+    } else if (a.rng_mode != 0) random_draw_loop<KP, 1, MASKED, SROWS, false, false>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
     else if (a.s.uniform_len > 0) random_draw_loop<KP, NB, MASKED, SROWS, true, true>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
     else random_draw_loop<KP, NB, MASKED, SROWS, false, true>(a, chain_uid, chain_local, n, counts, lane, fix, base_rows);
     if (MASKED) {
