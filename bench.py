@@ -32,15 +32,18 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (n_seqs, length, k, chains per GPU, phase shifts)
-    "C1": (20, 100, 8, 1, True),          # reference-scale: 20 x 100 bp, planted 8-mer, 1 chain
+    "C1": (20, 100, 8, 1001, True),       # reference-scale: 20 x 100 bp, planted 8-mer, ONE sequential chain of 1000 iterations
+                                          # = numberOfRepetitions 1000 of fs:434 (at most 1001 restarts, run here as parallel chains)
     "C2": (1000, 500, 12, 1024, True),    # the single-GPU configuration the metric is quoted on
     "C3": (10000, 1000, 16, 1024, True),  # 8192 restarts over 8 GPUs = 1024 per GPU
     "C4": (100000, 200, 20, 148, True),   # ChIP-seq-peak-sized set with phase-shift moves
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step (ncu --set full, round 1)
-NCU_DRAM_BYTES_PER_STEP = int((0.316672 + 1.589760 + 3.313920 + 0.000000 + 1.631232 + 0.003328) * 1e6)
-NCU_DRAM_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of the three chain_kernel launches of one C2 step, "
-                   "profiles/r01_ncu_c2_final_summary.txt")
+# dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one C2 step (ncu --set full, round 2): init_smem_kernel,
+# chain_kernel T = 4 / 8 / 16, chain_cluster_kernel 4 / 8 (read, write in MB each)
+NCU_DRAM_BYTES_PER_STEP = int((0.224000 + 0.0 + 12.567040 + 1.397248 + 3.205632 + 0.0 + 1.615360 + 0.0
+                               + 0.563456 + 0.0 + 0.405504 + 0.0) * 1e6)
+NCU_DRAM_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one C2 step (init_smem_kernel, "
+                   "chain_kernel T=4/8/16, chain_cluster_kernel 4/8), profiles/r02_ncu_c2_step_summary.txt")
 # --family: which reference family the step runs (the default is the BASELINE.json workload)
 FAMILIES = {
     "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts", "gibbs::chain_kernel",
@@ -417,7 +420,14 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
         if world == 1 and not args.no_cpu and fam_oracle is not None:
             dt = ws = us = 0.0
             n_cpu_chains = 0
-            while dt < 12.0 and n_cpu_chains < 64:          # about 10-30 s of CPU work
+            if cfg_name == "C1":    # the reference-scale case runs in full: the restart loop of fs:434 with numberOfRepetitions = chains - 1
+                O = _oracle()
+                rng, _ = O.make_rng(seed=SEED, chain=0)
+                t0 = time.perf_counter()
+                _, _, st1 = O.best_information_content(0 if args.family == "bpv" else 1, chains - 1, O.sources(ps.sequences()), k,
+                                                       PSEUDOCOUNT, rng, pcv=O.pcv_from_acgt(bg) if args.family == "bpv" else None)
+                dt, ws, us, n_cpu_chains = time.perf_counter() - t0, st1.window_scores, st1.site_updates, int(st1.restarts)
+            while cfg_name != "C1" and dt < 12.0 and n_cpu_chains < 64:          # about 10-30 s of CPU work
                 d1, w1, u1 = cpu_sample(ps, k, bg, threads=1, full_restart=True, seed=SEED, chain_base=n_cpu_chains,
                                         family=args.family)
                 dt, ws, us, n_cpu_chains = dt + d1, ws + w1, us + u1, n_cpu_chains + 1
