@@ -46,14 +46,15 @@ NCU_DRAM_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of the six kern
                    "chain_kernel T=4/8/16, chain_cluster_kernel 4/8), profiles/r02_ncu_c2_step_summary.txt")
 # --family: which reference family the step runs (the default is the BASELINE.json workload)
 FAMILIES = {
-    "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts", "gibbs::chain_kernel",
-            "do_site_sampling_with_bpv"),
+    "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts",
+            "gibbs::chain_kernel (a step = init_smem_kernel / init_kernel + chain_kernel<KP,4|8|16> + chain_cluster_kernel<KP,4|8>, "
+            "timed together: kernel_ms)", "do_site_sampling_with_bpv"),
     "data": ("SiteSampler restarts with the data-derived drifting background (doSiteSampling, fs:697)",
              "data-derived, rebuilt per window (fs:470-473)", "gibbs::chain_kernel<KP, T, MASKED, DRIFT = true>", "do_site_sampling"),
     "motif": ("MotifSampler m = 1 restarts with a fixed background (doMotifSamplingWithPCV, fs:876), cutOff 0",
-              "fixed pcv, whole-set base counts", "gibbs::motif_kernel", None),
+              "fixed pcv, whole-set base counts", "gibbs::motif_kernel<KP, T = 4>", None),
     "motif-data": ("MotifSampler m = 1 restarts with the data-derived background (doMotifSampling, fs:1034), cutOff 0",
-                   "data-derived, rebuilt per held-out sequence (fs:896-905)", "gibbs::motif_kernel", None),
+                   "data-derived, rebuilt per held-out sequence (fs:896-905)", "gibbs::motif_kernel<KP, T = 4>", None),
 }
 PSEUDOCOUNT = 1e-4      # fsx:384
 ALPHABET_SIZE = 5       # dnaBases = [A; T; G; C; Gap], fsx:368-369
