@@ -45,6 +45,8 @@ GIBBS_CHAIN_TU(launch_init_smem);
 #undef GIBBS_CHAIN_TU
 cudaError_t launch_motif_t4(const MotifArgs &m, int grid, int smem, cudaStream_t stream); // gibbs_motif_tu.cu
 cudaError_t launch_motif_t1(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
+cudaError_t launch_motif_masked_t4(const MotifArgs &m, int grid, int smem, cudaStream_t stream); // symbols outside A,C,G,T
+cudaError_t launch_motif_masked_t1(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
 cudaError_t launch_motif2(const Motif2Args &q, int grid, int smem, cudaStream_t stream); // gibbs_motif2_tu.cu
 cudaError_t launch_motif2_seed(const int32_t *sites, long long cells, int32_t *pos2, cudaStream_t stream);
 // gibbs_cluster_tu.cu: one chain on a cluster of 4 / 8 CTAs (capacity_out != null: only report how many clusters fit)
@@ -637,7 +639,10 @@ int32_t launch_motif_kp(gibbs_handle *h, MotifArgs m) {
     }
     const int team = motif_team(h);
     const int smem = team_smem_bytes(m.c.s.row_words, team);
-    CUDA_TRY(team == 4 ? launch_motif_t4(m, m.c.n_chains, smem, h->stream) : launch_motif_t1(m, m.c.n_chains, smem, h->stream));
+    if (m.c.s.mask != nullptr)
+        CUDA_TRY(team == 4 ? launch_motif_masked_t4(m, m.c.n_chains, smem, h->stream) : launch_motif_masked_t1(m, m.c.n_chains, smem, h->stream));
+    else
+        CUDA_TRY(team == 4 ? launch_motif_t4(m, m.c.n_chains, smem, h->stream) : launch_motif_t1(m, m.c.n_chains, smem, h->stream));
     h->run_team = team;
     return GIBBS_OK;
 }
@@ -953,7 +958,6 @@ int32_t gibbs_pick_roulette(gibbs_handle *h, const int32_t *sites, int32_t heldo
     if (rc) return rc;
     if (p->background != GIBBS_BG_FIXED) return fail(GIBBS_ERR_UNSUPPORTED, "gibbs_pick_roulette takes a fixed background (WithPCV)");
     if (heldout < 0 || heldout >= h->n) return fail(GIBBS_ERR_ARG, "heldout %d outside 0..%d", heldout, h->n - 1);
-    if (h->n_masked > 0) return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler only");
     rc = set_device(h);
     if (rc) return rc;
     rc = stage_sites(h, sites, heldout, p->k);
@@ -1006,9 +1010,9 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
     if (m_amount > 2)
         return fail(GIBBS_ERR_UNSUPPORTED, "motifAmount = %d: combinations of one and two windows are built (fs:727-742); three and "
                                            "more sites per sequence are not", m_amount);
-    if (h->n_masked > 0 && p->sampler != GIBBS_SITE_SAMPLER)
-        return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T are built for the SiteSampler only (the MotifSampler needs "
-                                           "ACGT-only sequences)");
+    if (h->n_masked > 0 && p->sampler != GIBBS_SITE_SAMPLER && m_amount != 1)
+        return fail(GIBBS_ERR_UNSUPPORTED, "symbols outside A,C,G,T under the MotifSampler are built for motifAmount = 1 (motifAmount = 2 "
+                                           "needs ACGT-only sequences)");
     rc = set_device(h);
     if (rc) return rc;
     h->run_done = false;
@@ -1096,6 +1100,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         } else {
             h->bg_valid = false; // the fixed-background tables are not used; only the window stride is
             h->bg_wstride = h->max_len - p->k + 1;
+            if (h->n_masked > 0 && h->bg_wstride < 64) h->bg_wstride = 64; // the candidate scratch doubles as a 49-slot symbol-count table
             CUDA_TRY(h->gbuf.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride));
         }
         CUDA_TRY(h->cand_l.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride)); // one scratch list per warp
@@ -1108,6 +1113,8 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
         m.cand_l = h->cand_l.p;
         m.cand_w = h->cand_w.p;
         m.error = h->err_flag.p;
+        m.ascii = h->ascii.p;
+        m.off = h->off.p;
         m.data_bg = p->background == GIBBS_BG_DATA ? 1 : 0;
         m.greedy_fast_ok = a.fast_ok; // fixed background: the range check of the W table (ensure_wtab)
         if (m.data_bg) {
@@ -1124,7 +1131,7 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             m.greedy_fast_ok = (p->pseudocount >= 1e-30 && (double)p->k * log2(den / p->pseudocount) < 1000.0) ? 1 : 0;
             m.c.pvals = m.pvals; // the random starts use the SiteSampler's drifting-background routines (drift_tables / drift_pick)
             m.c.basecnt = m.basecnt;
-            m.c.maskcnt = nullptr;
+            m.c.maskcnt = h->n_masked > 0 ? h->maskcnt.p : nullptr; // symbols outside A,C,G,T per sequence (background denominators)
             m.c.ss = h->ss_valid ? h->ss.p : nullptr;
             m.c.ss_stride = h->max_len + 2;
             memcpy(m.c.gcnt, m.gcnt, sizeof m.gcnt);

@@ -40,7 +40,24 @@ struct MotifArgs {
     int32_t greedy_fast_ok; // greedy sweeps may rank windows in fixed point (no float64 under/overflow possible, pc > 0)
     int32_t roulette_scan_ok; // stochastic sweep may locate the roulette bucket with a warp scan (0 = always walk)
     int32_t init_done;      // the random starts already ran (grid-wide kernel): sites + raw products in hv are the state
+    // sets with symbols outside A,C,G,T, data-derived background: the uploaded symbols (see masked_background_window)
+    const uint8_t *ascii;
+    const int64_t *off;
 };
+
+// Background-only probability of a window that holds symbols outside the alphabet, data-derived background. The
+// held-out sequence adds ALL its symbols to the count vector (fs:953) and createNormalizedPCVOfFCV normalises the
+// alphabet slots only (fs:115-119): a symbol outside the alphabet keeps its raw count as its "probability", and
+// calculateSegmentScoreBy multiplies it in like any other (fs:123-124). symc = the 49 symbol counts of the sequence.
+static __device__ __noinline__ double masked_background_window(const uint8_t *seq, int w, int k, const double *q, const int32_t *symc) {
+    double v = 1.0;
+    for (int j = 0; j < k; ++j) {
+        const int c = seq[w + j];
+        const double f = c == 'A' ? q[0] : c == 'C' ? q[1] : c == 'G' ? q[2] : c == 'T' ? q[3] : (double)__ldcg(symc + (c - 42));
+        v = __dmul_rn(v, f);
+    }
+    return v;
+}
 
 // one thread per sequence
 static __global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1, double q2, double q3, int wstride, double *g,
@@ -48,6 +65,7 @@ static __global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= s.n) return;
     const uint32_t *row = s.packed + (size_t)n * s.row_words;
+    const uint32_t *mrow = (s.mask != nullptr && s.rowflag[n] != 0) ? s.mask + (size_t)n * s.row_words : nullptr;
     const int W = s.len[n] - k + 1;
     double sum = 0.0, best = 0.0;
     int best_i = 0;
@@ -56,7 +74,9 @@ static __global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1
         for (int j = 0; j < k; ++j) {
             const int pos = w + j;
             const int b = (row[pos >> 4] >> ((pos & 15) * 2)) & 3;
-            v = __dmul_rn(v, b == 0 ? q0 : b == 1 ? q1 : b == 2 ? q2 : q3);
+            double q = b == 0 ? q0 : b == 1 ? q1 : b == 2 ? q2 : q3;
+            if (mrow != nullptr && ((mrow[pos >> 4] >> ((pos & 15) * 2)) & 1u)) q = 0.0; // pcv of a symbol outside the alphabet (fs:115-119)
+            v = __dmul_rn(v, q);
         }
         g[(size_t)n * wstride + w] = v;
         sum = __dadd_rn(sum, v);
@@ -73,18 +93,21 @@ static __global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1
 // calculateNormalizedSegmentScores (fs:759-784), motifAmount = 1: the size-1 candidates, ascending
 // position, each with log2(score) > cutOff (fs:735). Written to cand_l / cand_w; returns their number.
 // Also returns the first maximum by PWMS among them (best_l = -inf when there is none).
-template <int KP>
+// MASKED, masked_n >= 0: the sequence holds symbols outside A,C,G,T; a window over one scores 0 (PWM row 0, fs:283-287),
+// log2 0 = -inf is never above the cut-off
+template <int KP, bool MASKED = false>
 __device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint32_t *row, int W, int k, double cutoff,
                                                 double raw_gate, double *cand_l, int32_t *cand_w, int lane,
-                                                double &best_l, int &best_w) {
+                                                double &best_l, int &best_w, const DeviceSeqs *sq = nullptr, int masked_n = -1) {
     // pass 1: every window's float64 product; the windows above a cheap gate just below 2^cutOff are compacted (in
     // window order) so that the logarithms -- ~150 instructions each, executed by the whole warp whenever one lane
     // needs one -- are taken over a dense list instead of over all W windows
     int gated = 0;
     for (int w0 = 0; w0 < W; w0 += 32) {
         const int w = w0 + lane;
-        const double s = w < W ? exact_window<KP>(row, w, k, T.wcol) : 0.0;
-        const bool g = w < W && s > raw_gate;
+        double s = w < W ? exact_window<KP>(row, w, k, T.wcol) : 0.0;
+        if (MASKED && masked_n >= 0 && w < W && mask_kmer(sq->mask, sq->row_words, masked_n, w, k) != 0) s = 0.0;
+        const bool g = w < W && s > raw_gate; // (raw_gate >= 0: a masked window never passes)
         const unsigned m = __ballot_sync(FULL, g);
         if (g) {
             const int at = gated + __popc(m & ((1u << lane) - 1u));
@@ -328,7 +351,11 @@ __device__ __forceinline__ void fixed_point_tables(const WarpTables &T, int lane
 #endif
 constexpr int MOTIF_BSUM_OFFSET = 2144; // 4 ints in the slack of the team's fixed shared memory (TEAM_FIXED_BYTES = 2176)
 
-template <int KP, int T>
+// MASKED = the set holds symbols outside A,C,G,T (a.s.mask != null): a separate instantiation, like chain_kernel's. Such a
+// symbol is counted in a dead row when it lies inside a site (fs:211-215), a window over one scores 0 and its
+// background-only probability is 0 (the pcv of a symbol outside the alphabet, fs:115-119); the held-out sequence's own
+// such symbols enter the denominator of the data-derived background (fs:953 adds every symbol, fs:117 sums all 49 slots).
+template <int KP, int T, bool MASKED = false>
 __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_BLOCKS : 2)) motif_kernel(const MotifArgs m) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
@@ -402,6 +429,8 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
             bool has_own = false;
             uint64_t own = 0, neu = 0;
             int cn[4] = {0, 0, 0, 0};
+            int masked_n = -1;
+            uint64_t own_mk = 0;
             if (active) {
                 const uint32_t *row = ring.wait(vbase + (uint32_t)n);
                 W = __ldg(a.s.len + n) - k + 1;
@@ -410,10 +439,15 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                     const double pw_n = __ldcg(pw + n);
                     has_own = site_n >= 0;
                     own = has_own ? kmer_shared<KP>(row, site_n) : 0;
+                    if (MASKED && __ldg(a.s.rowflag + n) != 0) {
+                        masked_n = n;
+                        if (has_own) own_mk = mask_kmer(a.s.mask, a.s.row_words, n, site_n, k);
+                    }
                     const double *g_n = m.bg.g + (size_t)n * m.bg.wstride;
                     double gsum_n = 0.0, gmax_n = 0.0;
                     if (!m.data_bg) {
-                        build_tables<KP>(WT, S.total, has_own, own, k, a.wtab, lane);
+                        if (MASKED && own_mk != 0) build_tables_masked<KP>(WT, S.total, own, k, a.wtab, lane, own_mk);
+                        else build_tables<KP>(WT, S.total, has_own, own, k, a.wtab, lane);
                         gsum_n = __ldg(m.bg.gsum + n);
                         gmax_n = __ldg(m.bg.gmax + n);
                     } else {
@@ -421,7 +455,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                         // those sites (fused over the alphabet), plus every base of the held-out sequence
                         for (int e = lane; e < 4 * k; e += 32) {
                             int c = S.total[e];
-                            if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3)) c -= 1;
+                            if (has_own && (int)((own >> (2 * (e >> 2))) & 3u) == (e & 3) && !(MASKED && ((own_mk >> (2 * (e >> 2))) & 1u))) c -= 1;
                             WT.lgcol[e] = c;
                         }
                         __syncwarp();
@@ -434,6 +468,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                             F[b] = bsum[b] - (has_own ? cn[b] : 0) - __reduce_add_sync(FULL, s) + cn[b];
                             fs += F[b];
                         }
+                        if (MASKED && masked_n >= 0) fs += __ldg(a.maskcnt + n); // its own symbols outside the alphabet (fs:953, fs:117)
                         const double den = __dadd_rn((double)fs, m.alpha_pc);
                         double q[4];
 #pragma unroll
@@ -452,11 +487,21 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                             qtab[e] = (e >> 2) < k ? (b == 0 ? q[0] : b == 1 ? q[1] : b == 2 ? q[2] : q[3]) : 1.0;
                         }
                         __syncwarp();
+                        const uint8_t *seq_n = nullptr;
+                        if (MASKED && masked_n >= 0) { // symbol counts of the held-out sequence (candidate scratch is free here)
+                            seq_n = m.ascii + __ldg(m.off + n);
+                            for (int e = lane; e < 64; e += 32) cand_w[e] = 0;
+                            __syncwarp();
+                            for (int i = lane; i < W + k - 1; i += 32) atomicAdd(&cand_w[seq_n[i] - 42], 1);
+                            __syncwarp();
+                        }
                         double bestg = 0.0;
                         for (int w0 = 0; w0 < W; w0 += 32) {
                             const int w = w0 + lane;
                             if (w < W) {
-                                const double v = exact_window<KP>(row, w, k, qtab);
+                                double v = exact_window<KP>(row, w, k, qtab);
+                                if (MASKED && masked_n >= 0 && mask_kmer(a.s.mask, a.s.row_words, n, w, k) != 0)
+                                    v = masked_background_window(seq_n, w, k, q, cand_w);
                                 gbuf[w] = v;
                                 bestg = fmax(bestg, v);
                             }
@@ -480,7 +525,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                     int best_w;
                     int n_cand = -1;
                     bool slow = false;
-                    if (phase == MPH_GREEDY && m.greedy_fast_ok) { // only the best candidate matters: rank, re-score, compare
+                    if (phase == MPH_GREEDY && m.greedy_fast_ok && !(MASKED && masked_n >= 0)) { // only the best candidate matters: rank, re-score, compare
                         if (m.data_bg) fixed_point_tables<KP>(WT, lane);
                         double pbest;
                         if (pick_unique_argmax<KP>(WT, row, W, k, lane, pbest, best_w)) {
@@ -489,7 +534,8 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                         }
                     }
                     if (n_cand < 0) {
-                        n_cand = motif_candidates<KP>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w);
+                        n_cand = motif_candidates<KP, MASKED>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w,
+                                                              &a.s, masked_n);
                         slow = true;
                     }
                     bool take;
@@ -557,9 +603,11 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
             if (phase == MPH_GREEDY) {
                 if (first_mover < T) { // in-place sweep: later n see the new state (fs:795 reads acc): -old k-mer, +new k-mer
                     if (warp == first_mover) {
-                        if (lane < k) {
-                            if (has_own) S.total[lane * 4 + (int)((own >> (2 * lane)) & 3u)] -= 1;
-                            if (new_site >= 0) S.total[lane * 4 + (int)((neu >> (2 * lane)) & 3u)] += 1;
+                        uint64_t neu_mk = 0;
+                        if (MASKED && masked_n >= 0 && new_site >= 0) neu_mk = mask_kmer(a.s.mask, a.s.row_words, n, new_site, k);
+                        if (lane < k) { // (bases outside A,C,G,T were never counted)
+                            if (has_own && !(MASKED && ((own_mk >> (2 * lane)) & 1u))) S.total[lane * 4 + (int)((own >> (2 * lane)) & 3u)] -= 1;
+                            if (new_site >= 0 && !(MASKED && ((neu_mk >> (2 * lane)) & 1u))) S.total[lane * 4 + (int)((neu >> (2 * lane)) & 3u)] += 1;
                         }
                         if (m.data_bg && has_own != (new_site >= 0) && lane < 4) { // the sequence gained or lost its site
                             const int d = lane == 0 ? cn[0] : lane == 1 ? cn[1] : lane == 2 ? cn[2] : cn[3];
@@ -639,8 +687,8 @@ static __global__ void __launch_bounds__(32) roulette_kernel(const RouletteArgs 
     const int W = __ldg(a.s.len + a.heldout) - a.k + 1;
     double best_l;
     int best_w;
-    const int n_cand = motif_candidates<KP>(WT, row, W, a.k, r.cutoff, exp2(r.cutoff) * (1.0 - 0x1p-30), r.cand_l, r.cand_w,
-                                            lane, best_l, best_w);
+    const int n_cand = motif_candidates<KP, true>(WT, row, W, a.k, r.cutoff, exp2(r.cutoff) * (1.0 - 0x1p-30), r.cand_l, r.cand_w,
+                                                  lane, best_l, best_w, &a.s, row_masked(a.s, a.heldout) ? a.heldout : -1);
     double pwms = 0.0;
     int site = -1;
     const bool ok = motif_roulette(r.bg.g + (size_t)a.heldout * r.bg.wstride, __ldg(r.bg.gsum + a.heldout), W, r.cand_l,

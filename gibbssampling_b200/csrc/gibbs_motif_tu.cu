@@ -1,17 +1,20 @@
-// gibbssampling_b200/csrc/gibbs_motif_tu.cu -- motif_kernel<KP, T> for the 16 k-widths, one team size per translation
-// unit (-DGIBBS_MOTIF_TU_T=1|4, see _build.py): register-limited like the chain kernels, so it gets a module of its
-// own (reproducible code generation, see gibbs_chain_tu.cu).
+// gibbssampling_b200/csrc/gibbs_motif_tu.cu -- motif_kernel<KP, T, MASKED> for the 16 k-widths, one team size per
+// translation unit (-DGIBBS_MOTIF_TU_T=1|4, -DGIBBS_MOTIF_TU_MASKED=0|1, see _build.py): register-limited like the chain
+// kernels, so it gets a module of its own (reproducible code generation, see gibbs_chain_tu.cu).
 #include "gibbs_motif.cuh"
 
 #if !defined(GIBBS_MOTIF_TU_T)
 #error "compile with -DGIBBS_MOTIF_TU_T=1 or 4 (see _build.py)"
+#endif
+#if !defined(GIBBS_MOTIF_TU_MASKED)
+#define GIBBS_MOTIF_TU_MASKED 0
 #endif
 
 namespace gibbs {
 
 template <int KPV>
 static cudaError_t launch_one(const MotifArgs &m, int grid, int smem, cudaStream_t stream) {
-    auto kernel = motif_kernel<KPV, GIBBS_MOTIF_TU_T>;
+    auto kernel = motif_kernel<KPV, GIBBS_MOTIF_TU_T, (GIBBS_MOTIF_TU_MASKED != 0)>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
@@ -20,7 +23,13 @@ static cudaError_t launch_one(const MotifArgs &m, int grid, int smem, cudaStream
     return cudaGetLastError();
 }
 
+#if GIBBS_MOTIF_TU_MASKED
 #if GIBBS_MOTIF_TU_T == 4
+#define GIBBS_MOTIF_TU_NAME launch_motif_masked_t4
+#else
+#define GIBBS_MOTIF_TU_NAME launch_motif_masked_t1
+#endif
+#elif GIBBS_MOTIF_TU_T == 4
 #define GIBBS_MOTIF_TU_NAME launch_motif_t4
 #else
 #define GIBBS_MOTIF_TU_NAME launch_motif_t1

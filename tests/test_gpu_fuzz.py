@@ -100,3 +100,57 @@ def test_random_motif_sampler_case_matches_oracle(seed):
         got_pos = [[int(p)] if p >= 0 else [] for p in res.sites[c]]
         assert got_pos == [list(p) for _, p in want], f"chain {c}"
         np.testing.assert_allclose(res.scores[c], [s for s, _ in want], rtol=1e-5)
+
+
+def _masked_motif_case(seed):
+    rng = np.random.default_rng(30_000 + seed)
+    n = int(rng.integers(2, 10))
+    k = int(rng.choice([2, 3, 5, 6, 8, 11, 12, 16, 20]))
+    lo = k + int(rng.integers(0, 4))
+    hi = lo + int(rng.choice([0, 5, 30, 120, 300]))
+    alen = int(rng.choice([4, 5]))
+    symbols = "N*RY" + ("-" if alen == 4 else "")
+    frac = float(rng.choice([0.005, 0.02, 0.1, 0.3]))
+    seqs = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        q = rng.choice(list("ACGT"), size=L, p=rng.dirichlet([2.0] * 4))
+        m = rng.random(L) < frac
+        q[m] = rng.choice(list(symbols), size=int(m.sum()))
+        seqs.append("".join(q).encode())
+    pc = float(rng.choice([1e-4, 1e-2, 0.5]))
+    cutoff = float(rng.choice([-5.0, 0.0, 1.0, 4.0]))
+    team = int(rng.choice([0, 1, 4]))
+    return n, k, alen, seqs, pc, cutoff, rng.random() < 0.5, rng.dirichlet([5.0] * 4).tolist(), team, rng
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_masked_motif_sampler_case_matches_oracle(seed):
+    """The MotifSampler (m = 1, both backgrounds) over sequences with symbols outside the alphabet."""
+    n, k, alen, seqs, pc, cutoff, data, bg, team, rng = _masked_motif_case(seed)
+    alphabet = b"ATGC" if alen == 4 else b"ATGC-"
+    S = O.sources(seqs)
+    params = make_params(k, pc, alen, bg, cutoff=cutoff, sampler=_abi.GIBBS_MOTIF_SAMPLER,
+                         background=_abi.GIBBS_BG_DATA if data else _abi.GIBBS_BG_FIXED)
+    with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
+        try:
+            res = eng.run(params, 3, chain_id_base=seed, seed=seed + 5, want_counts=False)
+            failed = None
+        except _abi.GibbsRouletteError as e:     # a pick beyond the accumulated mass (e.g. every window masked: 0 / 0)
+            failed = e
+    for c in range(3):
+        r, keep = O.make_rng(seed=seed + 5, chain=seed + c)
+        try:
+            want, st = O.motif_step("do_motif_sampling", 1 if data else 0, S, 1, k, pc, cutoff,
+                                    pcv=None if data else O.pcv_from_acgt(bg), rng=r, alphabet=alphabet)
+        except O.OracleError as e:
+            assert failed is not None and e.code == O.ERR_ROULETTE
+            return
+        assert failed is None
+        got_pos = [[int(p)] if p >= 0 else [] for p in res.sites[c]]
+        assert got_pos == [list(p) for _, p in want], f"chain {c}"
+        want_s = np.array([v for v, _ in want])
+        fin = np.isfinite(want_s)
+        np.testing.assert_allclose(res.scores[c][fin], want_s[fin], rtol=1e-5)
+        assert np.array_equal(res.scores[c][~fin], want_s[~fin], equal_nan=True)

@@ -140,8 +140,10 @@ def test_symbol_errors_and_unsupported_combinations():
         assert ok.sites.shape == (2, 2)
         data = eng.run(make_params(4, 1e-4, 4, BG, background=_abi.GIBBS_BG_DATA), 2, seed=5)   # built (see below)
         assert data.sites.shape == (2, 2)
-        with pytest.raises(_abi.GibbsUnsupportedError):
-            eng.run(make_params(4, 1e-4, 4, BG, sampler=_abi.GIBBS_MOTIF_SAMPLER, cutoff=0.0), 1)
+        motif = eng.run(make_params(4, 1e-4, 4, BG, sampler=_abi.GIBBS_MOTIF_SAMPLER, cutoff=0.0), 2, seed=5)   # built (see below)
+        assert motif.sites.shape == (2, 2)
+        with pytest.raises(_abi.GibbsUnsupportedError):           # two sites per sequence need ACGT-only sequences
+            eng.run(make_params(4, 1e-4, 4, BG, sampler=_abi.GIBBS_MOTIF_SAMPLER, cutoff=0.0, motif_amount=2), 1)
     with GibbsEngine([b"ACGTACGT", b"ACGTACGT"]) as eng:          # no masked symbol: everything stays available
         eng.run(make_params(4, 1e-4, 5, BG, background=_abi.GIBBS_BG_DATA), 1)
 
@@ -200,3 +202,99 @@ def test_data_derived_background_with_masked_symbols(case):
     rng, keep = O.make_rng(uniforms=u[0])
     score, pos, _ = O.site_step("do_site_sampling", S, k, 1e-4, rng=rng, alphabet=alphabet)
     assert inj.sites[0].tolist() == pos.tolist()
+
+
+MOTIF_CASES = [  # (seed, n, lo, hi, k, other symbols, fraction, alphabet_size, pc, cutoff)
+    (11, 6, 30, 60, 6, "NRY*", 0.05, 5, 1e-4, 1.0),
+    (12, 9, 50, 90, 8, "N", 0.02, 5, 1e-2, 0.0),      # low cut-off: long candidate lists next to masked windows
+    (13, 5, 25, 40, 7, "N-W", 0.10, 4, 1e-4, 1.0),    # Gap outside an alphabet of 4
+    (14, 8, 200, 260, 12, "NB", 0.006, 5, 1e-4, 2.0), # 16-window chunks: unmasked rows take the ranking pass, masked ones the list
+    (15, 4, 12, 20, 3, "N", 0.30, 5, 1.0, -1.0),      # heavy masking, negative cut-off (the sequential roulette walk)
+]
+
+
+def _motif_same(got_sites, got_scores, want):
+    assert [([int(x)] if x >= 0 else []) for x in got_sites] == [p for _, p in want]
+    np.testing.assert_allclose(got_scores, [v for v, _ in want], rtol=LOG2_RTOL)
+
+
+@pytest.mark.parametrize("team", [1, 4])
+@pytest.mark.parametrize("case", MOTIF_CASES, ids=lambda c: f"s{c[0]}_n{c[1]}_k{c[4]}")
+def test_motif_sampler_with_masked_symbols(case, team):
+    """doMotifSamplingWithPCV (fs:876) over sequences that hold symbols outside the alphabet: a window over one is never a
+    candidate (log2 0 = -inf), its background entry has probability 0, a site that covers one counts it in a dead row."""
+    seed, n, lo, hi, k, sym, frac, alen, pc, cutoff = case
+    seqs = _seqs(seed, n, lo, hi, sym, frac)
+    S = O.sources(seqs)
+    pcv = O.pcv_from_acgt(BG)
+    alphabet = _alphabet(alen)
+    n_chains = 4
+    with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
+        params = make_params(k, pc, alen, BG, cutoff=cutoff, sampler=_abi.GIBBS_MOTIF_SAMPLER)
+        res = eng.run(params, n_chains, chain_id_base=11, seed=90 + seed, want_counts=False)
+        for c in range(n_chains):
+            rng, _ = O.make_rng(seed=90 + seed, chain=11 + c)
+            want, _ = O.motif_step("do_motif_sampling", 0, S, 1, k, pc, cutoff, pcv=pcv, rng=rng, alphabet=alphabet)
+            _motif_same(res.sites[c], res.scores[c], want)
+        # the roulette primitive on states that include site-less sequences and sites over masked symbols
+        rng_np = np.random.default_rng(seed)
+        for trial in range(3):
+            sites = np.array([rng_np.integers(0, len(q) - k + 1) for q in seqs], dtype=np.int32)
+            if trial == 2:
+                sites[0] = -1
+            for h in (0, n - 1):
+                pfm = np.zeros((O.NSLOT, k), dtype=np.int32)
+                for i, p0 in enumerate(sites):
+                    if i != h and p0 >= 0:
+                        for j in range(k):
+                            pfm[seqs[i][p0 + j] - 42, j] += 1
+                ppm = O.ppm_of_pfm(pfm, n - 1, pc, alphabet)
+                cand = O.candidates(seqs[h], k, 1, cutoff, pcv, ppm, alphabet)
+                weights = [cd[0] for cd in cand]
+                if not (sum(weights) > 0.0) or min(weights) < 0.0:
+                    continue                                   # (no mass / negative weights: the walk is exercised by the restarts above)
+                for u in (0.0, 0.003, 0.5, 0.999, float(rng_np.random())):
+                    idx = O.roulette(weights, u)
+                    pwms, site = eng.pick_roulette(sites, h, params, u)
+                    assert ([site] if site >= 0 else []) == cand[idx][1], (trial, h, u)
+                    assert pwms == pytest.approx(cand[idx][0], rel=LOG2_RTOL)
+
+
+@pytest.mark.parametrize("team", [1, 4])
+@pytest.mark.parametrize("case", MOTIF_CASES[:4], ids=lambda c: f"s{c[0]}_n{c[1]}_k{c[4]}")
+def test_data_background_motif_sampler_with_masked_symbols(case, team):
+    """doMotifSampling (fs:1034): the background of a held-out sequence takes the others' alphabet symbols outside their
+    sites (fuse keeps alphabet rows, fs:67-69) plus EVERY symbol of the held-out sequence (fs:953) -- its symbols outside
+    the alphabet count in the denominator (fs:117)."""
+    seed, n, lo, hi, k, sym, frac, alen, pc, cutoff = case
+    seqs = _seqs(seed, n, lo, hi, sym, frac)
+    S = O.sources(seqs)
+    alphabet = _alphabet(alen)
+    n_chains = 4
+    with GibbsEngine(seqs) as eng:
+        eng.set_team_warps(team)
+        params = make_params(k, pc, alen, [0.25] * 4, cutoff=cutoff, sampler=_abi.GIBBS_MOTIF_SAMPLER, background=_abi.GIBBS_BG_DATA)
+        res = eng.run(params, n_chains, chain_id_base=3, seed=40 + seed, want_counts=False)
+        for c in range(n_chains):
+            rng, _ = O.make_rng(seed=40 + seed, chain=3 + c)
+            want, _ = O.motif_step("do_motif_sampling", 1, S, 1, k, pc, cutoff, rng=rng, alphabet=alphabet)
+            _motif_same(res.sites[c], res.scores[c], want)
+
+
+def test_motif_sampler_masked_set_equals_clean_set_when_masks_are_never_touched():
+    """A set whose only symbol outside the alphabet sits in ONE sequence: every other sequence's updates must equal what the
+    plain instantiation computes on the same sequences -- checked through the whole-restart result against the oracle on a
+    larger shape (1 masked base in 40 x 150 bp)."""
+    rng = np.random.default_rng(5)
+    seqs = ["".join(rng.choice(list("ACGT"), size=150)).encode() for _ in range(40)]
+    s7 = bytearray(seqs[7]); s7[75] = ord("N"); seqs[7] = bytes(s7)
+    S = O.sources(seqs)
+    pcv = O.pcv_from_acgt(BG)
+    k, pc, cutoff = 10, 1e-4, 1.0
+    with GibbsEngine(seqs) as eng:
+        res = eng.run(make_params(k, pc, 5, BG, cutoff=cutoff, sampler=_abi.GIBBS_MOTIF_SAMPLER), 3, seed=8, want_counts=False)
+    for c in range(3):
+        r, _ = O.make_rng(seed=8, chain=c)
+        want, _ = O.motif_step("do_motif_sampling", 0, S, 1, k, pc, cutoff, pcv=pcv, rng=r)
+        _motif_same(res.sites[c], res.scores[c], want)
