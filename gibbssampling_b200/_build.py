@@ -97,6 +97,9 @@ def _jobs(nvcc: str, verbose: bool) -> list[tuple[str, list[str]]]:
         obj = os.path.join(OBJ_DIR, f"launch_motif_masked_t{t}.o")   # sets with symbols outside A,C,G,T
         jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [f"-DGIBBS_MOTIF_TU_T={t}", "-DGIBBS_MOTIF_TU_MASKED=1", "-c", "-o", obj,
                                                             MOTIF_SOURCE]))
+    for t in (8, 16):   # the hand-over stages of the MotifSampler (A,C,G,T-only sets)
+        obj = os.path.join(OBJ_DIR, f"launch_motif_t{t}.o")
+        jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [f"-DGIBBS_MOTIF_TU_T={t}", "-c", "-o", obj, MOTIF_SOURCE]))
     obj = os.path.join(OBJ_DIR, "launch_motif2.o")
     jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + ["-c", "-o", obj, MOTIF2_SOURCE]))
     for c in (4, 8):

@@ -10,6 +10,7 @@
 #include "gibbs_motif2.cuh"
 #include "gibbs_drift.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -45,6 +46,8 @@ GIBBS_CHAIN_TU(launch_init_smem);
 #undef GIBBS_CHAIN_TU
 cudaError_t launch_motif_t4(const MotifArgs &m, int grid, int smem, cudaStream_t stream); // gibbs_motif_tu.cu
 cudaError_t launch_motif_t1(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
+cudaError_t launch_motif_t8(const MotifArgs &m, int grid, int smem, cudaStream_t stream);  // hand-over stages
+cudaError_t launch_motif_t16(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
 cudaError_t launch_motif_masked_t4(const MotifArgs &m, int grid, int smem, cudaStream_t stream); // symbols outside A,C,G,T
 cudaError_t launch_motif_masked_t1(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
 cudaError_t launch_motif2(const Motif2Args &q, int grid, int smem, cudaStream_t stream); // gibbs_motif2_tu.cu
@@ -622,10 +625,48 @@ BgTables bg_tables(const gibbs_handle *h) {
     return b;
 }
 
-// warps per chain of the MotifSampler kernel
+// warps per chain of the MotifSampler kernel (first stage)
 int motif_team(const gibbs_handle *h) {
     if (h->team_warps == 1) return 1;
     return (h->n >= 4 && team_smem_bytes(h->row_words, 4) <= 200 * 1024) ? 4 : 1;
+}
+
+// The stages of a MotifSampler run: teams of 4 warps for every restart, then -- A,C,G,T-only sets, automatic team size --
+// the restarts still running are handed over to teams of 8 and of 16 warps as in launch_chain_kp (same thresholds).
+struct MotifStage { int team, pause_below; };
+int motif_stages(const gibbs_handle *h, int n_chains, MotifStage *stages) {
+    const int sms = h->sm_count, N = h->n;
+    auto fits = [&](int t) { return N >= t && team_smem_bytes(h->row_words, t) <= 200 * 1024; };
+    int n_stages = 0;
+    const int team = motif_team(h);
+    if (team != 4 || h->n_masked > 0 || h->team_warps != 0) {
+        stages[n_stages++] = {team, 0};
+        return n_stages;
+    }
+    int first = n_chains > h->opt_stage2_at * sms ? 4 : n_chains > h->opt_stage3_at * sms ? 8 : 16;
+    if (first == 16 && !fits(16)) first = 8;
+    if (first == 8 && !fits(8)) first = 4;
+    stages[n_stages++] = {first, 0};
+    if (first == 4 && fits(8)) {
+        stages[n_stages - 1].pause_below = h->opt_stage2_at * sms;
+        stages[n_stages++] = {8, 0};
+    }
+    if (stages[n_stages - 1].team == 8 && fits(16)) {
+        stages[n_stages - 1].pause_below = h->opt_stage3_at * sms;
+        stages[n_stages++] = {16, 0};
+    }
+    return n_stages;
+}
+// warps that hold a scratch list at once, over the stages of a run (the lists are indexed by CTA)
+size_t motif_scratch_warps(const gibbs_handle *h, int n_chains) {
+    MotifStage stages[3];
+    const int n_stages = motif_stages(h, n_chains, stages);
+    size_t most = 0;
+    for (int st = 0; st < n_stages; ++st) {
+        const size_t grid = st == 0 ? (size_t)n_chains : (size_t)stages[st - 1].pause_below;
+        most = std::max(most, grid * (size_t)stages[st].team);
+    }
+    return most;
 }
 
 template <int KPV>
@@ -637,13 +678,38 @@ int32_t launch_motif_kp(gibbs_handle *h, MotifArgs m) {
         if (rc) return rc;
         m.init_done = (before & GIBBS_PHASE_INIT) && !(m.c.phase_mask & GIBBS_PHASE_INIT);
     }
-    const int team = motif_team(h);
-    const int smem = team_smem_bytes(m.c.s.row_words, team);
-    if (m.c.s.mask != nullptr)
-        CUDA_TRY(team == 4 ? launch_motif_masked_t4(m, m.c.n_chains, smem, h->stream) : launch_motif_masked_t1(m, m.c.n_chains, smem, h->stream));
-    else
-        CUDA_TRY(team == 4 ? launch_motif_t4(m, m.c.n_chains, smem, h->stream) : launch_motif_t1(m, m.c.n_chains, smem, h->stream));
-    h->run_team = team;
+    MotifStage stages[3];
+    const int n_stages = motif_stages(h, m.c.n_chains, stages);
+    CUDA_TRY(h->ctl.reserve(8));
+    const int32_t ctl0[8] = {m.c.n_chains, 0, 0, 0, 0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h->ctl.p, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, h->stream));
+    m.c.active = h->ctl.p;
+    if (n_stages > 1) {
+        CUDA_TRY(h->resume.reserve((size_t)m.c.n_chains));
+        CUDA_TRY(h->pending.reserve((size_t)(n_stages - 1) * (size_t)m.c.n_chains));
+        m.c.resume = h->resume.p;
+    }
+    for (int st = 0; st < n_stages; ++st) {
+        MotifArgs b = m;
+        const int team = stages[st].team;
+        b.c.pause_below = stages[st].pause_below;
+        b.c.from_list = st > 0;
+        b.c.pending_in = st > 0 ? h->pending.p + (size_t)(st - 1) * m.c.n_chains : nullptr;
+        b.c.pending_in_n = st > 0 ? h->ctl.p + st : nullptr;
+        b.c.pending_out = st + 1 < n_stages ? h->pending.p + (size_t)st * m.c.n_chains : nullptr;
+        b.c.pending_out_n = st + 1 < n_stages ? h->ctl.p + st + 1 : nullptr;
+        const int grid = st == 0 ? m.c.n_chains : stages[st - 1].pause_below; // at most that many restarts were paused
+        const int smem = team_smem_bytes(m.c.s.row_words, team);
+        if (m.c.s.mask != nullptr)
+            CUDA_TRY(team == 4 ? launch_motif_masked_t4(b, grid, smem, h->stream) : launch_motif_masked_t1(b, grid, smem, h->stream));
+        else
+            CUDA_TRY(team == 16 ? launch_motif_t16(b, grid, smem, h->stream)
+                     : team == 8 ? launch_motif_t8(b, grid, smem, h->stream)
+                     : team == 4 ? launch_motif_t4(b, grid, smem, h->stream) : launch_motif_t1(b, grid, smem, h->stream));
+        if (st > 0) h->run_extra_launches += 1;
+    }
+    h->run_team = stages[0].team;
+    h->run_stages = n_stages;
     return GIBBS_OK;
 }
 
@@ -1101,10 +1167,10 @@ int32_t gibbs_run_device(gibbs_handle *h, const gibbs_params *p, int32_t n_chain
             h->bg_valid = false; // the fixed-background tables are not used; only the window stride is
             h->bg_wstride = h->max_len - p->k + 1;
             if (h->n_masked > 0 && h->bg_wstride < 64) h->bg_wstride = 64; // the candidate scratch doubles as a 49-slot symbol-count table
-            CUDA_TRY(h->gbuf.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride));
+            CUDA_TRY(h->gbuf.reserve(motif_scratch_warps(h, n_chains) * h->bg_wstride));
         }
-        CUDA_TRY(h->cand_l.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride)); // one scratch list per warp
-        CUDA_TRY(h->cand_w.reserve((size_t)n_chains * motif_team(h) * h->bg_wstride));
+        CUDA_TRY(h->cand_l.reserve(motif_scratch_warps(h, n_chains) * h->bg_wstride)); // one scratch list per warp
+        CUDA_TRY(h->cand_w.reserve(motif_scratch_warps(h, n_chains) * h->bg_wstride));
         CUDA_TRY(h->err_flag.reserve(1));
         CUDA_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int32_t), h->stream));
         MotifArgs m{};

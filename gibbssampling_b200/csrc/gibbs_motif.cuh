@@ -355,14 +355,21 @@ constexpr int MOTIF_BSUM_OFFSET = 2144; // 4 ints in the slack of the team's fix
 // symbol is counted in a dead row when it lies inside a site (fs:211-215), a window over one scores 0 and its
 // background-only probability is 0 (the pcv of a symbol outside the alphabet, fs:115-119); the held-out sequence's own
 // such symbols enter the denominator of the data-derived background (fs:953 adds every symbol, fs:117 sums all 49 slots).
+// Straggler hand-over as in chain_kernel: restarts need 5 to 20+ greedy sweeps, so once few of them are still running they
+// pause at a sweep boundary (phase and sweep count in a.resume, the chain in a.pending_out) and the next launch on the
+// stream continues them with teams of 8, then 16 warps. Scratch lists are indexed by CTA, not by chain.
 template <int KP, int T, bool MASKED = false>
-__global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_BLOCKS : 2)) motif_kernel(const MotifArgs m) {
+__global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_BLOCKS : T == 8 ? 2 : 1)) motif_kernel(const MotifArgs m) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int THREADS = 32 * T;
     constexpr int R = (2 * T < 4) ? 4 : 2 * T;
     const ChainArgs &a = m.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chain = blockIdx.x;
+    int chain = blockIdx.x;
+    if (a.from_list) { // continuing paused restarts: one CTA per list entry
+        if ((int)blockIdx.x >= *a.pending_in_n) return;
+        chain = a.pending_in[blockIdx.x];
+    }
     const TeamSmem S = carve_smem(smem_raw, T);
     const WarpTables WT = warp_tables(S, warp);
     require_aligned_tables(WT);
@@ -371,9 +378,9 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
     int32_t *sites = a.sites + (size_t)chain * N;
     double *pw = a.scores + (size_t)chain * N; // PWMS of the MotifIndex state
     double *hv = a.hv + (size_t)chain * N;
-    double *cand_l = m.cand_l + ((size_t)chain * T + warp) * m.bg.wstride;
-    int32_t *cand_w = m.cand_w + ((size_t)chain * T + warp) * m.bg.wstride;
-    double *gbuf = m.data_bg ? m.gbuf + ((size_t)chain * T + warp) * m.bg.wstride : nullptr;
+    double *cand_l = m.cand_l + ((size_t)blockIdx.x * T + warp) * m.bg.wstride;
+    int32_t *cand_w = m.cand_w + ((size_t)blockIdx.x * T + warp) * m.bg.wstride;
+    double *gbuf = m.data_bg ? m.gbuf + ((size_t)blockIdx.x * T + warp) * m.bg.wstride : nullptr;
     const uint64_t chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
     const double raw_gate = exp2(a.cutoff) * (1.0 - 0x1p-30);
 
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
     int st_sweeps = 0, capped = 0;
     uint32_t vbase = 0;
 
-    if (m.init_done) { // the random starts ran in their own kernel (gibbs_api.cu, launch_random_starts): the state is
+    if (m.init_done && !a.from_list) { // the random starts ran in their own kernel (gibbs_api.cu, launch_random_starts): the state is
         // SiteSampler.getPWMOfRandomStarts[WithBPV] |> createMotifIndex prob [position] (fs:876-877, fs:993-994)
         for (int n = tid; n < N; n += THREADS) pw[n] = log2_ref(__ldcg(hv + n));
         team_sync<T>();
@@ -395,8 +402,16 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
     int phase = MPH_STOCH;
     while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
     int sweeps_in_phase = 0;
+    bool resumed = false, paused = false;
+    if (a.from_list) {
+        const int r = a.resume[chain];
+        phase = r & 255;
+        sweeps_in_phase = r >> 8;
+        resumed = true;
+    }
     while (phase != MPH_DONE) {
-        if (phase == MPH_STOCH || sweeps_in_phase == 0) {
+        if (phase == MPH_STOCH || sweeps_in_phase == 0 || resumed) {
+            resumed = false;
             site_counts<KP, T>(a.s, sites, -1, k, SHIFT_NONE, S.total, S.lut, S.fix, tid);
             if (m.data_bg) {
                 if (tid < 4) bsum[tid] = 0;
@@ -637,11 +652,21 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
             ++phase;
             while (phase < MPH_DONE && !((a.phase_mask >> (phase == MPH_STOCH ? 4 : 5)) & 1)) ++phase;
         }
+        // sweep boundary: when few restarts are still running, hand this one over to the wide-team launch
+        if (phase != MPH_DONE && a.pause_below > 0) {
+            if (tid == 0) S.flags[2 * T] = (*(volatile int32_t *)a.active <= a.pause_below) ? 1 : 0;
+            team_sync<T>();
+            if (S.flags[2 * T]) {
+                paused = true;
+                break;
+            }
+        }
     }
     if (tid == 0) // the ring always has R rows in flight: let them land before the CTA exits
         for (int i = 0; i < R; ++i) ring.wait(vbase + (uint32_t)i);
     team_sync<T>();
-    for (int n = tid; n < N; n += THREADS) hv[n] = __ldcg(pw + n);
+    if (!paused)
+        for (int n = tid; n < N; n += THREADS) hv[n] = __ldcg(pw + n);
     if (lane == 0) {
         atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
         atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
@@ -649,11 +674,17 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
         atomicAdd(a.stats + ST_SPECULATED, st_spec);
     }
     if (tid == 0) {
-        double sum = 0.0;
-        for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(pw + n));
-        a.sums[chain] = sum;
         atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
         atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
+        if (paused) {
+            a.resume[chain] = phase | (sweeps_in_phase << 8);
+            a.pending_out[atomicAdd(a.pending_out_n, 1)] = chain;
+        } else {
+            double sum = 0.0;
+            for (int n = 0; n < N; ++n) sum = __dadd_rn(sum, __ldcg(pw + n));
+            a.sums[chain] = sum;
+            if (a.active) atomicSub(a.active, 1);
+        }
     }
 }
 

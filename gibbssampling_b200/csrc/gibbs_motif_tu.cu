@@ -4,7 +4,7 @@
 #include "gibbs_motif.cuh"
 
 #if !defined(GIBBS_MOTIF_TU_T)
-#error "compile with -DGIBBS_MOTIF_TU_T=1 or 4 (see _build.py)"
+#error "compile with -DGIBBS_MOTIF_TU_T=1, 4, 8 or 16 (see _build.py)"
 #endif
 #if !defined(GIBBS_MOTIF_TU_MASKED)
 #define GIBBS_MOTIF_TU_MASKED 0
@@ -29,6 +29,10 @@ static cudaError_t launch_one(const MotifArgs &m, int grid, int smem, cudaStream
 #else
 #define GIBBS_MOTIF_TU_NAME launch_motif_masked_t1
 #endif
+#elif GIBBS_MOTIF_TU_T == 16
+#define GIBBS_MOTIF_TU_NAME launch_motif_t16
+#elif GIBBS_MOTIF_TU_T == 8
+#define GIBBS_MOTIF_TU_NAME launch_motif_t8
 #elif GIBBS_MOTIF_TU_T == 4
 #define GIBBS_MOTIF_TU_NAME launch_motif_t4
 #else

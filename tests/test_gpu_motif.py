@@ -201,3 +201,36 @@ def test_greedy_ranking_pass_equals_the_all_windows_candidate_list(shape, data):
     assert fast.sites.tolist() == exact.sites.tolist()
     assert fast.scores.tobytes() == exact.scores.tobytes()
     assert fast.sums.tobytes() == exact.sums.tobytes()
+
+
+@pytest.mark.parametrize("data", [False, True], ids=["fixed", "data"])
+@pytest.mark.parametrize("shape", [(20, 60, 40, 6, 1.0), (40, 150, None, 10, 0.0)], ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
+def test_handover_stages_equal_one_warp_per_restart(shape, data):
+    """More restarts than two per SM: the run starts with teams of 4 warps, the restarts still running when few are left pause at
+    a sweep boundary and continue on teams of 8, then 16 warps (motif_stages, gibbs_api.cu). Every restart must end exactly
+    where the one-warp kernel ends, and the device-side restart loop must return the same array."""
+    n, L, Lmin, k, cutoff = shape
+    ps = planted_motif_set(n, L, k, seed=21, min_length=Lmin)
+    seqs = ps.sequences()
+    bg = background_of(ps.ascii, 1e-4, 5)
+    params = make_params(k, 1e-4, 5, bg, cutoff=cutoff, sampler=_abi.GIBBS_MOTIF_SAMPLER,
+                         background=_abi.GIBBS_BG_DATA if data else _abi.GIBBS_BG_FIXED)
+    n_chains = 700
+    with GibbsEngine(seqs) as eng:
+        staged = eng.run(params, n_chains, chain_id_base=5, seed=13, want_counts=False)
+        best_staged = eng.fetch_best(n_chains - 1)
+        eng.set_option(_abi.GIBBS_OPT_STAGE2_AT, 4)         # hand over earlier: more restarts travel through all three stages
+        eng.set_option(_abi.GIBBS_OPT_STAGE3_AT, 3)
+        early = eng.run(params, n_chains, chain_id_base=5, seed=13, want_counts=False)
+        eng.set_team_warps(1)
+        single = eng.run(params, n_chains, chain_id_base=5, seed=13, want_counts=False)
+        best_single = eng.fetch_best(n_chains - 1)
+    assert staged.stats["kernel_launches"] > single.stats["kernel_launches"]
+    for got in (staged, early):
+        assert got.sites.tolist() == single.sites.tolist()
+        assert got.scores.tobytes() == single.scores.tobytes()
+        assert got.sums.tobytes() == single.sums.tobytes()
+        assert got.stats["site_updates"] == single.stats["site_updates"]
+        assert got.stats["sweeps"] == single.stats["sweeps"]
+    assert best_staged.restart == best_single.restart
+    assert best_staged.sites.tolist() == best_single.sites.tolist()
