@@ -32,6 +32,11 @@ def _bg_of(alphabet: Sequence, pcv: ProbabilityCompositeVector) -> list[float]:
             _abi.GIBBS_ERR_UNSUPPORTED,
             f"alphabet lacks {missing}: windows over those bases would score 0 (fs:283-287); "
             "the 2-bit GPU path needs A, C, G, T in the alphabet")
+    extra = sorted(chr(c) for c in codes if chr(c) not in "ACGT-")
+    if extra:   # the library takes a fifth alphabet member to be Gap (include/gibbs_b200.h, alphabet_size)
+        raise _abi.GibbsUnsupportedError(
+            _abi.GIBBS_ERR_UNSUPPORTED,
+            f"alphabet members {extra} besides A, C, G, T and Gap would have PWM rows of their own (fs:283-287); not built")
     return [float(pcv[ch]) for ch in "ACGT"]
 
 
@@ -89,12 +94,14 @@ def _run_phases(phase_mask: int, motifLength: int, pseudoCount: float, alphabet,
 # ---------------------------------------------------------------------------------------------
 # the reference's functions
 # ---------------------------------------------------------------------------------------------
-def getBestPWMSsWithBPV(motifLength: int, pseudoCount: float, alphabet, sources, pcv, positions: Sequence[int],
-                        heldOut: int, *, engine: Optional[GibbsEngine] = None) -> tuple[float, int]:
-    """fs:301-314 applied to sources.[heldOut] with the leave-one-out PPM of `positions` (fs:392-398).
+def bestPWMSOfHeldOutWithBPV(motifLength: int, pseudoCount: float, alphabet, sources, pcv, positions: Sequence[int],
+                             heldOut: int, *, engine: Optional[GibbsEngine] = None) -> tuple[float, int]:
+    """One site update: getBestPWMSsWithBPV (fs:301-314) applied to sources.[heldOut] with the leave-one-out PPM of
+    `positions`, i.e. the body of the loop at fs:392-398.
 
-    The reference takes the PPM as an argument; at this boundary the PPM never leaves the GPU, so
-    the caller passes what it is built from: the other sequences' start positions.
+    Not named after the reference function on purpose: getBestPWMSsWithBPV takes (motifLength, alphabet, source, pcv,
+    positionProbabilityMatrix); at this boundary the PPM never leaves the GPU, so the caller passes what it is built
+    from -- the other sequences' start positions -- and the argument list differs.
     """
     bg = _bg_of(alphabet, pcv)
     eng, own = _engine_for(sources, engine)

@@ -221,3 +221,18 @@ def test_event_walk_equals_the_sequential_restart_loop(seed):
         b = _event_walk(sums, scores, msites, reps, motif=True)
         gotm = [MotifSampler.MotifIndex(0.0, ())] if b < 0 else MotifSampler._to_motif_array(scores[b], msites[b])
         assert str(gotm) == str(wantm), (seed, reps)
+
+
+def test_alphabet_members_the_tables_cannot_hold_are_rejected():
+    """A fifth alphabet member is taken to be Gap (the script's dnaBases, fsx:368-369); any other extra member would have a PWM
+    row of its own in the reference (fs:283-287), so the host layer refuses it instead of scoring it as a dead symbol."""
+    from gibbssampling_b200 import _abi
+    from gibbssampling_b200.CompositeVector import ProbabilityCompositeVector
+    from gibbssampling_b200.SiteSampler import _bg_of
+    pcv = ProbabilityCompositeVector.ofACGT(0.1, 0.2, 0.3, 0.4)
+    assert _bg_of(list("ATGC-"), pcv) == [0.1, 0.2, 0.3, 0.4]
+    assert _bg_of(list("ACGT"), pcv) == [0.1, 0.2, 0.3, 0.4]
+    with pytest.raises(_abi.GibbsUnsupportedError):
+        _bg_of(list("ACGTN"), pcv)
+    with pytest.raises(_abi.GibbsUnsupportedError):
+        _bg_of(list("ACG"), pcv)
