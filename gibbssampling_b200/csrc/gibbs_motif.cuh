@@ -90,18 +90,15 @@ static __global__ void bg_setup_kernel(DeviceSeqs s, int k, double q0, double q1
     gmax_i[n] = best_i;
 }
 
-// calculateNormalizedSegmentScores (fs:759-784), motifAmount = 1: the size-1 candidates, ascending
-// position, each with log2(score) > cutOff (fs:735). Written to cand_l / cand_w; returns their number.
-// Also returns the first maximum by PWMS among them (best_l = -inf when there is none).
+// calculateNormalizedSegmentScores (fs:759-784), motifAmount = 1, in two passes.
+// Pass 1 (motif_gate): every window's float64 product; the windows above a cheap gate just below 2^cutOff are compacted
+// (in window order) into cand_l (raw products) / cand_w, so that the logarithms -- ~150 instructions each, executed by the
+// whole warp whenever one lane needs one -- are taken over a dense list instead of over all W windows. Returns their number.
 // MASKED, masked_n >= 0: the sequence holds symbols outside A,C,G,T; a window over one scores 0 (PWM row 0, fs:283-287),
 // log2 0 = -inf is never above the cut-off
 template <int KP, bool MASKED = false>
-__device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint32_t *row, int W, int k, double cutoff,
-                                                double raw_gate, double *cand_l, int32_t *cand_w, int lane,
-                                                double &best_l, int &best_w, const DeviceSeqs *sq = nullptr, int masked_n = -1) {
-    // pass 1: every window's float64 product; the windows above a cheap gate just below 2^cutOff are compacted (in
-    // window order) so that the logarithms -- ~150 instructions each, executed by the whole warp whenever one lane
-    // needs one -- are taken over a dense list instead of over all W windows
+__device__ __forceinline__ int motif_gate(const WarpTables &T, const uint32_t *row, int W, int k, double raw_gate, double *cand_l,
+                                          int32_t *cand_w, int lane, const DeviceSeqs *sq = nullptr, int masked_n = -1) {
     int gated = 0;
     for (int w0 = 0; w0 < W; w0 += 32) {
         const int w = w0 + lane;
@@ -117,8 +114,14 @@ __device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint3
         gated += __popc(m);
     }
     __syncwarp();
-    // pass 2: the decision itself is made on the log (fs:735); survivors are compacted in place (a block writes only
-    // below what it has read)
+    return gated;
+}
+
+// Pass 2 (motif_logs): the decision itself is made on the log (fs:735); the size-1 candidates, ascending position, each
+// with log2(score) > cutOff, are compacted in place (a block writes only below what it has read) with their PWMS in
+// cand_l. Returns their number and the first maximum by PWMS among them (best_l = -inf when there is none).
+__device__ __forceinline__ int motif_logs(double cutoff, double *cand_l, int32_t *cand_w, int gated, int lane, double &best_l,
+                                          int &best_w) {
     int count = 0;
     double bl = -INFINITY;
     int bw = INT32_MAX;
@@ -150,6 +153,76 @@ __device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint3
     best_w = bw;
     __syncwarp();
     return count;
+}
+
+template <int KP, bool MASKED = false>
+__device__ __forceinline__ int motif_candidates(const WarpTables &T, const uint32_t *row, int W, int k, double cutoff,
+                                                double raw_gate, double *cand_l, int32_t *cand_w, int lane,
+                                                double &best_l, int &best_w, const DeviceSeqs *sq = nullptr, int masked_n = -1) {
+    const int gated = motif_gate<KP, MASKED>(T, row, W, k, raw_gate, cand_l, cand_w, lane, sq, masked_n);
+    return motif_logs(cutoff, cand_l, cand_w, gated, lane, best_l, best_w);
+}
+
+// The roulette pick of the stochastic sweep without a float64 logarithm per candidate. log2 of a gated product to 1e-6:
+// exponent + MUFU.LG2 of the float mantissa (|error| < 5e-7 for any normal product). With those weights the candidates
+// are decided (further than 1e-6 from the cut-off, else the exact path runs), their prefix sums locate the bucket of the
+// pick, and the error of any prefix -- (items + 64) * 1e-6 -- is far below a bucket width (a candidate weighs more than
+// the cut-off): when the pick clears both edges of its bucket by twice that bound the sequential float64 walk of
+// fs:746-754 must stop in the same bucket, and only that item's PWMS is computed with the reference's logarithm.
+// Needs cutOff >= 0 (no negative weights). false = undecided: the caller runs motif_logs + motif_roulette on the same list.
+__device__ __forceinline__ float log2_coarse(double s) {
+    const int hi = __double2hiint(s);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const float m = (float)__hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s)); // mantissa in [1, 2]
+    return (float)e + __log2f(m);
+}
+__device__ __forceinline__ bool motif_stoch_fast(double gsum, double cutoff, const double *cand_l, const int32_t *cand_w, int gated,
+                                                 double pick, int lane, double &pwms_out, int &site_out) {
+    constexpr double TOL = 1e-6;
+    if (gated == 0 || !(cutoff >= 0.0) || !(gsum >= 0.0)) return false;
+    const int B = (gated + 31) >> 5;
+    const int i0 = min(gated, lane * B), i1 = min(gated, i0 + B);
+    double part = 0.0;
+    bool unsure = false;
+    for (int i = i0; i < i1; ++i) {
+        const double s = cand_l[i];
+        const double l = (double)log2_coarse(s);
+        unsure |= !(s >= 0x1p-1000 && s <= 0x1p1000) || fabs(l - cutoff) <= TOL;
+        if (l > cutoff) part += l;
+    }
+    if (__ballot_sync(FULL, unsure)) return false;
+    double incl = part; // inclusive scan of the block sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const double total = gsum + __shfl_sync(FULL, incl, 31);
+    const double err = 2.0 * ((double)(gated + 64) * TOL + total * 0x1p-40);
+    const double target = pick * total;
+    if (!(target > gsum + err) || !(total < INFINITY)) return false; // background entries (1e-4 of the mass at most): exact path
+    const unsigned holds = __ballot_sync(FULL, i0 < i1 && target <= gsum + incl);
+    if (!holds) return false;
+    const int src = __ffs(holds) - 1;
+    int idx = -1;
+    if (lane == src) {
+        double acc = gsum + incl - part;
+        for (int i = i0; i < i1; ++i) {
+            const double l = (double)log2_coarse(cand_l[i]);
+            if (!(l > cutoff)) continue;
+            const double nxt = acc + l;
+            if (target <= nxt) {
+                if (target > acc + err && target < nxt - err) idx = i;
+                break;
+            }
+            acc = nxt;
+        }
+    }
+    idx = __shfl_sync(FULL, idx, src);
+    if (idx < 0) return false;
+    pwms_out = log2_ref(cand_l[idx]);
+    site_out = cand_w[idx];
+    return true;
 }
 
 // rouletteWheelSelection (fs:746-754) over [W background entries] ++ [candidates]: exact sequential
@@ -548,9 +621,13 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                             n_cand = best_l > a.cutoff ? 1 : 0; // fs:735
                         }
                     }
+                    int gated = -1;
                     if (n_cand < 0) {
-                        n_cand = motif_candidates<KP, MASKED>(WT, row, W, k, a.cutoff, raw_gate, cand_l, cand_w, lane, best_l, best_w,
-                                                              &a.s, masked_n);
+                        gated = motif_gate<KP, MASKED>(WT, row, W, k, raw_gate, cand_l, cand_w, lane, &a.s, masked_n);
+                        if (phase != MPH_STOCH || !m.roulette_scan_ok) {
+                            n_cand = motif_logs(a.cutoff, cand_l, cand_w, gated, lane, best_l, best_w);
+                            gated = -1;
+                        }
                         slow = true;
                     }
                     bool take;
@@ -567,8 +644,12 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                         } else {
                             u = ((int64_t)d < a.uniforms_per_chain) ? __ldg(a.uniforms + (size_t)chain * a.uniforms_per_chain + d) : 0.0;
                         }
-                        const bool ok = motif_roulette(g_n, gsum_n, W, cand_l, cand_w, n_cand, u, lane, new_pw, new_site,
-                                                       m.roulette_scan_ok != 0);
+                        bool ok = gated >= 0 && motif_stoch_fast(gsum_n, a.cutoff, cand_l, cand_w, gated, u, lane, new_pw, new_site);
+                        if (!ok) {
+                            if (gated >= 0) n_cand = motif_logs(a.cutoff, cand_l, cand_w, gated, lane, best_l, best_w);
+                            ok = motif_roulette(g_n, gsum_n, W, cand_l, cand_w, n_cand, u, lane, new_pw, new_site,
+                                                m.roulette_scan_ok != 0);
+                        }
                         if (!ok) {
                             if (lane == 0) atomicExch(m.error, 1);
                             new_pw = pw_n;
