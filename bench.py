@@ -288,6 +288,9 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
     host_off.numpy()[:] = ps.offsets
 
     eng = GibbsEngine(ps.sequences(), device=local_rank)
+    for item in args.opt:                    # measurement switches (gibbs_set_option): none changes a result
+        name, _, value = item.partition("=")
+        eng.set_option(getattr(_abi, "GIBBS_OPT_" + name.upper()), int(value))
     stream = torch.cuda.Stream()            # a real (non-NULL) stream shared by torch events and the library
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
@@ -492,6 +495,8 @@ def main() -> None:
                     help="reference family of the step; bpv = the BASELINE.json workload (the only one the driver runs)")
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="gibbs_set_option switch for A/B measurements, e.g. --opt coop=0 (include/gibbs_b200.h, GIBBS_OPT_*)")
     ap.add_argument("--no-families", action="store_true", help="skip the short runs of the other reference families")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
