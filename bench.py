@@ -452,7 +452,8 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
             "measurement": {"l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event window; the packed "
                                   "sequences (144 KB at C2) are L2/SMEM-resident by design",
                             "timing": "CUDA events on the launch stream around each step, summed; max over ranks",
-                            "init_path": {1: "chain kernel", 2: "grid-wide kernel, global gathers", 3: "grid-wide kernel, set in shared memory"}.get(step_stats[-1]["init_path"]),
+                            "init_path": {1: "chain kernel", 2: "grid-wide kernel, global gathers", 3: "grid-wide kernel, set in shared memory",
+                                          4: "grid-wide kernel, set streamed through shared memory in tiles"}.get(step_stats[-1]["init_path"]),
                             "clock_sampler": "one nvidia-smi process on rank 0 for all GPUs of the job"},
             "window_scores_per_step": g_windows / args.steps, "site_updates_per_step": g_updates / args.steps,
             "sweeps_per_chain": g_sweeps / (args.steps * chains * world), "exact_rescans_per_step": g_rescans / args.steps,

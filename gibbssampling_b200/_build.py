@@ -88,7 +88,7 @@ def _jobs(nvcc: str, verbose: bool) -> list[tuple[str, list[str]]]:
         jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [
             f"-DGIBBS_TU_NAME={name}", f"-DGIBBS_TU_T={team}", f"-DGIBBS_TU_MASKED={masked}", f"-DGIBBS_TU_DRIFT={drift}",
             "-DGIBBS_TU_INIT_ONLY=1", "-c", "-o", obj, CHAIN_SOURCE]))
-    for kind, name in enumerate(("launch_init_wide", "launch_init_wide_drift", "launch_init_smem")):
+    for kind, name in enumerate(("launch_init_wide", "launch_init_wide_drift", "launch_init_smem", "launch_init_tiled")):
         obj = os.path.join(OBJ_DIR, name + ".o")
         jobs.append((obj, [nvcc] + COMMON_FLAGS + extra + [f"-DGIBBS_INIT_TU_KIND={kind}", "-c", "-o", obj, INIT_SOURCE]))
     for t in (4, 1):

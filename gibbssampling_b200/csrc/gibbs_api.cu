@@ -44,6 +44,7 @@ GIBBS_CHAIN_TU(launch_init_wide);       // gibbs_init_tu.cu: the grid-wide rando
 GIBBS_CHAIN_TU(launch_init_wide_drift);
 GIBBS_CHAIN_TU(launch_init_smem);
 #undef GIBBS_CHAIN_TU
+cudaError_t launch_init_tiled(const ChainArgs &a, int grid, int smem, cudaStream_t stream, int tile_rows); // gibbs_init_tu.cu
 cudaError_t launch_motif_t4(const MotifArgs &m, int grid, int smem, cudaStream_t stream); // gibbs_motif_tu.cu
 cudaError_t launch_motif_t1(const MotifArgs &m, int grid, int smem, cudaStream_t stream);
 cudaError_t launch_motif_t8(const MotifArgs &m, int grid, int smem, cudaStream_t stream);  // hand-over stages
@@ -174,6 +175,7 @@ struct gibbs_handle {
     int32_t opt_exact_scans = 0;       // gibbs_set_option(GIBBS_OPT_EXACT_SCANS)
     int32_t opt_stage2_at = 2, opt_stage3_at = 1; // hand-over thresholds in chains per SM (GIBBS_OPT_STAGE2_AT / _STAGE3_AT)
     int32_t opt_min_width = -1;        // GIBBS_OPT_MIN_WIDTH: -1 = automatic
+    int32_t opt_tile_rows = 0;         // GIBBS_OPT_TILE_ROWS: cap on the sequences per tile of init_tiled_kernel (0 = what fits)
     int32_t opt_cluster = 8;           // largest cluster the last hand-over stages may use: 0 (none), 4 or 8 (GIBBS_OPT_CLUSTER)
     int32_t cluster_cap[2] = {-1, -1}; // clusters of 4 / 8 CTAs the device holds at once (queried once per shape)
     int32_t cluster_cap_n = 0, cluster_cap_rw = 0, cluster_cap_k = 0;
@@ -301,18 +303,38 @@ int32_t launch_team(gibbs_handle *h, int team, bool masked, bool drift, const Ch
 template <int KPV>
 int32_t launch_random_starts(gibbs_handle *h, ChainArgs &a, bool drift) {
     const bool masked = a.s.mask != nullptr; // symbols outside A,C,G,T: inside the MASKED chain kernel
-    int init_path = GIBBS_INIT_CHAIN;
+    int init_path = GIBBS_INIT_CHAIN, tile_rows = 0;
     if ((a.phase_mask & GIBBS_PHASE_INIT) && !masked) {
         const bool smem_ok = !drift && init_smem_total_bytes(a.s.n, a.s.row_words, KPV) <= h->smem_optin;
         const bool smem_fits = smem_ok && (long long)a.n_chains * a.s.n >= (long long)h->sm_count * ISM_WARPS;
         const bool wide_fits = init_smem_bytes(a.s.row_words) <= 200 * 1024;
         const bool wide_wins = a.n_chains < 4 * h->sm_count || a.s.n >= 4096 || a.sampler == GIBBS_MOTIF_SAMPLER;
         init_path = smem_fits ? GIBBS_INIT_SMEM : (wide_fits && wide_wins) ? GIBBS_INIT_WIDE : GIBBS_INIT_CHAIN;
+        // the set streamed through shared memory in tiles: the Philox stream, fixed background, at least 256 sequences per
+        // tile; chosen by itself where the global gathers of the wide kernel are the limit (many sequences, work for every SM)
+        tile_rows = (int)(((long long)h->smem_optin - 128 - 256 - (long long)TILED_WARPS * (ism_table_bytes(KPV) + a.s.row_words * 4)) / 2
+                          / ((long long)a.s.row_words * 4));
+        const bool tile_auto = tile_rows >= 256;
+        if (tile_rows > a.s.n) tile_rows = a.s.n;
+        if (h->opt_tile_rows > 0 && tile_rows > h->opt_tile_rows) tile_rows = h->opt_tile_rows; // (tests: many small tiles)
+        const bool tiled_ok = !drift && a.rng_mode == 0 && a.sampler == GIBBS_SITE_SAMPLER && tile_rows >= 1;
+        if (init_path == GIBBS_INIT_WIDE && tiled_ok && tile_auto && a.s.n >= 4096 && (long long)a.n_chains * a.s.n >= 8LL * h->sm_count * TILED_WARPS)
+            init_path = GIBBS_INIT_TILED;
         if (h->opt_init_path == GIBBS_INIT_CHAIN) init_path = GIBBS_INIT_CHAIN;
         if (h->opt_init_path == GIBBS_INIT_WIDE && wide_fits) init_path = GIBBS_INIT_WIDE;
         if (h->opt_init_path == GIBBS_INIT_SMEM && smem_ok) init_path = GIBBS_INIT_SMEM;
+        if (h->opt_init_path == GIBBS_INIT_TILED && tiled_ok) init_path = GIBBS_INIT_TILED;
     }
     h->run_init_path = init_path;
+    if (init_path == GIBBS_INIT_TILED) {
+        const int smem = (int)init_tiled_total_bytes(tile_rows, a.s.row_words, KPV);
+        const long long items = (long long)a.n_chains * a.s.n;
+        long long grid = (items + TILED_WARPS - 1) / TILED_WARPS;
+        if (grid > h->sm_count) grid = h->sm_count;
+        CUDA_TRY(launch_init_tiled(a, (int)grid, smem, h->stream, tile_rows));
+        a.phase_mask &= ~GIBBS_PHASE_INIT; // the chain kernel continues from the state just written
+        h->run_extra_launches += 1;
+    } else
     if (init_path == GIBBS_INIT_SMEM) {
         const int smem = (int)init_smem_total_bytes(a.s.n, a.s.row_words, KPV);
         const long long items = (long long)a.n_chains * a.s.n;
@@ -1525,7 +1547,7 @@ int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value) {
     if (!h) return fail(GIBBS_ERR_ARG, "null handle");
     switch (option) {
     case GIBBS_OPT_INIT_PATH:
-        if (value < GIBBS_INIT_AUTO || value > GIBBS_INIT_SMEM) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_INIT_PATH takes GIBBS_INIT_AUTO .. GIBBS_INIT_SMEM");
+        if (value < GIBBS_INIT_AUTO || value > GIBBS_INIT_TILED) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_INIT_PATH takes GIBBS_INIT_AUTO .. GIBBS_INIT_TILED");
         h->opt_init_path = value;
         return GIBBS_OK;
     case GIBBS_OPT_EXACT_SCANS:
@@ -1534,6 +1556,10 @@ int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value) {
     case GIBBS_OPT_MIN_WIDTH:
         if (value < -1 || value > 128) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_MIN_WIDTH takes -1 (automatic) .. 128");
         h->opt_min_width = value;
+        return GIBBS_OK;
+    case GIBBS_OPT_TILE_ROWS:
+        if (value < 0) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_TILE_ROWS takes 0 (what fits) or a positive number of sequences");
+        h->opt_tile_rows = value;
         return GIBBS_OK;
     case GIBBS_OPT_CLUSTER:
         if (value != 0 && value != 4 && value != 8) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_CLUSTER takes 0, 4 or 8");

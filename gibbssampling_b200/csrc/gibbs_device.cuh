@@ -425,17 +425,25 @@ struct Hist {
 template <int KP>
 struct KmerCounter {
     static constexpr int NW = (KP > 8) ? 2 : 1; // 32-bit words of a k-mer (16 columns each)
+    // 16 < k <= 20: the second word of a k-mer holds 4 columns (one byte). The four k-mers of a quad share ONE word
+    // there (byte i = columns 16..19 of k-mer i), which is counted once per quad instead of once per k-mer (C4: k = 20).
+    static constexpr bool HI4 = (KP == 9 || KP == 10);
     using Word = typename std::conditional<(KP > 8), uint64_t, uint32_t>::type; // a k-mer as the gathers deliver it
-    uint32_t nib[NW][3][2];      // [word][base - 1][column parity]: 4-bit fields, field m = column 16 word + 2 m + parity
-    uint32_t byt[NW][3][2][2];   // [..][nibble parity h]: 8-bit fields, field q = column 16 word + 4 q + 2 h + parity
-    int quads;                   // quads since the last nibble spill (<= 3)
+    uint32_t nib[HI4 ? 1 : NW][3][2]; // [word][base - 1][column parity]: 4-bit fields, field m = column 16 word + 2 m + parity
+    uint32_t byt[NW][3][2][2];        // [..][nibble parity h]: 8-bit fields, field q = column 16 word + 4 q + 2 h + parity
+    uint32_t hq[HI4 ? 3 : 1];         // HI4: [base - 1] 2-bit fields of the shared word, field 4 i + c = column 16 + c of k-mer i
+    int quads;                        // quads since the last nibble spill (<= 3)
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int w = 0; w < NW; ++w)
 #pragma unroll
             for (int b = 0; b < 3; ++b)
 #pragma unroll
-                for (int p = 0; p < 2; ++p) nib[w][b][p] = byt[w][b][p][0] = byt[w][b][p][1] = 0;
+                for (int p = 0; p < 2; ++p) {
+                    if (!HI4 || w == 0) nib[HI4 ? 0 : w][b][p] = 0;
+                    byt[w][b][p][0] = byt[w][b][p][1] = 0;
+                }
+        if (HI4) hq[0] = hq[1] = hq[2] = 0;
         quads = 0;
     }
     __device__ __forceinline__ void spill() {
@@ -445,17 +453,24 @@ struct KmerCounter {
             for (int b = 0; b < 3; ++b)
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
-                    byt[w][b][p][0] += nib[w][b][p] & 0x0F0F0F0Fu;
-                    byt[w][b][p][1] += (nib[w][b][p] >> 4) & 0x0F0F0F0Fu;
-                    nib[w][b][p] = 0;
+                    uint32_t v;
+                    if (HI4 && w == 1) {
+                        v = (p == 0 ? hq[b] : (hq[b] >> 2)) & 0x33333333u; // (<= 3 per field: three quads)
+                    } else {
+                        v = nib[HI4 ? 0 : w][b][p];
+                        nib[HI4 ? 0 : w][b][p] = 0;
+                    }
+                    byt[w][b][p][0] += v & 0x0F0F0F0Fu;
+                    byt[w][b][p][1] += (v >> 4) & 0x0F0F0F0Fu;
                 }
+        if (HI4) hq[0] = hq[1] = hq[2] = 0;
         quads = 0;
     }
     // four k-mers (an invalid draw passes 0: base 0 everywhere, counted nowhere)
     __device__ __forceinline__ void add4(const Word x[4]) {
         if (quads == 3) spill();
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
+        for (int w = 0; w < (HI4 ? 1 : NW); ++w) {
             uint32_t f[4][3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -471,13 +486,22 @@ struct KmerCounter {
                 nib[w][b][1] += ((s3 >> 2) & 0x33333333u) + ((f[3][b] >> 2) & 0x11111111u);
             }
         }
+        if constexpr (HI4) {
+            const uint32_t h01 = __byte_perm((uint32_t)((uint64_t)x[0] >> 32), (uint32_t)((uint64_t)x[1] >> 32), 0x0040);
+            const uint32_t h23 = __byte_perm((uint32_t)((uint64_t)x[2] >> 32), (uint32_t)((uint64_t)x[3] >> 32), 0x0040);
+            const uint32_t v = __byte_perm(h01, h23, 0x5410), t = v >> 1; // byte i = columns 16..19 of k-mer i
+            hq[0] += v & ~t & 0x55555555u;
+            hq[1] += ~v & t & 0x55555555u;
+            hq[2] += v & t & 0x55555555u;
+        }
         ++quads;
     }
     // Warp totals into dst[j*4 + b] for b = 1, 2, 3 and columns j < k; dst[j*4] gets `added` (the k-mers the whole warp
     // added since the last flush; finish() turns it into the count of base 0). At most 252 k-mers per lane between
     // flushes. first: dst is written, else increased. Reduction number `it` (two byte fields widened to 16 bits, one
     // REDUX.SUM) is kept by lane `it`, so the results leave with two stores per lane instead of a predicated
-    // read-modify-write per reduction.
+    // read-modify-write per reduction. HI4: the byte fields of the shared word belong to k-mer slots g and g + 2 of the
+    // same column 16 + 2 h + p; the lanes g = 0 / 1 of a (b, p, h) group add their halves up.
     __device__ __forceinline__ void flush(int32_t *dst, int k, int added, bool first, int lane) {
         spill();
         uint32_t mine[NW] = {};
@@ -492,19 +516,26 @@ struct KmerCounter {
 #pragma unroll
                         for (int g = 0; g < 2; ++g) { // g = 0: byte fields 0, 2; g = 1: byte fields 1, 3
                             const int it = (((b * 2 + p) * 2 + h) * 2 + g); // 0 .. 23 within word w
-                            if (16 * w + 4 * g + 2 * h + p < 2 * KP) {      // (first column of the pair exists)
+                            const int col0 = (HI4 && w == 1) ? 16 + 2 * h + p : 16 * w + 4 * g + 2 * h + p;
+                            if (col0 < 2 * KP) {                            // (first column of the pair exists)
                                 const uint32_t s = __reduce_add_sync(FULL, (byt[w][b][p][h] >> (8 * g)) & 0x00FF00FFu);
                                 if (lane == it) mine[w] = s;
                             }
                         }
-        if (lane < 24) {
+        {
             const int g = lane & 1, h = (lane >> 1) & 1, p = (lane >> 2) & 1, b = lane >> 3;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                const int c0 = 16 * w + 4 * g + 2 * h + p, c1 = c0 + 8; // columns of the two 16-bit halves
                 const int32_t v0 = (int32_t)(mine[w] & 0xFFFFu), v1 = (int32_t)(mine[w] >> 16);
-                if (c0 < k) dst[c0 * 4 + b + 1] = first ? v0 : dst[c0 * 4 + b + 1] + v0;
-                if (c1 < k) dst[c1 * 4 + b + 1] = first ? v1 : dst[c1 * 4 + b + 1] + v1;
+                if (HI4 && w == 1) {
+                    const int32_t half = v0 + v1, tot = half + __shfl_xor_sync(FULL, half, 1);
+                    const int c = 16 + 2 * h + p;
+                    if (lane < 24 && g == 0 && c < k) dst[c * 4 + b + 1] = first ? tot : dst[c * 4 + b + 1] + tot;
+                } else if (lane < 24) {
+                    const int c0 = 16 * w + 4 * g + 2 * h + p, c1 = c0 + 8; // columns of the two 16-bit halves
+                    if (c0 < k) dst[c0 * 4 + b + 1] = first ? v0 : dst[c0 * 4 + b + 1] + v0;
+                    if (c1 < k) dst[c1 * 4 + b + 1] = first ? v1 : dst[c1 * 4 + b + 1] + v1;
+                }
             }
         }
 #pragma unroll

@@ -407,6 +407,217 @@ static __global__ void __launch_bounds__(ISM_WARPS * 32, 1) init_smem_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------------
+// random starts of LARGE sets: the packed set streamed through shared memory in tiles
+// ------------------------------------------------------------------------------------------------
+// C4 (100 000 x 200 bp) draws N (N - 1) = 1e10 sites per restart. From global memory every draw is a gather at a random
+// address: one L1 sector per lane, and the L1 tag stage takes about one sector per cycle per SM -- 148 x 1.965 GHz =
+// 2.9e11 draws/s whatever else the kernel does (init_kernel with the 64-bit gather copy measures 2.84e11, l1tex
+// throughput 75 %, 0.87 sectors per cycle per SM: profiles/r02_ncu_init_wide.txt). Shared memory takes a random gather
+// per lane at a few-way bank conflict instead, so the set is cut into tiles of `tile_rows` sequences that pass through
+// two shared-memory buffers (cp.async.bulk, one mbarrier each): one CTA per SM, one (chain, held-out sequence) item per
+// warp, all warps of the CTA on the same tile at the same time. A tile holds the sequences i0 <= i < i1, i.e. the draws
+// of ranks [i0 - (i0 > n), i1 - (i1 > n)) of item (chain, n) (rank = position of i among the sequences other than n,
+// fs:419-421) -- a contiguous range of the item's Philox stream, so the bit-sliced counters (KmerCounter) simply stay
+// in registers from tile to tile. Philox blocks cut by a tile edge are computed on both sides (2 of ~275 per tile).
+// After the last tile the warp scans its own sequence, staged from global memory, exactly like the other init kernels.
+#ifndef GIBBS_TILED_WARPS
+#define GIBBS_TILED_WARPS 16 // 128 registers per thread: the counters of k > 16 (36 registers) and a Philox block without spills
+#endif
+constexpr int TILED_WARPS = GIBBS_TILED_WARPS;
+#ifndef GIBBS_TILED_NB
+#define GIBBS_TILED_NB 1 // Philox blocks per lane and loop iteration
+#endif
+
+template <int KP, bool UNI>
+__device__ __forceinline__ void tile_draws(const ChainArgs &a, uint64_t chain_uid, uint64_t base, int n, int ra, int rb, int i0,
+                                           const uint32_t *tile, uint32_t range_u, KmerCounter<KP> &h, int &since, bool &first,
+                                           int32_t *counts, int lane) {
+    using Word = typename KmerCounter<KP>::Word;
+    const int k = a.k, row_words = a.s.row_words;
+    const uint64_t blkA = (base + (uint64_t)ra) >> 2, blkB = (base + (uint64_t)rb + 3) >> 2;
+    const int n_blk = (int)(blkB - blkA);
+    constexpr int NB = GIBBS_TILED_NB;
+    const int iters = (n_blk + 32 * NB - 1) / (32 * NB);
+    const int r_first = (int)((int64_t)(blkA << 2) - (int64_t)base); // rank of draw 0 of block blkA (may lie before ra)
+    const unsigned span = (unsigned)(rb - ra);
+    for (int it = 0; it < iters; ++it) {
+        // NB Philox blocks per lane and iteration: independent dependency chains for the few warps of this kernel
+        int r0[NB];
+        bool act[NB], plain = true;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int bi = (it * NB + q) * 32 + lane;
+            r0[q] = r_first + 4 * bi;
+            act[q] = bi < n_blk;
+            // a plain block: its four draws belong to this tile and lie on one side of the held-out sequence, so they visit
+            // four consecutive rows of the tile -- no validity test, no skip of n per draw
+            plain = plain && (!act[q] || (r0[q] >= ra && r0[q] + 4 <= rb && (r0[q] >= n || r0[q] + 3 < n)));
+        }
+        Word kmer[NB][4];
+        if (__all_sync(FULL, plain)) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) kmer[q][x] = 0;
+                if (act[q]) {
+                    const uint64_t blk = blkA + (uint64_t)((it * NB + q) * 32 + lane);
+                    const uint4 r4 = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    const uint32_t wd[4] = {r4.x, r4.y, r4.z, r4.w};
+                    const int ib = r0[q] + (r0[q] >= n ? 1 : 0) - i0;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const uint32_t range = UNI ? range_u : (uint32_t)(__ldg(a.s.len + i0 + ib + x) - k + 1);
+                        const int pos = (int)__umulhi(wd[x], range); // floor(word * 2^-32 * range), exact
+                        kmer[q][x] = gather_kmer<KP, true>(tile, row_words, ib + x, pos);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const uint64_t blk = blkA + (uint64_t)((it * NB + q) * 32 + lane);
+                const uint4 r4 = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
+                                               make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                const uint32_t wd[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const bool ok = (unsigned)(r0[q] + x - ra) < span; // the draw belongs to this tile (and to the item at all)
+                    const int r = ok ? r0[q] + x : ra;
+                    const int i = r + (r >= n ? 1 : 0);
+                    const uint32_t range = UNI ? range_u : (uint32_t)(__ldg(a.s.len + i) - k + 1);
+                    const int pos = (int)__umulhi(wd[x], range);
+                    const Word km = gather_kmer<KP, true>(tile, row_words, i - i0, pos);
+                    kmer[q][x] = ok ? km : (Word)0;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            h.add4(kmer[q]);
+            if (++since == 63) { // 252 k-mers per lane: the byte fields are full
+                h.flush(counts, k, 0, first, lane);
+                first = false;
+                since = 0;
+            }
+        }
+    }
+}
+
+__host__ __device__ inline size_t init_tiled_tile_bytes(int tile_rows, int row_words) { return ((size_t)tile_rows * row_words * 4 + 127) / 128 * 128; }
+__host__ __device__ inline size_t init_tiled_total_bytes(int tile_rows, int row_words, int kp) {
+    return 128 + 2 * init_tiled_tile_bytes(tile_rows, row_words) + (size_t)TILED_WARPS * (ism_table_bytes(kp) + (size_t)row_words * 4);
+}
+
+template <int KP>
+static __global__ void __launch_bounds__(TILED_WARPS * 32, 1) init_tiled_kernel(const ChainArgs a, int tile_rows) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.s.n, k = a.k, row_words = a.s.row_words;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    const size_t tile_bytes = init_tiled_tile_bytes(tile_rows, row_words);
+    uint32_t *tiles = reinterpret_cast<uint32_t *>(smem_raw + 128);
+    unsigned char *wbase = smem_raw + 128 + 2 * tile_bytes;
+    WarpTables WT;
+    {
+        unsigned char *b = wbase + warp * ism_table_bytes(KP);
+        WT.wcol = reinterpret_cast<double *>(b);
+        WT.ptab = reinterpret_cast<int32_t *>(b + 64 * KP);
+        WT.lgcol = reinterpret_cast<int32_t *>(b + 128 * KP);
+        WT.counts = reinterpret_cast<int32_t *>(b + 160 * KP);
+    }
+    require_aligned_tables(WT);
+    uint32_t *own_row = reinterpret_cast<uint32_t *>(wbase + (size_t)TILED_WARPS * ism_table_bytes(KP)) + warp * row_words;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const long long total = (long long)a.n_chains * N;
+    const long long per_batch = (long long)gridDim.x * TILED_WARPS;
+    const long long first_item = (long long)blockIdx.x * TILED_WARPS;
+    const int n_tiles = (N + tile_rows - 1) / tile_rows;
+    const long long n_batches = first_item < total ? (total - first_item + per_batch - 1) / per_batch : 0;
+    const long long total_q = n_batches * n_tiles;
+    auto issue = [&](long long q) { // thread 0: tile q % n_tiles into buffer q & 1
+        const int t = (int)(q % n_tiles);
+        const int r0 = t * tile_rows, r1 = min(N, r0 + tile_rows);
+        const uint32_t bytes = (uint32_t)(r1 - r0) * (uint32_t)row_words * 4u;
+        uint64_t *b = bar + (q & 1);
+        unsigned char *dst = reinterpret_cast<unsigned char *>(tiles) + (q & 1) * tile_bytes;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.s.packed + (size_t)r0 * row_words);
+        mbar_expect_tx(b, bytes);
+        for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(dst + o, src + o, min(32768u, bytes - o), b);
+    };
+    const uint32_t range_u = (uint32_t)(a.s.uniform_len - k + 1);
+    unsigned long long st_updates = 0, st_windows = 0, st_slow = 0;
+    KmerCounter<KP> h;
+    h.clear();
+    int since = 0, chain = 0, n = 0, t = 0;
+    bool first = true, valid = false;
+    uint64_t base = 0, chain_uid = 0;
+    long long batch = 0;
+    if (tid == 0 && total_q > 0) issue(0);
+    for (long long q = 0; q < total_q; ++q) {
+        if (tid == 0 && q + 1 < total_q) issue(q + 1); // its buffer was released by the barrier that ended tile q - 1
+        if (t == 0) { // a new batch: this warp's item
+            const long long item = first_item + batch * per_batch + warp;
+            valid = item < total;
+            if (valid) {
+                chain = (int)(item / N);
+                n = (int)(item % N);
+                chain_uid = (uint64_t)a.chain_id_base + (uint64_t)chain;
+                base = (uint64_t)n * (uint64_t)(N - 1);
+                for (int i = lane; i < row_words; i += 32) own_row[i] = __ldg(a.s.packed + (size_t)n * row_words + i);
+            }
+            h.clear();
+            since = 0;
+            first = true;
+        }
+        mbar_wait(bar + (q & 1), (uint32_t)((q >> 1) & 1));
+        if (valid) {
+            const int i0 = t * tile_rows, i1 = min(N, i0 + tile_rows);
+            const int ra = i0 - (i0 > n ? 1 : 0), rb = i1 - (i1 > n ? 1 : 0);
+            const uint32_t *tile = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(tiles) + (q & 1) * tile_bytes);
+            if (rb > ra) {
+                if (a.s.uniform_len > 0) tile_draws<KP, true>(a, chain_uid, base, n, ra, rb, i0, tile, range_u, h, since, first, WT.counts, lane);
+                else tile_draws<KP, false>(a, chain_uid, base, n, ra, rb, i0, tile, range_u, h, since, first, WT.counts, lane);
+            }
+        }
+        __syncthreads(); // every warp is done with this buffer
+        if (++t == n_tiles) {
+            t = 0;
+            ++batch;
+            if (valid) {
+                h.flush(WT.counts, k, N - 1, first, lane);
+                KmerCounter<KP>::finish(WT.counts, k, lane);
+                const int Wn = __ldg(a.s.len + n) - k + 1;
+                build_tables<KP>(WT, WT.counts, false, 0, k, a.wtab, lane);
+                double p;
+                int w;
+                const bool slow = pick_argmax<KP>(WT, own_row, Wn, k, a.fast_ok, lane, p, w);
+                if (lane == 0) {
+                    a.sites[(size_t)chain * N + n] = w;
+                    a.hv[(size_t)chain * N + n] = p;
+                }
+                st_updates += 1;
+                st_windows += (unsigned long long)Wn;
+                st_slow += slow ? 1 : 0;
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + ST_SITE_UPDATES, st_updates);
+        atomicAdd(a.stats + ST_WINDOW_SCORES, st_windows);
+        atomicAdd(a.stats + ST_EXACT_RESCANS, st_slow);
+    }
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)a.n_chains);
+}
+
+// ------------------------------------------------------------------------------------------------
 // the chain kernel: one team (CTA of T warps) = one restart of SiteSampler.doSiteSamplingWithBPV
 // (fs:691-695)
 // ------------------------------------------------------------------------------------------------

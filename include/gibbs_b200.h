@@ -98,7 +98,7 @@ typedef struct gibbs_run_stats {
     int32_t kernel_launches; /* CUDA kernels launched by the call                               */
     int32_t fast_path;     /* 1 = fixed-point filter + float64 verification was usable          */
     int32_t team_warps;    /* warps per chain of the first launch (1, 4, 8 or 16)               */
-    int32_t init_path;     /* where the random starts ran: GIBBS_INIT_CHAIN / _WIDE / _SMEM       */
+    int32_t init_path;     /* where the random starts ran: GIBBS_INIT_CHAIN / _WIDE / _SMEM / _TILED */
     double kernel_ms;      /* device time of the chain kernel (CUDA events on the handle stream) */
 } gibbs_run_stats;
 
@@ -133,13 +133,15 @@ int32_t gibbs_synchronize(gibbs_handle *h);
  * None of them changes a result.
  *   GIBBS_OPT_INIT_PATH    where the random starts (fs:412-430) run: GIBBS_INIT_AUTO (default) picks per launch;
  *                          _CHAIN = inside the chain kernel, _WIDE = grid-wide kernel gathering from global memory,
- *                          _SMEM = grid-wide kernel with the packed set in shared memory (used only when it fits)
+ *                          _SMEM = grid-wide kernel with the packed set in shared memory (used only when it fits),
+ *                          _TILED = grid-wide kernel streaming the packed set through shared memory in tiles (large sets)
  *   GIBBS_OPT_EXACT_SCANS  1 = no ranking pass anywhere: every window in float64, sequential roulette walk
  *   GIBBS_OPT_STAGE2_AT / GIBBS_OPT_STAGE3_AT  straggler hand-over of the SiteSampler chain kernel: once this many chains
  *                          per SM (or fewer) are still running they continue with 8 / 16 warps per chain (defaults 2, 1)
  *   GIBBS_OPT_MIN_WIDTH    narrowest speculative round of the greedy sweeps while chains share an SM (default 1; once a
  *                          chain has an SM or a cluster to itself its rounds always use the whole team)
  *   GIBBS_OPT_CLUSTER      largest thread-block cluster the last stages may give one chain: 8 (default), 4 or 0 (none)
+ *   GIBBS_OPT_TILE_ROWS    cap on the sequences per shared-memory tile of the _TILED random starts (0 = as many as fit)
  */
 #define GIBBS_OPT_INIT_PATH 1
 #define GIBBS_OPT_EXACT_SCANS 2
@@ -147,10 +149,12 @@ int32_t gibbs_synchronize(gibbs_handle *h);
 #define GIBBS_OPT_STAGE3_AT 4
 #define GIBBS_OPT_CLUSTER 5
 #define GIBBS_OPT_MIN_WIDTH 6
+#define GIBBS_OPT_TILE_ROWS 7
 #define GIBBS_INIT_AUTO 0
 #define GIBBS_INIT_CHAIN 1
 #define GIBBS_INIT_WIDE 2
 #define GIBBS_INIT_SMEM 3
+#define GIBBS_INIT_TILED 4
 int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value);
 
 /* ---- primitives: parity can be checked at the level the reference composes them -------------- */

@@ -97,7 +97,7 @@ def test_c2_every_chain_matches_the_oracle():
             assert res.sites[c].tolist() == pos.tolist(), f"chain {c}"
             np.testing.assert_allclose(res.scores[c], score, rtol=1e-5)
         # every init path gives the same chains
-        for path in (_abi.GIBBS_INIT_CHAIN, _abi.GIBBS_INIT_WIDE, _abi.GIBBS_INIT_SMEM):
+        for path in (_abi.GIBBS_INIT_CHAIN, _abi.GIBBS_INIT_WIDE, _abi.GIBBS_INIT_SMEM, _abi.GIBBS_INIT_TILED):
             eng.set_option(_abi.GIBBS_OPT_INIT_PATH, path)
             part = eng.run(params, 160, chain_id_base=g["chain_base"] + 512, seed=g["seed"], want_counts=False)
             assert part.stats["init_path"] == path

@@ -152,15 +152,17 @@ def test_chains_match_oracle_philox(case, team):
     assert res.counts.tolist() == want_counts.tolist()
 
 
-INIT_PATHS = {"chain": _abi.GIBBS_INIT_CHAIN, "wide": _abi.GIBBS_INIT_WIDE, "smem": _abi.GIBBS_INIT_SMEM}
+INIT_PATHS = {"chain": _abi.GIBBS_INIT_CHAIN, "wide": _abi.GIBBS_INIT_WIDE, "smem": _abi.GIBBS_INIT_SMEM,
+              "tiled": _abi.GIBBS_INIT_TILED}
 
 
 @pytest.mark.parametrize("path", sorted(INIT_PATHS))
 @pytest.mark.parametrize("shape", [(70, 64, 40, 9), (300, 90, None, 12), (1100, 40, 30, 16), (90, 700, 500, 20), (40, 130, None, 31)],
                          ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
 def test_random_starts_same_on_every_init_path(shape, path):
-    """Random starts (fs:412-430) run inside the chain kernel, as the grid-wide kernel gathering from global memory, or
-    as the grid-wide kernel with the packed set in shared memory (gibbs_api.cu picks by shape;
+    """Random starts (fs:412-430) run inside the chain kernel, as the grid-wide kernel gathering from global memory, as
+    the grid-wide kernel with the packed set in shared memory, or as the one that streams it through shared memory in
+    tiles (gibbs_api.cu picks by shape;
     gibbs_set_option(GIBBS_OPT_INIT_PATH) forces one). All must consume the uniform stream exactly as the oracle does:
     N(N-1) draws, bit-sliced base counters with several nibble spills and (N = 1100) warp flushes, one- and two-word k-mers."""
     n, L, Lmin, k = shape
@@ -183,6 +185,36 @@ def test_random_starts_same_on_every_init_path(shape, path):
         if n <= 300 or c == 0:   # the oracle's full restart is O(N^2 L k): seconds at N = 1100
             score, pos, _ = _oracle_chain(S, k, 1e-4, pcv, b"ATGC-", seed=99, chain=7 + c)
             assert full.sites[c].tolist() == pos.tolist(), f"chain {c}"
+
+
+@pytest.mark.parametrize("tile_rows", [1, 3, 7, 32, 33, 250])
+@pytest.mark.parametrize("shape", [(70, 64, 40, 9), (300, 90, None, 12), (1100, 40, 30, 16), (90, 300, 200, 20), (40, 130, None, 31)],
+                         ids=lambda s: f"n{s[0]}_L{s[1]}_k{s[3]}")
+def test_tiled_random_starts_for_any_tile_size(shape, tile_rows):
+    """init_tiled_kernel streams the set through shared memory in tiles; a tile holds a contiguous range of every item's
+    Philox stream, cut at arbitrary places (inside Philox blocks, at the held-out sequence, tiles of one sequence, a
+    short last tile). GIBBS_OPT_TILE_ROWS forces small tiles; the result must not depend on the tile size: compared
+    bit for bit with the chain kernel's own random starts and with the oracle."""
+    n, L, Lmin, k = shape
+    ps = planted_motif_set(n, L, k, seed=23, min_length=Lmin)
+    seqs = ps.sequences()
+    bg = background_of(ps.ascii, 1e-4, 5)
+    n_chains = 5
+    prm = make_params(k, 1e-4, 5, bg, phase_mask=_abi.PHASE_INIT)
+    with GibbsEngine(seqs) as eng:
+        eng.set_option(_abi.GIBBS_OPT_INIT_PATH, _abi.GIBBS_INIT_CHAIN)
+        want = eng.run(prm, n_chains, chain_id_base=2, seed=5)
+        eng.set_option(_abi.GIBBS_OPT_INIT_PATH, _abi.GIBBS_INIT_TILED)
+        eng.set_option(_abi.GIBBS_OPT_TILE_ROWS, tile_rows)
+        got = eng.run(prm, n_chains, chain_id_base=2, seed=5)
+    assert got.stats["init_path"] == _abi.GIBBS_INIT_TILED
+    assert got.sites.tobytes() == want.sites.tobytes()
+    assert got.scores.tobytes() == want.scores.tobytes()
+    assert got.stats["site_updates"] == want.stats["site_updates"] == n_chains * n
+    S = O.sources(seqs)
+    pcv = O.pcv_from_acgt(bg)
+    score, pos, _ = _oracle_chain(S, k, 1e-4, pcv, b"ATGC-", seed=5, chain=2, name="random_starts_with_bpv")
+    assert got.sites[0].tolist() == pos.tolist()
 
 
 @pytest.mark.parametrize("team", TEAMS)
