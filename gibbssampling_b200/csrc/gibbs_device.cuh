@@ -283,6 +283,33 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// The same block cipher with the ten round keys precomputed on the host (they depend on the seed alone) and passed as a
+// kernel parameter: the round keys become constant-bank operands of the LOP3s instead of twenty registers or two IADDs
+// per round (init_tiled_kernel runs at its register limit and on the integer pipe).
+struct PhiloxKeys {
+    uint32_t x[10], y[10];
+};
+inline PhiloxKeys philox_round_keys(uint64_t seed) {
+    PhiloxKeys pk;
+    uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        pk.x[r] = kx;
+        pk.y[r] = ky;
+        kx += 0x9E3779B9u;
+        ky += 0xBB67AE85u;
+    }
+    return pk;
+}
+__device__ __forceinline__ uint4 philox4x32_10_keyed(uint4 c, const PhiloxKeys &pk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ pk.x[r], lo1, hi0 ^ c.w ^ pk.y[r], lo0);
+    }
+    return c;
+}
+
 // ------------------------------------------------------------------------------------------------
 // 2-bit k-mer extraction
 // ------------------------------------------------------------------------------------------------

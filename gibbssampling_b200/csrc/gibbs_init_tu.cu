@@ -19,7 +19,7 @@ static cudaError_t launch_tiled_one(const ChainArgs &a, int grid, int smem, cuda
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    kernel<<<grid, TILED_WARPS * 32, smem, stream>>>(a, tile_rows);
+    kernel<<<grid, TILED_WARPS * 32, smem, stream>>>(a, tile_rows, philox_round_keys(a.seed));
     return cudaGetLastError();
 }
 

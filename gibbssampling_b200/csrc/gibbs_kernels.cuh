@@ -429,9 +429,9 @@ constexpr int TILED_WARPS = GIBBS_TILED_WARPS;
 #endif
 
 template <int KP, bool UNI>
-__device__ __forceinline__ void tile_draws(const ChainArgs &a, uint64_t chain_uid, uint64_t base, int n, int ra, int rb, int i0,
-                                           const uint32_t *tile, uint32_t range_u, KmerCounter<KP> &h, int &since, bool &first,
-                                           int32_t *counts, int lane) {
+__device__ __forceinline__ void tile_draws(const ChainArgs &a, const PhiloxKeys &pk, uint64_t chain_uid, uint64_t base, int n, int ra,
+                                           int rb, int i0, const uint32_t *tile, uint32_t range_u, KmerCounter<KP> &h, int &since,
+                                           bool &first, int32_t *counts, int lane) {
     using Word = typename KmerCounter<KP>::Word;
     const int k = a.k, row_words = a.s.row_words;
     const uint64_t blkA = (base + (uint64_t)ra) >> 2, blkB = (base + (uint64_t)rb + 3) >> 2;
@@ -440,29 +440,35 @@ __device__ __forceinline__ void tile_draws(const ChainArgs &a, uint64_t chain_ui
     const int iters = (n_blk + 32 * NB - 1) / (32 * NB);
     const int r_first = (int)((int64_t)(blkA << 2) - (int64_t)base); // rank of draw 0 of block blkA (may lie before ra)
     const unsigned span = (unsigned)(rb - ra);
+    // Plain blocks: all four draws belong to this tile and lie on one side of the held-out sequence, so they visit four
+    // consecutive rows of the tile -- no validity test, no skip of n per draw. They are the blocks [lo_blk, hi_blk) except
+    // the one that straddles n (hole_blk); an iteration whose 32 NB blocks are all plain (or past the end, when the last
+    // block is whole) takes the short path. Warp-uniform arithmetic, nothing per lane.
+    const int lo_blk = r_first == ra ? 0 : 1;
+    const int hi_blk = (rb - r_first) >> 2; // blocks that end at or before rb
+    const int hole_off = n - r_first;       // rank n relative to block 0: a block straddles n iff n is not at its start
+    const int hole_blk = (hole_off > 0 && (hole_off & 3) != 0) ? (hole_off >> 2) : -1;
     for (int it = 0; it < iters; ++it) {
         // NB Philox blocks per lane and iteration: independent dependency chains for the few warps of this kernel
         int r0[NB];
-        bool act[NB], plain = true;
+        bool act[NB];
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
             const int bi = (it * NB + q) * 32 + lane;
             r0[q] = r_first + 4 * bi;
             act[q] = bi < n_blk;
-            // a plain block: its four draws belong to this tile and lie on one side of the held-out sequence, so they visit
-            // four consecutive rows of the tile -- no validity test, no skip of n per draw
-            plain = plain && (!act[q] || (r0[q] >= ra && r0[q] + 4 <= rb && (r0[q] >= n || r0[q] + 3 < n)));
         }
+        const int b_first = it * NB * 32, b_last = b_first + NB * 32; // this iteration's blocks [b_first, b_last)
+        const bool plain = b_first >= lo_blk && (b_last <= hi_blk || hi_blk == n_blk) && !(hole_blk >= b_first && hole_blk < b_last);
         Word kmer[NB][4];
-        if (__all_sync(FULL, plain)) {
+        if (plain) {
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
 #pragma unroll
                 for (int x = 0; x < 4; ++x) kmer[q][x] = 0;
                 if (act[q]) {
                     const uint64_t blk = blkA + (uint64_t)((it * NB + q) * 32 + lane);
-                    const uint4 r4 = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
-                                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    const uint4 r4 = philox4x32_10_keyed(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)), pk);
                     const uint32_t wd[4] = {r4.x, r4.y, r4.z, r4.w};
                     const int ib = r0[q] + (r0[q] >= n ? 1 : 0) - i0;
 #pragma unroll
@@ -477,8 +483,7 @@ __device__ __forceinline__ void tile_draws(const ChainArgs &a, uint64_t chain_ui
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
                 const uint64_t blk = blkA + (uint64_t)((it * NB + q) * 32 + lane);
-                const uint4 r4 = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)),
-                                               make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                const uint4 r4 = philox4x32_10_keyed(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_uid, (uint32_t)(chain_uid >> 32)), pk);
                 const uint32_t wd[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
@@ -510,7 +515,7 @@ __host__ __device__ inline size_t init_tiled_total_bytes(int tile_rows, int row_
 }
 
 template <int KP>
-static __global__ void __launch_bounds__(TILED_WARPS * 32, 1) init_tiled_kernel(const ChainArgs a, int tile_rows) {
+static __global__ void __launch_bounds__(TILED_WARPS * 32, 1) init_tiled_kernel(const ChainArgs a, int tile_rows, const PhiloxKeys pk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.s.n, k = a.k, row_words = a.s.row_words;
@@ -582,8 +587,8 @@ static __global__ void __launch_bounds__(TILED_WARPS * 32, 1) init_tiled_kernel(
             const int ra = i0 - (i0 > n ? 1 : 0), rb = i1 - (i1 > n ? 1 : 0);
             const uint32_t *tile = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(tiles) + (q & 1) * tile_bytes);
             if (rb > ra) {
-                if (a.s.uniform_len > 0) tile_draws<KP, true>(a, chain_uid, base, n, ra, rb, i0, tile, range_u, h, since, first, WT.counts, lane);
-                else tile_draws<KP, false>(a, chain_uid, base, n, ra, rb, i0, tile, range_u, h, since, first, WT.counts, lane);
+                if (a.s.uniform_len > 0) tile_draws<KP, true>(a, pk, chain_uid, base, n, ra, rb, i0, tile, range_u, h, since, first, WT.counts, lane);
+                else tile_draws<KP, false>(a, pk, chain_uid, base, n, ra, rb, i0, tile, range_u, h, since, first, WT.counts, lane);
             }
         }
         __syncthreads(); // every warp is done with this buffer
