@@ -42,7 +42,7 @@ module Native =
         val mutable kernelLaunches: int
         val mutable fastPath      : int
         val mutable teamWarps     : int
-        val mutable initPath      : int   // GIBBS_INIT_CHAIN / _WIDE / _SMEM
+        val mutable initPath      : int   // GIBBS_INIT_CHAIN / _WIDE / _SMEM / _TILED
         val mutable kernelMs      : float
 
     [<Literal>]
