@@ -355,7 +355,7 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
 
     def e2e_step(s_: int):
         eng.upload_flat(host_ascii.numpy(), host_off.numpy())      # H2D + GPU 2-bit pack
-        eng.run_device(params, chains, chain_id_base=chain_base, seed=SEED + 1000 + s_)
+        eng.run_device(params, chains, chain_id_base=chain_base, seed=SEED + s_)   # the same restarts as the device-timed step s_
         return finish_step(eng)                                     # what fs:434 / fs:615 / fs:856 returns
 
     for w in range(args.warmup):            # untimed: first use allocates the page-locked result buffers
@@ -474,7 +474,8 @@ def run_gpu_arm(args, cfg_name, cfg) -> None:
             "e2e": {"value": g_e2e_windows / e2e_s, "unit": "window-scores/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "api": "gibbs_upload + gibbs_run_device + gibbs_fetch_best (C ABI): ASCII in, the restart loop's "
-                           "(float*int)[] out; the fs:434 loop is decided on the device"},
+                           "(float*int)[] out; the fs:434 loop is decided on the device; wall clock over the same "
+                           "restarts (seeds) as the device-timed steps, each step uploading from pinned host memory"},
             "families": families,
             "gpu_launches": launches, "gpu_launches_e2e_per_step": launches_e2e,
             "clocks": clocks,

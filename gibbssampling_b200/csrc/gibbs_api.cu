@@ -317,7 +317,7 @@ int32_t launch_random_starts(gibbs_handle *h, ChainArgs &a, bool drift) {
         const bool tile_auto = tile_rows >= 256;
         if (tile_rows > a.s.n) tile_rows = a.s.n;
         if (h->opt_tile_rows > 0 && tile_rows > h->opt_tile_rows) tile_rows = h->opt_tile_rows; // (tests: many small tiles)
-        const bool tiled_ok = !drift && a.rng_mode == 0 && a.sampler == GIBBS_SITE_SAMPLER && tile_rows >= 1;
+        const bool tiled_ok = !drift && a.rng_mode == 0 && tile_rows >= 1; // (both samplers: the MotifSampler starts from the same sweep)
         if (init_path == GIBBS_INIT_WIDE && tiled_ok && tile_auto && a.s.n >= 4096 && (long long)a.n_chains * a.s.n >= 8LL * h->sm_count * TILED_WARPS)
             init_path = GIBBS_INIT_TILED;
         if (h->opt_init_path == GIBBS_INIT_CHAIN) init_path = GIBBS_INIT_CHAIN;

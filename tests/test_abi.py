@@ -67,3 +67,18 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in text and "gibbs_oracle" not in text, f
+
+
+def test_constants_of_the_python_binding_match_the_header():
+    """every #define GIBBS_* <integer> of include/gibbs_b200.h that _abi.py mirrors carries the same value (options, init
+    paths, error codes, phases ...): a constant added on one side only is caught here, without a GPU"""
+    text = open(os.path.join(ROOT, "include", "gibbs_b200.h")).read()
+    defines = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"^#define\s+(GIBBS_[A-Z0-9_]+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\s*(?:/\*.*)?$", text, flags=re.M)}
+    assert {"GIBBS_OPT_INIT_PATH", "GIBBS_OPT_TILE_ROWS", "GIBBS_INIT_TILED", "GIBBS_INIT_SMEM"} <= set(defines)
+    mirrored = [name for name in defines if hasattr(_abi, name)]
+    assert len(mirrored) >= 18
+    for name in mirrored:
+        assert getattr(_abi, name) == defines[name], name
+    for name in defines:
+        if name.startswith(("GIBBS_OPT_", "GIBBS_INIT_")):
+            assert hasattr(_abi, name), f"{name} is in the header but not in _abi.py"

@@ -87,6 +87,23 @@ def test_motif_restarts_match_oracle(case):
     assert res.stats["site_updates"] > 0
 
 
+@pytest.mark.parametrize("tile_rows", [5, 64])
+def test_motif_restarts_on_tiled_random_starts(tile_rows):
+    """The MotifSampler's random starts (fs:868) on init_tiled_kernel: same restarts as on the default path."""
+    case = _cases()[0]
+    n, L, Lmin, k, pc, cutoff, seed = case
+    ps, seqs, bg = _setup(case)
+    params = make_params(k, pc, 5, bg, cutoff=cutoff, sampler=_abi.GIBBS_MOTIF_SAMPLER)
+    with GibbsEngine(seqs) as eng:
+        want = eng.run(params, 6, chain_id_base=40, seed=77 + seed, want_counts=False)
+        eng.set_option(_abi.GIBBS_OPT_INIT_PATH, _abi.GIBBS_INIT_TILED)
+        eng.set_option(_abi.GIBBS_OPT_TILE_ROWS, tile_rows)
+        got = eng.run(params, 6, chain_id_base=40, seed=77 + seed, want_counts=False)
+    assert got.stats["init_path"] == _abi.GIBBS_INIT_TILED and want.stats["init_path"] != _abi.GIBBS_INIT_TILED
+    assert got.sites.tobytes() == want.sites.tobytes()
+    assert got.scores.tobytes() == want.scores.tobytes()
+
+
 def test_motif_phases_and_injected_uniforms():
     case = (7, 80, 50, 8, 1e-4, 1.0, 9)
     n, L, Lmin, k, pc, cutoff, seed = case
