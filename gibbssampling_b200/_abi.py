@@ -43,6 +43,7 @@ EXPORTS = [
 ]
 GIBBS_OPT_INIT_PATH, GIBBS_OPT_EXACT_SCANS, GIBBS_OPT_STAGE2_AT, GIBBS_OPT_STAGE3_AT, GIBBS_OPT_CLUSTER, GIBBS_OPT_MIN_WIDTH = 1, 2, 3, 4, 5, 6
 GIBBS_OPT_TILE_ROWS = 7
+GIBBS_OPT_SEQ_SWEEPS = 8
 GIBBS_INIT_AUTO, GIBBS_INIT_CHAIN, GIBBS_INIT_WIDE, GIBBS_INIT_SMEM, GIBBS_INIT_TILED = 0, 1, 2, 3, 4
 
 

@@ -175,6 +175,7 @@ struct gibbs_handle {
     int32_t opt_exact_scans = 0;       // gibbs_set_option(GIBBS_OPT_EXACT_SCANS)
     int32_t opt_stage2_at = 2, opt_stage3_at = 1; // hand-over thresholds in chains per SM (GIBBS_OPT_STAGE2_AT / _STAGE3_AT)
     int32_t opt_min_width = -1;        // GIBBS_OPT_MIN_WIDTH: -1 = automatic
+    int32_t opt_seq_sweeps = 1;        // GIBBS_OPT_SEQ_SWEEPS: greedy sweeps run by one warp per chain before the team stages
     int32_t opt_tile_rows = 0;         // GIBBS_OPT_TILE_ROWS: cap on the sequences per tile of init_tiled_kernel (0 = what fits)
     int32_t opt_cluster = 8;           // largest cluster the last hand-over stages may use: 0 (none), 4 or 8 (GIBBS_OPT_CLUSTER)
     int32_t cluster_cap[2] = {-1, -1}; // clusters of 4 / 8 CTAs the device holds at once (queried once per shape)
@@ -409,8 +410,8 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
     // with 16 warps. Late sweeps move few sites, so the wider speculative rounds are rarely discarded.
     const int N = a.s.n, sms = h->sm_count;
     auto fits = [&](int t) { return N >= t && team_smem_bytes(a.s.row_words, t) <= 200 * 1024; };
-    struct Stage { int team, pause_below, cluster; };
-    Stage stages[5];
+    struct Stage { int team, pause_below, cluster, min_sweeps; };
+    Stage stages[8] = {};
     int n_stages = 0;
     if (masked) {
         stages[n_stages++] = {team_smem_bytes(a.s.row_words, 4) <= 200 * 1024 ? 4 : 1, 0, 0};
@@ -435,6 +436,15 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
         if (first == 16 && !fits(16)) first = 8;
         if (first == 8 && !fits(8)) first = 4;
         if (first == 4 && !fits(4)) first = 1;
+        // The first greedy sweep moves a site in almost every update (C2: 99 %, then 28 % in sweep 1), so its rounds run at
+        // width 1 and three warps of a four-warp team wait. One warp per chain with 128 registers and no team barrier runs
+        // such a sweep faster (C2, sweeps 0 / 1 / 2 / 3 alone: 1.74 / 1.61 / 1.57 / 1.52 ms against 2.20 / 2.18 / 1.59 / 1.15 ms,
+        // tools/seq_regime_probe.py). So the first GIBBS_OPT_SEQ_SWEEPS sweeps are a stage of their own on
+        // chain_kernel<KP, 1>: every chain pauses at the boundary of that sweep (pause_below = all chains) and the next
+        // stage continues it. The hand-over itself costs ~0.3 ms (the slowest chain's sweep ends the launch), so whole C2
+        // steps measure 23.76 / 23.18 / 23.48 / 24.2 ms for 0 / 1 / 2 / 3 such sweeps: the default is 1.
+        if (first == 4 && N >= 64 && (a.phase_mask & GIBBS_PHASE_GREEDY) && h->opt_seq_sweeps > 0)
+            stages[n_stages++] = {1, a.n_chains, 0, h->opt_seq_sweeps};
         stages[n_stages++] = {first, 0, 0};
         if (first == 4 && fits(8)) {
             stages[n_stages - 1].pause_below = h->opt_stage2_at * sms;
@@ -468,7 +478,7 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
             }
         }
     }
-    h->run_team = stages[0].team;
+    h->run_team = stages[0].team == 1 && n_stages > 1 && stages[0].pause_below == a.n_chains ? 4 : stages[0].team; // (the team of the main stage)
     h->run_stages = n_stages;
     // control words: [0] chains still running, [s] number of chains paused by stage s
     CUDA_TRY(h->ctl.reserve(8));
@@ -483,6 +493,7 @@ int32_t launch_chain_kp(gibbs_handle *h, ChainArgs a, bool drift) {
     for (int st = 0; st < n_stages; ++st) {
         ChainArgs b = a;
         b.pause_below = stages[st].pause_below;
+        b.pause_min_sweeps = stages[st].min_sweeps;
         b.from_list = st > 0;
         {   // chains that reach this stage per SM (at most): with an SM or more per chain, never narrow a speculative round
             const int per_sm = st == 0 ? (a.n_chains + sms - 1) / sms : (stages[st - 1].pause_below + sms - 1) / sms;
@@ -1556,6 +1567,10 @@ int32_t gibbs_set_option(gibbs_handle *h, int32_t option, int32_t value) {
     case GIBBS_OPT_MIN_WIDTH:
         if (value < -1 || value > 128) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_MIN_WIDTH takes -1 (automatic) .. 128");
         h->opt_min_width = value;
+        return GIBBS_OK;
+    case GIBBS_OPT_SEQ_SWEEPS:
+        if (value < 0 || value > 3) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_SEQ_SWEEPS takes 0 .. 3");
+        h->opt_seq_sweeps = value;
         return GIBBS_OK;
     case GIBBS_OPT_TILE_ROWS:
         if (value < 0) return fail(GIBBS_ERR_ARG, "GIBBS_OPT_TILE_ROWS takes 0 (what fits) or a positive number of sequences");

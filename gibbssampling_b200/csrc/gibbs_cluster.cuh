@@ -122,8 +122,9 @@ static __global__ void __launch_bounds__(32 * CL_T, 1) chain_cluster_kernel(cons
     int st_sweeps = 0, capped = 0;
     int phase, sweeps_in_phase;
     {
-        const int r = a.resume[chain];
-        phase = r & 255;
+        const int r = a.resume[chain]; // phase | capped so far << 7 | sweeps in phase << 8
+        phase = r & 127;
+        capped = (r >> 7) & 1;
         sweeps_in_phase = r >> 8;
     }
     bool resumed = true, paused = false;
@@ -328,11 +329,11 @@ static __global__ void __launch_bounds__(32 * CL_T, 1) chain_cluster_kernel(cons
     if (crank != 0) return;
     if (tid == 0) {
         atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
-        atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
+        if (!paused) atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped); // (a chain counts once, where it ends)
     }
     if (paused) {
         if (tid == 0) {
-            a.resume[chain] = phase | (sweeps_in_phase << 8);
+            a.resume[chain] = phase | (capped << 7) | (sweeps_in_phase << 8);
             a.pending_out[atomicAdd(a.pending_out_n, 1)] = chain;
         }
         return;

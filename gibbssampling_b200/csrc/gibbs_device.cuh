@@ -98,6 +98,7 @@ struct ChainArgs {
     int32_t min_width;
     int32_t *active;          // chains not finished yet
     int32_t pause_below;      // pause when *active <= pause_below (0 = never)
+    int32_t pause_min_sweeps; // ... and the chain has run at least this many sweeps in this launch (chain_kernel only)
     int32_t from_list;        // 1 = this launch continues the chains listed in pending_in
     int32_t *resume;          // [chains] phase | sweeps_in_phase << 8 of a paused chain
     const int32_t *pending_in;

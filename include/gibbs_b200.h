@@ -141,6 +141,9 @@ int32_t gibbs_synchronize(gibbs_handle *h);
  *   GIBBS_OPT_MIN_WIDTH    narrowest speculative round of the greedy sweeps while chains share an SM (default 1; once a
  *                          chain has an SM or a cluster to itself its rounds always use the whole team)
  *   GIBBS_OPT_CLUSTER      largest thread-block cluster the last stages may give one chain: 8 (default), 4 or 0 (none)
+ *   GIBBS_OPT_SEQ_SWEEPS   how many of a restart's first sweeps run with one warp per chain before the team stages take over
+ *                          (default 1: the first greedy sweep is sequential, a lone warp with more registers runs it faster
+ *                          than a team that mostly waits; 0 = teams from the start; at most 3)
  *   GIBBS_OPT_TILE_ROWS    cap on the sequences per shared-memory tile of the _TILED random starts (0 = as many as fit)
  */
 #define GIBBS_OPT_INIT_PATH 1
@@ -150,6 +153,7 @@ int32_t gibbs_synchronize(gibbs_handle *h);
 #define GIBBS_OPT_CLUSTER 5
 #define GIBBS_OPT_MIN_WIDTH 6
 #define GIBBS_OPT_TILE_ROWS 7
+#define GIBBS_OPT_SEQ_SWEEPS 8
 #define GIBBS_INIT_AUTO 0
 #define GIBBS_INIT_CHAIN 1
 #define GIBBS_INIT_WIDE 2
