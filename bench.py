@@ -38,16 +38,16 @@ CONFIGS = {
     "C3": (10000, 1000, 16, 1024, True),  # 8192 restarts over 8 GPUs = 1024 per GPU
     "C4": (100000, 200, 20, 148, True),   # ChIP-seq-peak-sized set with phase-shift moves
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one C2 step (ncu --set full, round 2): init_smem_kernel,
-# chain_kernel T = 4 / 8 / 16, chain_cluster_kernel 4 / 8 (read, write in MB each)
-NCU_DRAM_BYTES_PER_STEP = int((0.224000 + 0.0 + 12.567040 + 1.397248 + 3.205632 + 0.0 + 1.615360 + 0.0
-                               + 0.563456 + 0.0 + 0.405504 + 0.0) * 1e6)
-NCU_DRAM_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one C2 step (init_smem_kernel, "
-                   "chain_kernel T=4/8/16, chain_cluster_kernel 4/8), profiles/r02_ncu_c2_step_summary.txt")
+# dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one C2 step (ncu --set full, round 2, final build):
+# init_smem_kernel, chain_kernel T = 1 / 4 / 8 / 16, chain_cluster_kernel 4 / 8 (read, write in MB each)
+NCU_DRAM_BYTES_PER_STEP = int((0.224256 + 0.0 + 12.561664 + 0.0 + 12.574208 + 1.434112 + 3.177472 + 0.000256 + 1.545728 + 0.0
+                               + 0.502016 + 0.0 + 0.429824 + 0.0) * 1e6)
+NCU_DRAM_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one C2 step (init_smem_kernel, "
+                   "chain_kernel T=1/4/8/16, chain_cluster_kernel 4/8), profiles/r02_ncu_c2_step_summary.txt")
 # --family: which reference family the step runs (the default is the BASELINE.json workload)
 FAMILIES = {
     "bpv": ("SiteSampler WithBPV restarts (fs:691)", "fixed (WithBPV), whole-set base counts",
-            "gibbs::chain_kernel (a step = init_smem_kernel / init_kernel + chain_kernel<KP,4|8|16> + chain_cluster_kernel<KP,4|8>, "
+            "gibbs::chain_kernel (a step = init_smem_kernel / init_tiled_kernel / init_kernel + chain_kernel<KP,1|4|8|16> + chain_cluster_kernel<KP,4|8>, "
             "timed together: kernel_ms)", "do_site_sampling_with_bpv"),
     "data": ("SiteSampler restarts with the data-derived drifting background (doSiteSampling, fs:697)",
              "data-derived, rebuilt per window (fs:470-473)", "gibbs::chain_kernel<KP, T, MASKED, DRIFT = true>", "do_site_sampling"),

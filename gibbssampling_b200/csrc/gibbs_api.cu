@@ -666,33 +666,35 @@ int motif_team(const gibbs_handle *h) {
 
 // The stages of a MotifSampler run: teams of 4 warps for every restart, then -- A,C,G,T-only sets, automatic team size --
 // the restarts still running are handed over to teams of 8 and of 16 warps as in launch_chain_kp (same thresholds).
-struct MotifStage { int team, pause_below; };
+struct MotifStage { int team, pause_below, min_sweeps; };
 int motif_stages(const gibbs_handle *h, int n_chains, MotifStage *stages) {
     const int sms = h->sm_count, N = h->n;
     auto fits = [&](int t) { return N >= t && team_smem_bytes(h->row_words, t) <= 200 * 1024; };
     int n_stages = 0;
     const int team = motif_team(h);
     if (team != 4 || h->n_masked > 0 || h->team_warps != 0) {
-        stages[n_stages++] = {team, 0};
+        stages[n_stages++] = {team, 0, 0};
         return n_stages;
     }
     int first = n_chains > h->opt_stage2_at * sms ? 4 : n_chains > h->opt_stage3_at * sms ? 8 : 16;
     if (first == 16 && !fits(16)) first = 8;
     if (first == 8 && !fits(8)) first = 4;
-    stages[n_stages++] = {first, 0};
+    // (One warp per restart for the first greedy sweeps, as launch_chain_kp does for the SiteSampler, was measured here too:
+    // the sweeps themselves gain 1.4 ms on C2, the two hand-overs around them cost 2.5 ms -- tools/experiments/README.md.)
+    stages[n_stages++] = {first, 0, 0};
     if (first == 4 && fits(8)) {
         stages[n_stages - 1].pause_below = h->opt_stage2_at * sms;
-        stages[n_stages++] = {8, 0};
+        stages[n_stages++] = {8, 0, 0};
     }
     if (stages[n_stages - 1].team == 8 && fits(16)) {
         stages[n_stages - 1].pause_below = h->opt_stage3_at * sms;
-        stages[n_stages++] = {16, 0};
+        stages[n_stages++] = {16, 0, 0};
     }
     return n_stages;
 }
 // warps that hold a scratch list at once, over the stages of a run (the lists are indexed by CTA)
 size_t motif_scratch_warps(const gibbs_handle *h, int n_chains) {
-    MotifStage stages[3];
+    MotifStage stages[8];
     const int n_stages = motif_stages(h, n_chains, stages);
     size_t most = 0;
     for (int st = 0; st < n_stages; ++st) {
@@ -711,7 +713,7 @@ int32_t launch_motif_kp(gibbs_handle *h, MotifArgs m) {
         if (rc) return rc;
         m.init_done = (before & GIBBS_PHASE_INIT) && !(m.c.phase_mask & GIBBS_PHASE_INIT);
     }
-    MotifStage stages[3];
+    MotifStage stages[8];
     const int n_stages = motif_stages(h, m.c.n_chains, stages);
     CUDA_TRY(h->ctl.reserve(8));
     const int32_t ctl0[8] = {m.c.n_chains, 0, 0, 0, 0, 0, 0, 0};
@@ -726,6 +728,7 @@ int32_t launch_motif_kp(gibbs_handle *h, MotifArgs m) {
         MotifArgs b = m;
         const int team = stages[st].team;
         b.c.pause_below = stages[st].pause_below;
+        b.c.pause_min_sweeps = stages[st].min_sweeps;
         b.c.from_list = st > 0;
         b.c.pending_in = st > 0 ? h->pending.p + (size_t)(st - 1) * m.c.n_chains : nullptr;
         b.c.pending_in_n = st > 0 ? h->ctl.p + st : nullptr;

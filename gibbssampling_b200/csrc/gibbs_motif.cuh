@@ -477,8 +477,9 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
     int sweeps_in_phase = 0;
     bool resumed = false, paused = false;
     if (a.from_list) {
-        const int r = a.resume[chain];
-        phase = r & 255;
+        const int r = a.resume[chain]; // phase | capped so far << 7 | sweeps in phase << 8
+        phase = r & 127;
+        capped = (r >> 7) & 1;
         sweeps_in_phase = r >> 8;
         resumed = true;
     }
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
         }
         // sweep boundary: when few restarts are still running, hand this one over to the wide-team launch
         if (phase != MPH_DONE && a.pause_below > 0) {
-            if (tid == 0) S.flags[2 * T] = (*(volatile int32_t *)a.active <= a.pause_below) ? 1 : 0;
+            if (tid == 0) S.flags[2 * T] = (*(volatile int32_t *)a.active <= a.pause_below && st_sweeps >= a.pause_min_sweeps) ? 1 : 0;
             team_sync<T>();
             if (S.flags[2 * T]) {
                 paused = true;
@@ -756,9 +757,9 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
     }
     if (tid == 0) {
         atomicAdd(a.stats + ST_SWEEPS, (unsigned long long)st_sweeps);
-        atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped);
+        if (!paused) atomicAdd(a.stats + ST_CAPPED, (unsigned long long)capped); // (a restart counts once, where it ends)
         if (paused) {
-            a.resume[chain] = phase | (sweeps_in_phase << 8);
+            a.resume[chain] = phase | (capped << 7) | (sweeps_in_phase << 8);
             a.pending_out[atomicAdd(a.pending_out_n, 1)] = chain;
         } else {
             double sum = 0.0;

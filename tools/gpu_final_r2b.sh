@@ -13,6 +13,8 @@ timeout 900 python bench.py --config C3 --steps 3 --warmup 2 --no-cpu --no-famil
 timeout 900 python bench.py --config C4 --steps 2 --warmup 1 --no-cpu --no-families > gpurun_out/f_bench_C4.json 2> gpurun_out/f_bench_C4.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/f_launches_c2.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-families > gpurun_out/f_ncu_launches.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/f_launches_C4.csv python bench.py --config C4 --steps 1 --warmup 1 --no-cpu --no-families > gpurun_out/f_ncu_launches_C4.log 2>&1
+timeout 1500 ncu --set full --clock-control none -k regex:"chain|init_smem" -c 7 -o /tmp/prof_step -f python tools/prof_probe.py 1024 0 > gpurun_out/f_ncu_step.log 2>&1
+ncu -i /tmp/prof_step.ncu-rep --page raw --csv > gpurun_out/f_step_raw.csv 2>/dev/null
 timeout 900 ncu --set full --clock-control none -k regex:init_tiled -c 1 -o /tmp/prof_tiled -f python tools/prof_init.py 20000 200 20 2 > gpurun_out/f_ncu_tiled.log 2>&1
 ncu -i /tmp/prof_tiled.ncu-rep --page raw --csv > gpurun_out/f_tiled_raw.csv 2>/dev/null
 ncu -i /tmp/prof_tiled.ncu-rep --page source --csv --print-source sass > gpurun_out/f_tiled_sass.csv 2>/dev/null
