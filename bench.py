@@ -40,8 +40,8 @@ CONFIGS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one C2 step (ncu --set full, round 2, final build):
 # init_smem_kernel, chain_kernel T = 1 / 4 / 8 / 16, chain_cluster_kernel 4 / 8 (read, write in MB each)
-NCU_DRAM_BYTES_PER_STEP = int((0.224256 + 0.0 + 12.561664 + 0.0 + 12.574208 + 1.434112 + 3.177472 + 0.000256 + 1.545728 + 0.0
-                               + 0.502016 + 0.0 + 0.429824 + 0.0) * 1e6)
+NCU_DRAM_BYTES_PER_STEP = int((0.224000 + 0.0 + 12.561920 + 0.000256 + 12.574208 + 1.253120 + 6.464000 + 0.000256 + 1.509120
+                               + 0.000256 + 0.552192 + 0.0 + 0.465664 + 0.0) * 1e6)
 NCU_DRAM_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one C2 step (init_smem_kernel, "
                    "chain_kernel T=1/4/8/16, chain_cluster_kernel 4/8), profiles/r02_ncu_c2_step_summary.txt")
 # --family: which reference family the step runs (the default is the BASELINE.json workload)

@@ -125,7 +125,7 @@ int32_t gibbs_destroy(gibbs_handle *h);
 int32_t gibbs_set_stream(gibbs_handle *h, void *cuda_stream);
 int32_t gibbs_num_sequences(const gibbs_handle *h);
 /* tuning knob: warps per chain, 1 / 4 / 8 / 16. 0 = automatic: 4 warps while many chains run, the last
- * 2 (1) chains per SM are handed over to launches with 8 (16) warps per chain */
+ * 4 (1) chains per SM are handed over to launches with 8 (16) warps per chain */
 int32_t gibbs_set_team_warps(gibbs_handle *h, int32_t warps);
 int32_t gibbs_synchronize(gibbs_handle *h);
 /*
@@ -137,8 +137,9 @@ int32_t gibbs_synchronize(gibbs_handle *h);
  *                          _TILED = grid-wide kernel streaming the packed set through shared memory in tiles (large sets)
  *   GIBBS_OPT_EXACT_SCANS  1 = no ranking pass anywhere: every window in float64, sequential roulette walk
  *   GIBBS_OPT_STAGE2_AT / GIBBS_OPT_STAGE3_AT  straggler hand-over of the SiteSampler chain kernel: once this many chains
- *                          per SM (or fewer) are still running they continue with 8 / 16 warps per chain (defaults 2, 1)
- *   GIBBS_OPT_MIN_WIDTH    narrowest speculative round of the greedy sweeps while chains share an SM (default 1; once a
+ *                          per SM (or fewer) are still running they continue with 8 / 16 warps per chain (defaults 4, 1)
+ *   GIBBS_OPT_MIN_WIDTH    narrowest speculative round of the greedy sweeps while chains share an SM (default: the team size when
+ *                          the first sweep runs on its own one-warp stage, else 1; once a
  *                          chain has an SM or a cluster to itself its rounds always use the whole team)
  *   GIBBS_OPT_CLUSTER      largest thread-block cluster the last stages may give one chain: 8 (default), 4 or 0 (none)
  *   GIBBS_OPT_SEQ_SWEEPS   how many of a restart's first sweeps run with one warp per chain before the team stages take over

@@ -16,8 +16,9 @@ pytestmark = pytest.mark.gpu
 
 
 def _many_chains():
-    """enough chains that the first team stage shares SMs (more than 2 per SM): 148 SMs on a B200"""
-    return 2 * 148 + 40
+    """enough chains that the first team stage is the four-warp one (more than GIBBS_OPT_STAGE2_AT = 4 chains per SM):
+    148 SMs on a B200"""
+    return 4 * 148 + 40
 
 
 @pytest.mark.parametrize("n,L,Lmin,k", [(70, 120, 90, 9), (64, 300, None, 12), (130, 90, None, 20)])
