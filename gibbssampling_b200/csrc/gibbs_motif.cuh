@@ -10,6 +10,9 @@
 #include "gibbs_kernels.cuh"
 #include "gibbs_drift.cuh"
 
+#ifndef GIBBS_MOTIF_NARROW_SWEEPS
+#define GIBBS_MOTIF_NARROW_SWEEPS 1 // greedy sweeps whose speculative rounds may narrow after a discard (C2: 0 / 1 / 2 / 3 / all = 28.4 / 26.6 / 26.8 / 27.1 / 29.0 ms per step)
+#endif
 namespace gibbs {
 
 enum MotifPhase { MPH_INIT = 0, MPH_STOCH = 1, MPH_GREEDY = 2, MPH_DONE = 3 };
@@ -508,7 +511,11 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
         }
         bool changed = false;
         int n0 = 0;
-        int width = (phase == MPH_GREEDY) ? 1 : T; // greedy: speculation width adapts as in chain_kernel
+        // greedy: speculation width adapts as in chain_kernel. The first GIBBS_MOTIF_NARROW_SWEEPS greedy sweeps move a site in
+        // most updates: their rounds start at width 1 and narrow after a discard. Later sweeps never narrow: they discard
+        // little, and a round that stays wide costs the other restarts of the SM less than it gains.
+        const int min_w = (phase == MPH_GREEDY && sweeps_in_phase < GIBBS_MOTIF_NARROW_SWEEPS) ? 1 : T;
+        int width = (phase == MPH_GREEDY) ? min_w : T;
         unsigned round = 0;
         while (n0 < N) {
             const int n = n0 + warp;
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(32 * T, (T == 1 ? 8 : T == 4 ? GIBBS_MOTIF_T4_
                         }
                     }
                     team_sync<T>(); // counts updated before the next round builds its tables
-                    width = max(1, width >> 1);
+                    width = max(min_w, width >> 1);
                 } else {
                     width = min(T, width * 2);
                 }
